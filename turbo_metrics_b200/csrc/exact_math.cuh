@@ -1,0 +1,180 @@
+// exact_math.cuh -- bit-exact restatements of the two libm routines the reference's CPU path calls.
+//
+// Why this exists.  SSIMULACRA2's sigma=1.5 recursive Gaussian has its poles ON the unit circle, so
+// f32 round-off never decays along a scan line: the SSIM' map in flat regions (denominator ~ C2 =
+// 9e-4) is dominated by that round-off pattern, and the pattern is a chaotic function of every input
+// bit.  Measured with the CPU oracle: flipping ONE ulp in 100 of 1.5M XYB inputs moves some of the
+// 108 norms by 1e-3 relative, flipping them all moves the small-scale SSIM norms by 5-10 % and the
+// score by up to 0.02.  The parity bar (norms 1e-4 relative, score 0.01) is therefore only reachable
+// if the inputs of the filters are BIT-IDENTICAL to the CPU reference's, which means reproducing
+// its cbrtf (Rust f32::cbrt -> libm cbrtf, cpu.rs:462-464) and powf exactly, not "accurately".
+//
+// Both routines below follow glibc 2.39 x86-64 (the libm of this image, Ubuntu 24.04), read from
+// its disassembly and cross-checked bit-for-bit on the host by tests/test_exact_math.py:
+//   cbrtf : sysdeps/ieee754/flt-32/s_cbrtf.c (polynomial seed in double -> float, one Halley step in
+//           double, no FMA contraction)
+//   powf  : sysdeps/ieee754/flt-32/e_powf.c, the FMA ifunc variant (__powf_fma; every a*b+c is fused),
+//           tables __powf_log2_data / __exp2f_data
+// They compile for the device (IEEE f64 add/mul/fma/div, compile with -fmad=false) and for the host
+// (tests only).  Inputs outside the fast path (zero, subnormal, inf, nan, negative base, overflow) fall
+// back to the platform routine; the pipeline never produces them from in-range frames.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define EM_HD __host__ __device__ __forceinline__
+#else
+#define EM_HD inline
+#endif
+
+namespace exact_math {
+
+struct PowfTables {
+    double log2_tab[16][2];  // {invc, logc}
+    uint64_t exp2_tab[32];
+};
+
+// __powf_log2_data.tab, __exp2f_data.tab (glibc 2.39)
+#define EM_POWF_LOG2_TAB                                                                             \
+    {0x1.661ec79f8f3bep+0, -0x1.efec65b963019p-2}, {0x1.571ed4aaf883dp+0, -0x1.b0b6832d4fca4p-2},    \
+    {0x1.49539f0f010b0p+0, -0x1.7418b0a1fb77bp-2}, {0x1.3c995b0b80385p+0, -0x1.39de91a6dcf7bp-2},    \
+    {0x1.30d190c8864a5p+0, -0x1.01d9bf3f2b631p-2}, {0x1.25e227b0b8ea0p+0, -0x1.97c1d1b3b7af0p-3},    \
+    {0x1.1bb4a4a1a343fp+0, -0x1.2f9e393af3c9fp-3}, {0x1.12358f08ae5bap+0, -0x1.960cbbf788d5cp-4},    \
+    {0x1.0953f419900a7p+0, -0x1.a6f9db6475fcep-5}, {0x1.0000000000000p+0, 0x0.0p+0},                 \
+    {0x1.e608cfd9a47acp-1, 0x1.338ca9f24f53dp-4},  {0x1.ca4b31f026aa0p-1, 0x1.476a9543891bap-3},     \
+    {0x1.b2036576afce6p-1, 0x1.e840b4ac4e4d2p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.40645f0c6651cp-2},     \
+    {0x1.886e6037841edp-1, 0x1.88e9c2c1b9ff8p-2},  {0x1.767dcf5534862p-1, 0x1.ce0a44eb17bccp-2}
+#define EM_EXP2F_TAB                                                                                   \
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,        \
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,        \
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,        \
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,        \
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,        \
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,        \
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,        \
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull
+
+EM_HD uint32_t f2u(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+EM_HD float u2f(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+EM_HD uint64_t d2u(double d)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(d);
+#else
+    uint64_t u; memcpy(&u, &d, 8); return u;
+#endif
+}
+EM_HD double u2d(uint64_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double d; memcpy(&d, &u, 8); return d;
+#endif
+}
+
+// glibc 2.39 cbrtf.  Bit-exact for every finite x; zero / inf / nan return x + x like glibc;
+// subnormals take the platform cbrtf (never produced by the pipeline: the opsin bias keeps the
+// argument >= 0.0037).
+EM_HD float cbrtf_glibc(float x)
+{
+    const uint32_t ix = f2u(x) & 0x7fffffffu;
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+        if (ix == 0 || ix >= 0x7f800000u) return x + x;
+        return ::cbrtf(x);
+    }
+    // frexpf: |x| = xm * 2^e, xm in [0.5, 1)
+    const int e = (int)(ix >> 23) - 126;
+    const double xm = (double)u2f((ix & 0x007fffffu) | 0x3f000000u);
+    // u = 0.4926... + (0.6975... - 0.1915... * xm) * xm   (mulsd, subsd, mulsd, addsd; then cvtsd2ss)
+    double t = 0x1.8832490c2feddp-3 * xm;
+    t = 0x1.6527f4927f555p-1 - t;
+    t = t * xm;
+    t = t + 0x1.f87bc378ed415p-2;
+    const float u = (float)t;
+    const float t2 = (u * u) * u;
+    const double t2d = (double)t2, ud = (double)u;
+    // ym = u * (t2 + 2.0 * xm) / (2.0 * t2 + xm) * factor[2 + e % 3]
+    double num = (xm + xm) + t2d;
+    num = num * ud;
+    const double den = (t2d + t2d) + xm;
+    const int q3 = e / 3, r3 = e - 3 * q3;  // C semantics: truncation toward zero
+    double f;
+    switch (r3) {
+    case -2: f = 0x1.428a2f98d728ap-1; break;   // 1 / 2^(2/3)
+    case -1: f = 0x1.965fea53d6e3cp-1; break;   // 1 / 2^(1/3)
+    case 0: f = 1.0; break;
+    case 1: f = 0x1.428a2f98d728bp+0; break;    // 2^(1/3)
+    default: f = 0x1.965fea53d6e3dp+0; break;   // 2^(2/3)
+    }
+    const float ym = (float)((num / den) * f);
+    // ldexpf(+-ym, e / 3): exact scaling by a power of two (no subnormal results for normal inputs)
+    const float scale = u2f((uint32_t)(127 + q3) << 23);
+    const float r = ym * scale;
+    return (f2u(x) >> 31) ? -r : r;
+}
+
+// glibc 2.39 powf (FMA variant) for x > 0 normal and finite nonzero y; anything else, and results
+// that would leave the normal float range, go to the platform powf.
+EM_HD float powf_glibc(float x, float y, const PowfTables& T)
+{
+    const uint32_t ix = f2u(x), iy = f2u(y);
+    const bool x_special = ix - 0x00800000u >= 0x7f800000u - 0x00800000u;
+    const bool y_special = 2u * iy - 1u >= 2u * 0x7f800000u - 1u;
+    if (x_special || y_special) return ::powf(x, y);
+    // log2_inline
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (int)((tmp >> 19) & 15u);
+    const uint32_t top = tmp & 0xff800000u;
+    const uint32_t iz = ix - top;
+    const int k = (int32_t)top >> 23;
+    const double invc = T.log2_tab[i][0], logc = T.log2_tab[i][1];
+    const double z = (double)u2f(iz);
+    const double r = fma(z, invc, -1.0);
+    const double y0 = logc + (double)k;
+    const double A0 = 0x1.27616c9496e0bp-2, A1 = -0x1.71969a075c67ap-2, A2 = 0x1.ec70a6ca7baddp-2,
+                 A3 = -0x1.7154748bef6c8p-1, A4 = 0x1.71547652ab82bp+0;
+    const double r2 = r * r;
+    double yy = fma(A0, r, A1);
+    const double p = fma(A2, r, A3);
+    const double r4 = r2 * r2;
+    double q = fma(A4, r, y0);
+    q = fma(p, r2, q);
+    yy = fma(yy, r4, q);
+    const double ylogx = (double)y * yy;
+    if (((d2u(ylogx) >> 47) & 0xffffu) >= (0x405F800000000000ull >> 47)) return ::powf(x, y);  // |y log2 x| >= 126
+    // exp2_inline (sign_bias = 0)
+    const double SHIFT = 0x1.8p+47;
+    double kd = ylogx + SHIFT;
+    const uint64_t ki = d2u(kd);
+    kd = kd - SHIFT;
+    const double rr = ylogx - kd;
+    uint64_t tt = T.exp2_tab[ki & 31u];
+    tt += ki << 47;
+    const double s = u2d(tt);
+    const double C0 = 0x1.c6af84b912394p-5, C1 = 0x1.ebfce50fac4f3p-3, C2 = 0x1.62e42ff0c52d6p-1;
+    const double zz = fma(C0, rr, C1);
+    const double rr2 = rr * rr;
+    double w = fma(C2, rr, 1.0);
+    w = fma(zz, rr2, w);
+    w = w * s;
+    return (float)w;
+}
+
+}  // namespace exact_math

@@ -1,0 +1,630 @@
+// ssimu2_api.cu -- host side of libssimu2_b200.so: the C ABI declared in include/ssimu2_b200.h.
+//
+// Mirrors the reference's metric op (crates/ssimulacra2-cuda/src/lib.rs:27-291) and the per-pair
+// driver that calls it (crates/turbo-metrics/src/lib.rs:268-360), re-designed for throughput:
+//   * a handle owns `ring` batch slots; each slot has its own stream, workspace and result buffers;
+//   * pairs are collected into batches of `batch` and every batch is 4 kernel launches that cover
+//     all frames and all 6 scales (the reference records a 305-node graph per pair and syncs the
+//     host after every pair, lib.rs:342-352);
+//   * only the f64 scores (and, for parity tests, the 108 norms) travel back to the host.
+// There is no CPU fallback: without a usable CUDA device every call fails.
+#include "../../include/ssimu2_b200.h"
+#include "ssimu2_kernels.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace ssimu2;
+
+namespace {
+
+constexpr uint64_t kResultCap = 16384;  // tickets kept in the host/device result rings
+constexpr uint32_t kDefaultBatch = 8;
+constexpr uint32_t kDefaultRing = 3;
+
+#define CU_TRY(expr)                                 \
+    do {                                             \
+        cudaError_t _e = (expr);                     \
+        if (_e != cudaSuccess) return (int)_e;       \
+    } while (0)
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_in = nullptr;      // dependency on the submitter's stream
+    cudaEvent_t ev_done = nullptr;    // batch complete (results on host)
+    cudaEvent_t ev_k[5] = {};         // per-kernel timing marks
+    float* lin = nullptr;             // [batch] pyramids
+    float* hb = nullptr;              // [batch] H-pass planes
+    double* partials = nullptr;       // [batch][total_strips][18]
+    double* norms_d = nullptr;        // [batch][108]
+    double* scores_d = nullptr;       // [batch]
+    double* norms_h = nullptr;        // pinned
+    double* scores_h = nullptr;       // pinned
+    uint8_t* staging = nullptr;       // device staging for host frames: [batch][2][staging_frame_bytes]
+    BatchIn in{};
+    uint32_t count = 0;               // pairs recorded
+    uint64_t first_ticket = 0;
+    bool inflight = false;            // launched, results not harvested yet
+    bool timed = false;
+    void* last_stream = nullptr;
+    bool have_dep = false;
+};
+
+}  // namespace
+
+struct ssimu2_handle {
+    ssimu2_config cfg{};
+    Geo geo{};
+    uint32_t batch = 0, ring = 0;
+    std::vector<Slot> slots;
+    uint32_t cur = 0;
+    uint64_t next_ticket = 0;
+    double* scores_ring_d = nullptr;  // [kResultCap] device score stream
+    std::vector<double> res_scores;   // host result ring
+    std::vector<double> res_norms;    // [kResultCap][108]
+    std::vector<int32_t> res_slot;    // slot that served the ticket (for debug_read)
+    size_t device_bytes = 0;
+    size_t staging_frame_bytes = 0;
+    uint64_t launches = 0;
+    float last_ms[4] = {0, 0, 0, 0};
+    uint64_t alg_bytes = 0;
+};
+
+namespace {
+
+// ---- colour coefficients (host, f32 arithmetic as in cuda-colorspace-kernel/src/lib.rs:183-218) ----
+struct V3 { float x, y, z; };
+static V3 xyz_of(float x, float y) { return V3{x / y, 1.0f, (1.0f - x - y) / y}; }
+static float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static V3 cross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+static void luma_constants(int matrix, float& kr, float& kb)
+{
+    // primaries: constants.rs:3-18
+    float p[3][6] = {{0.640f, 0.330f, 0.300f, 0.600f, 0.150f, 0.060f},
+                     {0.630f, 0.340f, 0.310f, 0.595f, 0.155f, 0.070f},
+                     {0.640f, 0.330f, 0.290f, 0.600f, 0.150f, 0.060f}};
+    const float* m = p[matrix];
+    V3 r = xyz_of(m[0], m[1]), g = xyz_of(m[2], m[3]), b = xyz_of(m[4], m[5]), w = xyz_of(0.3127f, 0.3290f);
+    V3 xr{r.x, g.x, b.x}, yr{r.y, g.y, b.y}, zr{r.z, g.z, b.z};
+    float mul = 1.0f / dot(xr, cross(yr, zr));
+    kr = dot(w, cross(g, b)) * mul;
+    kb = dot(w, cross(r, g)) * mul;
+}
+
+static YuvCoef make_coef(int fmt, int matrix, int full_range)
+{
+    YuvCoef c{};
+    if (fmt != kNV12 && fmt != kP016) return c;
+    int bits = fmt == kNV12 ? 8 : 16;
+    float kr, kb;
+    luma_constants(matrix, kr, kb);
+    uint32_t lmin, lrange, crange;
+    if (full_range) {
+        lmin = 0; lrange = (1u << bits) - 1; crange = (1u << bits) - 1;
+    } else {
+        lmin = 16u << (bits - 8);
+        lrange = (235u << (bits - 8)) - lmin;
+        crange = (240u << (bits - 8)) - lmin;
+    }
+    float kg = 1.0f - kr - kb;
+    c.y = 1.0f / (float)lrange;
+    c.r = 2.0f * (1.0f - kr) * 1.0f / (float)crange;
+    c.b = 2.0f * (1.0f - kb) * 1.0f / (float)crange;
+    c.g1 = -2.0f * (1.0f - kb) * kb / kg * 1.0f / (float)crange;
+    c.g2 = -2.0f * (1.0f - kr) * kr / kg * 1.0f / (float)crange;
+    c.luma_min = (int)lmin;
+    c.neutral = 1 << (bits - 1);
+    return c;
+}
+
+static int in_bytes_per_px(int fmt)
+{
+    switch (fmt) {
+    case kNV12: return 3;       // 1.5 B x 2 images
+    case kP016: return 6;
+    case kSRGB8: return 6;
+    case kSRGB16: return 12;
+    default: return 24;
+    }
+}
+
+static void build_geo(ssimu2_handle* h)
+{
+    Geo& g = h->geo;
+    int w = (int)h->cfg.width, hh = (int)h->cfg.height;
+    long long lin_off = 0, hb_off = 0;
+    int strips = 0, ns = 0;
+    unsigned long long sum_px = 0, sum_px_ge1 = 0;
+    for (int s = 0; s < kMaxScales; s++) {
+        if (w < 8 || hh < 8) break;  // cpu.rs:359
+        ScaleDesc& d = g.sc[s];
+        d.w = w; d.h = hh;
+        d.pitch = (w + 31) / 32 * 32;
+        d.n_bands = (hh + kHRows - 1) / kHRows;
+        d.n_strips = (w + kVCols - 1) / kVCols;
+        d.strip0 = strips;
+        strips += d.n_strips;
+        d.lin_off = lin_off;
+        if (s >= 1) lin_off += 6LL * hh * d.pitch;
+        d.hb_off = hb_off;
+        hb_off += 15LL * hh * d.pitch;
+        sum_px += (unsigned long long)w * hh;
+        if (s >= 1) sum_px_ge1 += (unsigned long long)w * hh;
+        ns++;
+        w = (w + 1) / 2; hh = (hh + 1) / 2;
+    }
+    g.nscales = ns;
+    g.total_strips = strips;
+    g.lin_stride = lin_off > 0 ? lin_off : 32;
+    g.hb_stride = hb_off;
+    g.items_h = 0; g.items_v = 0;
+    for (int s = 0; s < ns; s++) { g.items_h += g.sc[s].n_bands; g.items_v += g.sc[s].n_strips; }
+    g.coef = make_coef(h->cfg.format, h->cfg.matrix, h->cfg.full_range);
+    // B_alg = 120*sum(P_s) + 2*in_0*P_0 + 72*sum_{s>=1}(P_s)
+    h->alg_bytes = 120ULL * sum_px + 2ULL * in_bytes_per_px(h->cfg.format) * h->cfg.width * h->cfg.height + 72ULL * sum_px_ge1;
+}
+
+template <int FMT>
+static int launch_batch_fmt(ssimu2_handle* h, Slot& sl)
+{
+    const Geo& g = h->geo;
+    const uint32_t n = sl.count;
+    cudaStream_t st = sl.stream;
+    if (sl.timed) cudaEventRecord(sl.ev_k[0], st);
+    if (g.nscales > 1) {
+        dim3 grid((g.sc[0].w + 63) / 64, (g.sc[0].h + 63) / 64, n);
+        k_pyramid<FMT><<<grid, 256, 0, st>>>(g, sl.in, sl.lin);
+        h->launches++;
+    }
+    if (sl.timed) cudaEventRecord(sl.ev_k[1], st);
+    k_hpass<FMT><<<dim3(g.items_h, n), kHThreads, kHSmemBytes, st>>>(g, sl.in, sl.lin, sl.hb);
+    if (sl.timed) cudaEventRecord(sl.ev_k[2], st);
+    k_vpass<FMT><<<dim3(g.items_v, n), kVThreads, 0, st>>>(g, sl.in, sl.lin, sl.hb, sl.partials);
+    if (sl.timed) cudaEventRecord(sl.ev_k[3], st);
+    k_finalize<<<n, 128, 0, st>>>(g, sl.partials, sl.norms_d, h->scores_ring_d, sl.first_ticket, kResultCap, sl.scores_d);
+    if (sl.timed) cudaEventRecord(sl.ev_k[4], st);
+    h->launches += 3;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(sl.scores_h, sl.scores_d, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(sl.norms_h, sl.norms_d, (size_t)n * 108 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventRecord(sl.ev_done, st));
+    sl.inflight = true;
+    return 0;
+}
+
+static int launch_batch(ssimu2_handle* h, Slot& sl)
+{
+    if (sl.count == 0) return 0;
+    if (sl.have_dep && sl.last_stream != (void*)sl.stream) {
+        // order the batch after everything the submitter enqueued so far on its stream
+        CU_TRY(cudaEventRecord(sl.ev_in, (cudaStream_t)sl.last_stream));
+        CU_TRY(cudaStreamWaitEvent(sl.stream, sl.ev_in, 0));
+    }
+    sl.have_dep = false;
+    switch (h->cfg.format) {
+    case kNV12: return launch_batch_fmt<kNV12>(h, sl);
+    case kP016: return launch_batch_fmt<kP016>(h, sl);
+    case kSRGB8: return launch_batch_fmt<kSRGB8>(h, sl);
+    case kSRGB16: return launch_batch_fmt<kSRGB16>(h, sl);
+    case kSRGBF32: return launch_batch_fmt<kSRGBF32>(h, sl);
+    case kLINEARF32: return launch_batch_fmt<kLINEARF32>(h, sl);
+    }
+    return SSIMU2_E_UNSUPPORTED;
+}
+
+// wait for a launched slot and move its results into the ticket-indexed host rings
+static int harvest(ssimu2_handle* h, uint32_t si)
+{
+    Slot& sl = h->slots[si];
+    if (!sl.inflight) return 0;
+    CU_TRY(cudaEventSynchronize(sl.ev_done));
+    for (uint32_t i = 0; i < sl.count; i++) {
+        uint64_t t = sl.first_ticket + i, r = t % kResultCap;
+        h->res_scores[r] = sl.scores_h[i];
+        memcpy(&h->res_norms[r * 108], &sl.norms_h[(size_t)i * 108], 108 * sizeof(double));
+        h->res_slot[r] = (int32_t)si;
+    }
+    if (sl.timed) {
+        for (int k = 0; k < 4; k++) cudaEventElapsedTime(&h->last_ms[k], sl.ev_k[k], sl.ev_k[k + 1]);
+    }
+    sl.inflight = false;
+    sl.count = 0;
+    return 0;
+}
+
+static int set_device(const ssimu2_handle* h) { return (int)cudaSetDevice(h->cfg.device); }
+
+// make slot `cur` ready to record a pair
+static int prepare_cur(ssimu2_handle* h)
+{
+    Slot& sl = h->slots[h->cur];
+    if (sl.inflight) {
+        int r = harvest(h, h->cur);
+        if (r) return r;
+    }
+    if (sl.count == 0) {
+        sl.first_ticket = h->next_ticket;
+        sl.in.first_ticket = h->next_ticket;
+        sl.have_dep = false;
+        sl.last_stream = nullptr;
+    }
+    return 0;
+}
+
+static int finish_pair(ssimu2_handle* h)
+{
+    Slot& sl = h->slots[h->cur];
+    sl.count++;
+    h->next_ticket++;
+    if (sl.count == h->batch) {
+        int r = launch_batch(h, sl);
+        if (r) return r;
+        h->cur = (h->cur + 1) % h->ring;
+    }
+    return 0;
+}
+
+static bool frame_ok(const ssimu2_handle* h, const ssimu2_frame* f)
+{
+    if (!f || !f->plane[0] || f->pitch == 0) return false;
+    if ((h->cfg.format == kNV12 || h->cfg.format == kP016) && !f->plane[1]) return false;
+    return true;
+}
+
+// locate a ticket: 0 = results on host, 1 = in a launched slot, 2 = in the slot being filled
+static int locate(ssimu2_handle* h, uint64_t ticket, uint32_t* slot_out)
+{
+    if (ticket >= h->next_ticket) return -1;
+    if (h->next_ticket - ticket > kResultCap) return -1;
+    for (uint32_t i = 0; i < h->ring; i++) {
+        Slot& sl = h->slots[i];
+        if (sl.count && ticket >= sl.first_ticket && ticket < sl.first_ticket + sl.count) {
+            *slot_out = i;
+            return sl.inflight ? 1 : 2;
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t ssimu2_version(void) { return (1u << 16) | 0u; }
+
+const char* ssimu2_strerror(int status)
+{
+    switch (status) {
+    case SSIMU2_OK: return "ok";
+    case SSIMU2_E_INVALID: return "invalid argument";
+    case SSIMU2_E_UNSUPPORTED: return "unsupported format or size";
+    case SSIMU2_E_NOMEM: return "out of memory";
+    case SSIMU2_E_NODEVICE: return "no usable CUDA device (sm_100 required)";
+    case SSIMU2_E_TICKET: return "unknown or expired ticket";
+    case SSIMU2_E_INTERNAL: return "internal error";
+    }
+    if (status > 0) return cudaGetErrorString((cudaError_t)status);
+    return "unknown status";
+}
+
+int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
+{
+    if (!out || !cfg) return SSIMU2_E_INVALID;
+    *out = nullptr;
+    if (cfg->width < 8 || cfg->height < 8 || cfg->width > 32768 || cfg->height > 32768) return SSIMU2_E_UNSUPPORTED;
+    if (cfg->format < 0 || cfg->format > kLINEARF32) return SSIMU2_E_UNSUPPORTED;
+    if (cfg->matrix < 0 || cfg->matrix > 2) return SSIMU2_E_UNSUPPORTED;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return SSIMU2_E_NODEVICE;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return SSIMU2_E_INVALID;
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return SSIMU2_E_NODEVICE;  // the only SASS in this library is sm_100a
+
+    ssimu2_handle* h = new (std::nothrow) ssimu2_handle();
+    if (!h) return SSIMU2_E_NOMEM;
+    h->cfg = *cfg;
+    h->batch = cfg->batch ? cfg->batch : kDefaultBatch;
+    if (h->batch > (uint32_t)kMaxBatch) h->batch = kMaxBatch;
+    h->ring = cfg->ring ? cfg->ring : kDefaultRing;
+    if (h->ring > 16) h->ring = 16;
+    build_geo(h);
+    int rc = 0;
+#define CR(expr)                                  \
+    do {                                          \
+        cudaError_t _e = (expr);                  \
+        if (_e != cudaSuccess) {                  \
+            rc = (_e == cudaErrorMemoryAllocation) ? SSIMU2_E_NOMEM : (int)_e; \
+            goto fail;                            \
+        }                                         \
+    } while (0)
+    CR(cudaSetDevice(cfg->device));
+    try {
+        h->slots.resize(h->ring);
+        h->res_scores.assign(kResultCap, 0.0);
+        h->res_norms.assign(kResultCap * 108, 0.0);
+        h->res_slot.assign(kResultCap, -1);
+    } catch (...) {
+        rc = SSIMU2_E_NOMEM;
+        goto fail;
+    }
+    CR(cudaMalloc(&h->scores_ring_d, kResultCap * sizeof(double)));
+    CR(cudaMemset(h->scores_ring_d, 0, kResultCap * sizeof(double)));
+    h->device_bytes += kResultCap * sizeof(double);
+    {
+        static const void* hfn[6] = {(const void*)k_hpass<kNV12>,   (const void*)k_hpass<kP016>,
+                                     (const void*)k_hpass<kSRGB8>,  (const void*)k_hpass<kSRGB16>,
+                                     (const void*)k_hpass<kSRGBF32>, (const void*)k_hpass<kLINEARF32>};
+        CR(cudaFuncSetAttribute(hfn[cfg->format], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBytes));
+    }
+    for (uint32_t i = 0; i < h->ring; i++) {
+        Slot& sl = h->slots[i];
+        const Geo& g = h->geo;
+        size_t lin_b = (size_t)g.lin_stride * h->batch * sizeof(float);
+        size_t hb_b = (size_t)g.hb_stride * h->batch * sizeof(float);
+        size_t part_b = (size_t)g.total_strips * 18 * h->batch * sizeof(double);
+        CR(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        CR(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+        CR(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+        for (int k = 0; k < 5; k++) CR(cudaEventCreate(&sl.ev_k[k]));
+        CR(cudaMalloc(&sl.lin, lin_b));
+        CR(cudaMalloc(&sl.hb, hb_b));
+        CR(cudaMalloc(&sl.partials, part_b));
+        CR(cudaMalloc(&sl.norms_d, (size_t)h->batch * 108 * sizeof(double)));
+        CR(cudaMalloc(&sl.scores_d, (size_t)h->batch * sizeof(double)));
+        CR(cudaMallocHost(&sl.norms_h, (size_t)h->batch * 108 * sizeof(double)));
+        CR(cudaMallocHost(&sl.scores_h, (size_t)h->batch * sizeof(double)));
+        h->device_bytes += lin_b + hb_b + part_b + (size_t)h->batch * 109 * sizeof(double);
+        sl.timed = getenv("SSIMU2_NO_TIMING") == nullptr;
+    }
+    *out = h;
+    return SSIMU2_OK;
+fail:
+    ssimu2_destroy(h);
+    return rc;
+#undef CR
+}
+
+int ssimu2_destroy(ssimu2_t* h)
+{
+    if (!h) return SSIMU2_OK;
+    cudaSetDevice(h->cfg.device);
+    for (auto& sl : h->slots) {
+        if (sl.stream) cudaStreamSynchronize(sl.stream);
+        if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+        for (int k = 0; k < 5; k++)
+            if (sl.ev_k[k]) cudaEventDestroy(sl.ev_k[k]);
+        cudaFree(sl.lin); cudaFree(sl.hb); cudaFree(sl.partials); cudaFree(sl.norms_d); cudaFree(sl.scores_d);
+        cudaFree(sl.staging);
+        if (sl.norms_h) cudaFreeHost(sl.norms_h);
+        if (sl.scores_h) cudaFreeHost(sl.scores_h);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
+    cudaFree(h->scores_ring_d);
+    delete h;
+    return SSIMU2_OK;
+}
+
+int ssimu2_mem_usage(const ssimu2_t* h, size_t* bytes)
+{
+    if (!h || !bytes) return SSIMU2_E_INVALID;
+    *bytes = h->device_bytes;
+    return SSIMU2_OK;
+}
+
+int ssimu2_submit(ssimu2_t* h, const ssimu2_frame* ref, const ssimu2_frame* dis, void* stream, uint64_t* ticket)
+{
+    if (!h || !frame_ok(h, ref) || !frame_ok(h, dis)) return SSIMU2_E_INVALID;
+    CU_TRY(cudaSetDevice(h->cfg.device));
+    int r = prepare_cur(h);
+    if (r) return r;
+    Slot& sl = h->slots[h->cur];
+    if (sl.have_dep && sl.last_stream != stream && sl.last_stream != (void*)sl.stream) {
+        // submitter switched streams inside one batch: pin the dependency on the previous one now
+        CU_TRY(cudaEventRecord(sl.ev_in, (cudaStream_t)sl.last_stream));
+        CU_TRY(cudaStreamWaitEvent(sl.stream, sl.ev_in, 0));
+    }
+    sl.last_stream = stream;
+    sl.have_dep = true;
+    FrameIn& a = sl.in.ref[sl.count];
+    FrameIn& b = sl.in.dis[sl.count];
+    a.p0 = (const uint8_t*)ref->plane[0]; a.p1 = (const uint8_t*)ref->plane[1]; a.pitch = ref->pitch; a.pad = 0;
+    b.p0 = (const uint8_t*)dis->plane[0]; b.p1 = (const uint8_t*)dis->plane[1]; b.pitch = dis->pitch; b.pad = 0;
+    if (ticket) *ticket = h->next_ticket;
+    return finish_pair(h);
+}
+
+int ssimu2_submit_batch(ssimu2_t* h, uint32_t n, const ssimu2_frame* refs, const ssimu2_frame* diss, void* stream,
+                        uint64_t* first_ticket)
+{
+    if (!h || (n && (!refs || !diss))) return SSIMU2_E_INVALID;
+    if (first_ticket) *first_ticket = h->next_ticket;
+    for (uint32_t i = 0; i < n; i++) {
+        int r = ssimu2_submit(h, &refs[i], &diss[i], stream, nullptr);
+        if (r) return r;
+    }
+    return SSIMU2_OK;
+}
+
+int ssimu2_submit_host(ssimu2_t* h, const ssimu2_frame* ref, const ssimu2_frame* dis, size_t frame_bytes, uint64_t* ticket)
+{
+    if (!h || !frame_ok(h, ref) || !frame_ok(h, dis) || frame_bytes == 0) return SSIMU2_E_INVALID;
+    const bool yuv = h->cfg.format == kNV12 || h->cfg.format == kP016;
+    if (yuv && (ref->plane[1] <= ref->plane[0] || dis->plane[1] <= dis->plane[0] ||
+                ref->plane[1] - ref->plane[0] >= frame_bytes || dis->plane[1] - dis->plane[0] >= frame_bytes))
+        return SSIMU2_E_INVALID;
+    CU_TRY(cudaSetDevice(h->cfg.device));
+    if (frame_bytes > h->staging_frame_bytes) {
+        // (re)allocate the staging rings; rare (first call), so a full drain is acceptable
+        for (uint32_t i = 0; i < h->ring; i++) {
+            Slot& sl = h->slots[i];
+            if (sl.count && !sl.inflight) { int r = launch_batch(h, sl); if (r) return r; }
+            int r = harvest(h, i);
+            if (r) return r;
+        }
+        size_t fb = (frame_bytes + 255) / 256 * 256;
+        for (auto& sl : h->slots) {
+            cudaFree(sl.staging);
+            sl.staging = nullptr;
+            if (cudaMalloc(&sl.staging, fb * 2 * h->batch) != cudaSuccess) { cudaGetLastError(); return SSIMU2_E_NOMEM; }
+        }
+        h->device_bytes += (fb - h->staging_frame_bytes) * 2 * h->batch * h->ring;
+        h->staging_frame_bytes = fb;
+    }
+    int r = prepare_cur(h);
+    if (r) return r;
+    Slot& sl = h->slots[h->cur];
+    uint8_t* da = sl.staging + (size_t)(2 * sl.count) * h->staging_frame_bytes;
+    uint8_t* db = da + h->staging_frame_bytes;
+    CU_TRY(cudaMemcpyAsync(da, (const void*)ref->plane[0], frame_bytes, cudaMemcpyHostToDevice, sl.stream));
+    CU_TRY(cudaMemcpyAsync(db, (const void*)dis->plane[0], frame_bytes, cudaMemcpyHostToDevice, sl.stream));
+    FrameIn& a = sl.in.ref[sl.count];
+    FrameIn& b = sl.in.dis[sl.count];
+    a.p0 = da; a.p1 = yuv ? da + (ref->plane[1] - ref->plane[0]) : nullptr; a.pitch = ref->pitch; a.pad = 0;
+    b.p0 = db; b.p1 = yuv ? db + (dis->plane[1] - dis->plane[0]) : nullptr; b.pitch = dis->pitch; b.pad = 0;
+    if (ticket) *ticket = h->next_ticket;
+    return finish_pair(h);
+}
+
+int ssimu2_flush(ssimu2_t* h)
+{
+    if (!h) return SSIMU2_E_INVALID;
+    CU_TRY(cudaSetDevice(h->cfg.device));
+    Slot& sl = h->slots[h->cur];
+    if (sl.count && !sl.inflight) {
+        int r = launch_batch(h, sl);
+        if (r) return r;
+        h->cur = (h->cur + 1) % h->ring;
+    }
+    return SSIMU2_OK;
+}
+
+int ssimu2_wait(ssimu2_t* h, uint64_t ticket)
+{
+    if (!h) return SSIMU2_E_INVALID;
+    CU_TRY(cudaSetDevice(h->cfg.device));
+    uint32_t si = 0;
+    int where = locate(h, ticket, &si);
+    if (where < 0) return SSIMU2_E_TICKET;
+    if (where == 2) {
+        int r = ssimu2_flush(h);
+        if (r) return r;
+        where = 1;
+    }
+    if (where == 1) return harvest(h, si);
+    return SSIMU2_OK;
+}
+
+int ssimu2_get_score(ssimu2_t* h, uint64_t ticket, double* score)
+{
+    if (!h || !score) return SSIMU2_E_INVALID;
+    int r = ssimu2_wait(h, ticket);
+    if (r) return r;
+    *score = h->res_scores[ticket % kResultCap];
+    return SSIMU2_OK;
+}
+
+int ssimu2_get_norms(ssimu2_t* h, uint64_t ticket, double* norms108)
+{
+    if (!h || !norms108) return SSIMU2_E_INVALID;
+    int r = ssimu2_wait(h, ticket);
+    if (r) return r;
+    memcpy(norms108, &h->res_norms[(ticket % kResultCap) * 108], 108 * sizeof(double));
+    return SSIMU2_OK;
+}
+
+int ssimu2_compute_sync(ssimu2_t* h, const ssimu2_frame* ref, const ssimu2_frame* dis, void* stream, double* score)
+{
+    uint64_t t = 0;
+    int r = ssimu2_submit(h, ref, dis, stream, &t);
+    if (r) return r;
+    return ssimu2_get_score(h, t, score);
+}
+
+int ssimu2_stream_wait(ssimu2_t* h, uint64_t ticket, void* stream)
+{
+    if (!h) return SSIMU2_E_INVALID;
+    CU_TRY(cudaSetDevice(h->cfg.device));
+    uint32_t si = 0;
+    int where = locate(h, ticket, &si);
+    if (where < 0) return SSIMU2_E_TICKET;
+    if (where == 2) {
+        int r = ssimu2_flush(h);
+        if (r) return r;
+        where = 1;
+    }
+    if (where == 1) CU_TRY(cudaStreamWaitEvent((cudaStream_t)stream, h->slots[si].ev_done, 0));
+    return SSIMU2_OK;
+}
+
+int ssimu2_scores_device(ssimu2_t* h, uint64_t* dptr, uint64_t* capacity)
+{
+    if (!h || !dptr || !capacity) return SSIMU2_E_INVALID;
+    *dptr = (uint64_t)(uintptr_t)h->scores_ring_d;
+    *capacity = kResultCap;
+    return SSIMU2_OK;
+}
+
+int ssimu2_get_info(const ssimu2_t* h, ssimu2_info* info)
+{
+    if (!h || !info) return SSIMU2_E_INVALID;
+    memset(info, 0, sizeof(*info));
+    info->nscales = (uint32_t)h->geo.nscales;
+    for (int s = 0; s < h->geo.nscales; s++) {
+        info->width[s] = (uint32_t)h->geo.sc[s].w;
+        info->height[s] = (uint32_t)h->geo.sc[s].h;
+        info->pitch[s] = (uint32_t)h->geo.sc[s].pitch;
+    }
+    info->batch = h->batch;
+    info->ring = h->ring;
+    info->alg_bytes_per_pair = h->alg_bytes;
+    info->kernel_launches = h->launches;
+    return SSIMU2_OK;
+}
+
+int ssimu2_debug_read(ssimu2_t* h, uint64_t ticket, int what, int scale, float* out, size_t out_floats)
+{
+    if (!h || !out || scale < 0 || scale >= h->geo.nscales) return SSIMU2_E_INVALID;
+    int r = ssimu2_wait(h, ticket);
+    if (r) return r;
+    int si = h->res_slot[ticket % kResultCap];
+    if (si < 0) return SSIMU2_E_TICKET;
+    Slot& sl = h->slots[si];
+    if (ticket < sl.first_ticket) return SSIMU2_E_TICKET;
+    size_t idx = (size_t)(ticket - sl.first_ticket);
+    if (idx >= h->batch) return SSIMU2_E_TICKET;
+    const ScaleDesc& sd = h->geo.sc[scale];
+    int planes;
+    const float* src;
+    if (what == 0) {
+        if (scale < 1) return SSIMU2_E_INVALID;
+        planes = 6;
+        src = sl.lin + idx * h->geo.lin_stride + sd.lin_off;
+    } else if (what == 1) {
+        planes = 15;
+        src = sl.hb + idx * h->geo.hb_stride + sd.hb_off;
+    } else {
+        return SSIMU2_E_INVALID;
+    }
+    if (out_floats < (size_t)planes * sd.w * sd.h) return SSIMU2_E_INVALID;
+    CU_TRY(cudaMemcpy2D(out, (size_t)sd.w * sizeof(float), src, (size_t)sd.pitch * sizeof(float),
+                        (size_t)sd.w * sizeof(float), (size_t)planes * sd.h, cudaMemcpyDeviceToHost));
+    return SSIMU2_OK;
+}
+
+int ssimu2_last_batch_ms(ssimu2_t* h, float ms[4])
+{
+    if (!h || !ms) return SSIMU2_E_INVALID;
+    memcpy(ms, h->last_ms, sizeof(h->last_ms));
+    return SSIMU2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,712 @@
+// ssimu2_kernels.cuh -- device code of the B200-native SSIMULACRA2 frame-pair scorer (sm_100a).
+//
+// Pipeline per batch of frame pairs (4 launches, every launch covers all frames and all 6 scales):
+//   k_pyramid  : source pair -> linear RGB -> levels 1..5 of the 2x box pyramid (planar f32)
+//   k_hpass    : per scale: (source | pyramid level) -> XYB -> 5 products -> HORIZONTAL recursive
+//                Gaussian of {ref^2, dis^2, ref*dis, ref, dis} x 3 channels -> 15 planes
+//   k_vpass    : per scale: VERTICAL recursive Gaussian of the 15 planes, fused with the SSIM /
+//                artifact / detail-loss maps and their L1 / L4 partial sums (f64)
+//   k_finalize : partial sums -> 108 norms -> weighted sum -> score (f64)
+//
+// Arithmetic contract: every operation that feeds the recursive filters replicates, operation for
+// operation, the reference's CPU implementation (crates/ssimulacra2-cuda/examples/cpu.rs) so that
+// the IIR outputs are bit-identical given identical inputs; compile with -fmad=false, fused ops are
+// explicit fmaf().  The GPU reference kernels this replaces are cited at each function.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ssimu2 {
+
+constexpr int kMaxScales = 6;
+constexpr int kMaxBatch = 32;
+
+enum Fmt : int { kNV12 = 0, kP016 = 1, kSRGB8 = 2, kSRGB16 = 3, kSRGBF32 = 4, kLINEARF32 = 5 };
+
+struct ScaleDesc {
+    int w, h, pitch;       // pitch in floats (multiple of 32)
+    int n_bands;           // H-pass work items (32-row bands)
+    int n_strips;          // V-pass work items (column strips)
+    int strip0;            // index of this scale's first strip in the partial-sum table
+    long long lin_off;     // float offset of level s (s >= 1) inside a slot's pyramid buffer: [2][3][h][pitch]
+    long long hb_off;      // float offset of scale s inside a slot's H-pass buffer: [15][h][pitch]
+};
+
+struct YuvCoef {           // MatrixCoefficients::coefficients, cuda-colorspace-kernel/src/lib.rs:183-201
+    float y, r, b, g1, g2;
+    int luma_min, neutral;
+};
+
+struct Geo {
+    ScaleDesc sc[kMaxScales];
+    int nscales;
+    int items_h, items_v;        // work items per frame (all scales)
+    int total_strips;            // partial-sum rows per frame
+    long long lin_stride;        // floats per slot
+    long long hb_stride;         // floats per slot
+    YuvCoef coef;
+};
+
+struct FrameIn {
+    const uint8_t* p0;
+    const uint8_t* p1;
+    uint32_t pitch;
+    uint32_t pad;
+};
+
+struct BatchIn {
+    FrameIn ref[kMaxBatch];
+    FrameIn dis[kMaxBatch];
+    unsigned long long first_ticket;
+};
+
+// ------------------------------------------------------------------------------------------
+// constants
+// ------------------------------------------------------------------------------------------
+__device__ const float kSrgb8Lut[256] = {
+#include "srgb8_lut.inc"
+};
+
+// Recursive Gaussian sigma = 1.5, radius 5 (cpu.rs:931-948; ssimulacra2-cuda-kernel/build.rs:28-145).
+#define RG_IN_1 0.055295236f
+#define RG_IN_3 (-0.058836687f)
+#define RG_IN_5 0.012955819f
+#define RG_PREV_1 1.9021131f
+#define RG_PREV_3 1.1755705f
+#define RG_PREV_5 0.00000000000000012246469f
+
+// ------------------------------------------------------------------------------------------
+// colour front-end
+// ------------------------------------------------------------------------------------------
+// BT709::eotf, cuda-colorspace-kernel/src/lib.rs:220-236 (same body for the BT601 variants).
+// The reference uses __nv_fast_powf; the accurate powf keeps us within an ulp or two of the oracle.
+__device__ __forceinline__ float bt709_eotf(float v)
+{
+    const float BETA = 0.018053968510807f;
+    const float ALPHA = 1.0f + 5.5f * BETA;
+    const float THRESHOLD = 0.08124285829863521110029445797874f;
+    if (v >= THRESHOLD)
+        return powf((v + (ALPHA - 1.0f)) / ALPHA, 1.0f / 0.45f);
+    return v / 4.5f;
+}
+
+// srgb_inverse_oetf, cuda-colorspace-kernel/src/srgb.rs:40-48.
+__device__ __forceinline__ float srgb_inverse_oetf(float x)
+{
+    const float SRGB_ALPHA = 1.0550107f;
+    const float SRGB_BETA = 0.0030412825f;
+    if (x < 12.92f * SRGB_BETA)
+        return x / 12.92f;
+    return powf((x + (SRGB_ALPHA - 1.0f)) / SRGB_ALPHA, 2.4f);
+}
+
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+
+// One source pixel -> linear RGB.  Replaces biplanaryuv420_to_linearrgb_generic
+// (cuda-colorspace-kernel/src/biplanar.rs:7-70), srgb_to_linear_u8_lookup / srgb_to_linear::<16> /
+// srgb_to_linear_f32 (srgb.rs:50-127).  x, y must be inside the frame.
+template <int FMT>
+__device__ __forceinline__ void load_px(const FrameIn& f, int x, int y, const YuvCoef& k, float& r, float& g, float& b)
+{
+    if constexpr (FMT == kNV12 || FMT == kP016) {
+        int Y, cbi, cri;
+        if constexpr (FMT == kNV12) {
+            Y = __ldg(f.p0 + (size_t)y * f.pitch + x);
+            const uint8_t* uv = f.p1 + (size_t)(y >> 1) * f.pitch + 2 * (x >> 1);
+            uchar2 c = __ldg(reinterpret_cast<const uchar2*>(uv));
+            cbi = c.x; cri = c.y;
+        } else {
+            Y = __ldg(reinterpret_cast<const uint16_t*>(f.p0 + (size_t)y * f.pitch) + x);
+            const uint16_t* uv = reinterpret_cast<const uint16_t*>(f.p1 + (size_t)(y >> 1) * f.pitch) + 2 * (x >> 1);
+            ushort2 c = __ldg(reinterpret_cast<const ushort2*>(uv));
+            cbi = c.x; cri = c.y;
+        }
+        float cb = (float)(cbi - k.neutral);
+        float cr = (float)(cri - k.neutral);
+        float r_ = k.r * cr;
+        float g_ = fmaf(k.g1, cb, k.g2 * cr);
+        float b_ = k.b * cb;
+        float luma = (float)(max(Y, k.luma_min) - k.luma_min) * k.y;
+        r = clamp01(bt709_eotf(luma + r_));
+        g = clamp01(bt709_eotf(luma + g_));
+        b = clamp01(bt709_eotf(luma + b_));
+    } else if constexpr (FMT == kSRGB8) {
+        const uint8_t* p = f.p0 + (size_t)y * f.pitch + 3 * x;
+        r = kSrgb8Lut[__ldg(p)];
+        g = kSrgb8Lut[__ldg(p + 1)];
+        b = kSrgb8Lut[__ldg(p + 2)];
+    } else if constexpr (FMT == kSRGB16) {
+        const uint16_t* p = reinterpret_cast<const uint16_t*>(f.p0 + (size_t)y * f.pitch) + 3 * x;
+        r = srgb_inverse_oetf((float)__ldg(p) / 65535.0f);
+        g = srgb_inverse_oetf((float)__ldg(p + 1) / 65535.0f);
+        b = srgb_inverse_oetf((float)__ldg(p + 2) / 65535.0f);
+    } else {
+        const float* p = reinterpret_cast<const float*>(f.p0 + (size_t)y * f.pitch) + 3 * x;
+        r = __ldg(p); g = __ldg(p + 1); b = __ldg(p + 2);
+        if constexpr (FMT == kSRGBF32) {
+            r = srgb_inverse_oetf(r); g = srgb_inverse_oetf(g); b = srgb_inverse_oetf(b);
+        }
+    }
+}
+
+// linear RGB -> rescaled XYB.  cpu.rs:421-496 (== ssimulacra2-cuda-kernel/src/xyb.rs:3-102).
+__device__ __forceinline__ void linear_to_xyb(float r, float g, float b, float& X, float& Y, float& B)
+{
+    const float K_M02 = 0.078f, K_M00 = 0.30f, K_M01 = 1.0f - K_M02 - K_M00;
+    const float K_M12 = 0.078f, K_M10 = 0.23f, K_M11 = 1.0f - K_M12 - K_M10;
+    const float K_M20 = 0.24342269f, K_M21 = 0.20476745f, K_M22 = 1.0f - K_M20 - K_M21;
+    const float K_B0 = 0.0037930734f;
+    const float K_B0_ROOT = 0.1559542025327239180319220163705f;
+    float rg = fmaf(K_M00, r, fmaf(K_M01, g, fmaf(K_M02, b, K_B0)));
+    float gr = fmaf(K_M10, r, fmaf(K_M11, g, fmaf(K_M12, b, K_B0)));
+    float bb = fmaf(K_M20, r, fmaf(K_M21, g, fmaf(K_M22, b, K_B0)));
+    rg = cbrtf(fmaxf(rg, 0.0f)) - K_B0_ROOT;
+    gr = cbrtf(fmaxf(gr, 0.0f)) - K_B0_ROOT;
+    bb = cbrtf(fmaxf(bb, 0.0f)) - K_B0_ROOT;
+    float x = 0.5f * (rg - gr);
+    float y = 0.5f * (rg + gr);
+    X = fmaf(x, 14.0f, 0.42f);
+    Y = y + 0.01f;
+    B = (bb - y) + 0.55f;
+}
+
+// Linear RGB of pixel (x, y) of image `img` (0 = ref, 1 = dis) at scale s: the source frame at
+// scale 0, the pyramid level otherwise.
+template <int FMT>
+__device__ __forceinline__ void load_linear(const Geo& g, const BatchIn& in, const float* lin_slot, int frame, int s,
+                                            int img, int x, int y, float& r, float& gg, float& b)
+{
+    if (s == 0) {
+        load_px<FMT>(img ? in.dis[frame] : in.ref[frame], x, y, g.coef, r, gg, b);
+    } else {
+        const ScaleDesc& sd = g.sc[s];
+        size_t plane = (size_t)sd.h * sd.pitch;
+        const float* p = lin_slot + sd.lin_off + (size_t)img * 3 * plane + (size_t)y * sd.pitch + x;
+        r = __ldg(p); gg = __ldg(p + plane); b = __ldg(p + 2 * plane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_pyramid: levels 1..5 of the linear-RGB pyramid.  Replaces downscale_by_2
+// (ssimulacra2-cuda-kernel/src/downscale.rs:4-35, host loop ssimulacra2-cuda/src/lib.rs:162-183)
+// and the colour conversion kernels; follows cpu.rs:545-579 (sum order (0,0),(1,0),(0,1),(1,1),
+// edge clamp min(src-1), x0.25).
+// One CTA = one 64x64 source tile of one frame, both images; 256 threads, thread = 4x4 source px.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float box4(float a, float b, float c, float d) { return (((0.0f + a) + b) + c + d) * 0.25f; }
+
+template <int FMT>
+__global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Geo g, const __grid_constant__ BatchIn in, float* __restrict__ lin_base)
+{
+    __shared__ float s2[6][16][16];
+    __shared__ float s3[6][8][8];
+    __shared__ float s4[6][4][4];
+    const int frame = blockIdx.z;
+    float* lin_slot = lin_base + (size_t)frame * g.lin_stride;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int W0 = g.sc[0].w, H0 = g.sc[0].h;
+    const int bx = blockIdx.x * 64 + tx * 4, by = blockIdx.y * 64 + ty * 4;  // source block origin
+    const int ns = g.nscales;
+
+    for (int img = 0; img < 2; img++) {
+        const FrameIn& f = img ? in.dis[frame] : in.ref[frame];
+        float l1[3][2][2];
+        const int W1 = g.sc[1].w, H1 = g.sc[1].h;
+        // level 1: 2x2 outputs per thread
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                int ox = bx / 2 + i, oy = by / 2 + j;
+                float acc[3][4];
+                bool valid = ns > 1 && ox < W1 && oy < H1;
+                if (valid) {
+#pragma unroll
+                    for (int iy = 0; iy < 2; iy++)
+#pragma unroll
+                        for (int ix = 0; ix < 2; ix++) {
+                            int x = min(2 * ox + ix, W0 - 1), y = min(2 * oy + iy, H0 - 1);
+                            load_px<FMT>(f, x, y, g.coef, acc[0][iy * 2 + ix], acc[1][iy * 2 + ix], acc[2][iy * 2 + ix]);
+                        }
+                }
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    l1[c][j][i] = valid ? box4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]) : 0.0f;
+            }
+        if (ns > 1) {
+            const ScaleDesc& sd = g.sc[1];
+            size_t plane = (size_t)sd.h * sd.pitch;
+            float* dst = lin_slot + sd.lin_off + (size_t)img * 3 * plane;
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    int ox = bx / 2, oy = by / 2 + j;
+                    if (oy < H1) {
+                        if (ox + 1 < W1)
+                            *reinterpret_cast<float2*>(dst + c * plane + (size_t)oy * sd.pitch + ox) =
+                                make_float2(l1[c][j][0], l1[c][j][1]);
+                        else if (ox < W1)
+                            dst[c * plane + (size_t)oy * sd.pitch + ox] = l1[c][j][0];
+                    }
+                }
+        }
+        // level 2: one output per thread, from registers
+        if (ns > 2) {
+            const ScaleDesc& sd = g.sc[2];
+            int ox = bx / 4, oy = by / 4;
+            bool valid = ox < sd.w && oy < sd.h;
+            int i1 = (2 * ox + 1 <= W1 - 1) ? 1 : 0, j1 = (2 * oy + 1 <= H1 - 1) ? 1 : 0;
+            size_t plane = (size_t)sd.h * sd.pitch;
+            float* dst = lin_slot + sd.lin_off + (size_t)img * 3 * plane;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                float v = 0.0f;
+                if (valid) {
+                    float a = l1[c][0][0], b = i1 ? l1[c][0][1] : l1[c][0][0];
+                    float cc = j1 ? l1[c][1][0] : l1[c][0][0];
+                    float d = j1 ? (i1 ? l1[c][1][1] : l1[c][1][0]) : (i1 ? l1[c][0][1] : l1[c][0][0]);
+                    v = box4(a, b, cc, d);
+                    dst[c * plane + (size_t)oy * sd.pitch + ox] = v;
+                }
+                s2[img * 3 + c][ty][tx] = v;
+            }
+        }
+    }
+    // levels 3..5 through shared memory (6 = 2 images x 3 channels)
+    if (ns > 3) {
+        __syncthreads();
+        const ScaleDesc& sp = g.sc[2];
+        const ScaleDesc& sd = g.sc[3];
+        size_t plane = (size_t)sd.h * sd.pitch;
+        for (int idx = threadIdx.x; idx < 6 * 64; idx += 256) {
+            int pc = idx >> 6, ly = (idx >> 3) & 7, lx = idx & 7;
+            int ox = blockIdx.x * 8 + lx, oy = blockIdx.y * 8 + ly;
+            float v = 0.0f;
+            if (ox < sd.w && oy < sd.h) {
+                int i1 = (2 * ox + 1 <= sp.w - 1) ? 1 : 0, j1 = (2 * oy + 1 <= sp.h - 1) ? 1 : 0;
+                v = box4(s2[pc][2 * ly][2 * lx], s2[pc][2 * ly][2 * lx + i1], s2[pc][2 * ly + j1][2 * lx],
+                         s2[pc][2 * ly + j1][2 * lx + i1]);
+                lin_slot[sd.lin_off + (size_t)pc * plane + (size_t)oy * sd.pitch + ox] = v;
+            }
+            s3[pc][ly][lx] = v;
+        }
+    }
+    if (ns > 4) {
+        __syncthreads();
+        const ScaleDesc& sp = g.sc[3];
+        const ScaleDesc& sd = g.sc[4];
+        size_t plane = (size_t)sd.h * sd.pitch;
+        for (int idx = threadIdx.x; idx < 6 * 16; idx += 256) {
+            int pc = idx >> 4, ly = (idx >> 2) & 3, lx = idx & 3;
+            int ox = blockIdx.x * 4 + lx, oy = blockIdx.y * 4 + ly;
+            float v = 0.0f;
+            if (ox < sd.w && oy < sd.h) {
+                int i1 = (2 * ox + 1 <= sp.w - 1) ? 1 : 0, j1 = (2 * oy + 1 <= sp.h - 1) ? 1 : 0;
+                v = box4(s3[pc][2 * ly][2 * lx], s3[pc][2 * ly][2 * lx + i1], s3[pc][2 * ly + j1][2 * lx],
+                         s3[pc][2 * ly + j1][2 * lx + i1]);
+                lin_slot[sd.lin_off + (size_t)pc * plane + (size_t)oy * sd.pitch + ox] = v;
+            }
+            s4[pc][ly][lx] = v;
+        }
+    }
+    if (ns > 5) {
+        __syncthreads();
+        const ScaleDesc& sp = g.sc[4];
+        const ScaleDesc& sd = g.sc[5];
+        size_t plane = (size_t)sd.h * sd.pitch;
+        for (int idx = threadIdx.x; idx < 6 * 4; idx += 256) {
+            int pc = idx >> 2, ly = (idx >> 1) & 1, lx = idx & 1;
+            int ox = blockIdx.x * 2 + lx, oy = blockIdx.y * 2 + ly;
+            if (ox < sd.w && oy < sd.h) {
+                int i1 = (2 * ox + 1 <= sp.w - 1) ? 1 : 0, j1 = (2 * oy + 1 <= sp.h - 1) ? 1 : 0;
+                float v = box4(s4[pc][2 * ly][2 * lx], s4[pc][2 * ly][2 * lx + i1], s4[pc][2 * ly + j1][2 * lx],
+                               s4[pc][2 * ly + j1][2 * lx + i1]);
+                lin_slot[sd.lin_off + (size_t)pc * plane + (size_t)oy * sd.pitch + ox] = v;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_hpass: XYB + products + horizontal recursive Gaussian.
+// Replaces linear_to_xyb_packed (xyb.rs:82-102), nppiMul x3 (ssimulacra2-cuda/src/lib.rs:300-317)
+// and one of the two blur_plane_pass_fused launches + its nppiTranspose x5 (lib.rs:328-361).
+// Follows RecursiveGaussian::horizontal_row, cpu.rs:967-1022.
+//
+// CTA = one 32-row band of one scale of one frame; 512 threads.
+//   convert : thread = one 2x2 quad of one image of the 32x32 chunk -> XYB -> smem (zero outside the row)
+//   scan    : warp p (0..14) = plane (quantity q = p/3, channel c = p%3), lane = row; walks the chunk
+//             4 columns per 128-bit smem access, filter state in registers across chunks
+//   store   : all threads, 128-bit coalesced stores of the 15x32x32 output tile
+// Step t consumes x[t] (right tap, index n+4) and x[t-10] (left tap, n-6) and emits y[t-4]
+// (n = t-4, cpu.rs:976-984).  Chunk k (k = -1, 0, ...) covers steps 32k+4 .. 32k+35, i.e. outputs
+// 32k .. 32k+31; chunk -1 only warms the state with x[0..3] (its other inputs are the zero padding).
+// ------------------------------------------------------------------------------------------
+constexpr int kHRows = 32;
+constexpr int kHCols = 32;
+constexpr int kHPitch = 36;  // floats; 144 B = 9 x 16 B -> conflict-free 128-bit row-per-lane access
+constexpr int kHThreads = 512;
+constexpr int kHSmemIn = 2 * 2 * 3 * kHRows * kHPitch;  // [buf][img][ch][row][col]
+constexpr int kHSmemOut = 15 * kHRows * kHPitch;        // [plane][row][col]
+constexpr size_t kHSmemBytes = (size_t)(kHSmemIn + kHSmemOut) * sizeof(float);
+
+struct HState {
+    float p1, p3, p5, pp1, pp3, pp5;
+};
+
+__device__ __forceinline__ float hstep(HState& s, float left, float right)
+{
+    float sum = left + right;
+    float o1 = sum * RG_IN_1, o3 = sum * RG_IN_3, o5 = sum * RG_IN_5;
+    o1 = o1 - s.pp1;  // == fmaf(MUL_PREV2 = -1, prev2, out): the product is exact
+    o3 = o3 - s.pp3;
+    o5 = o5 - s.pp5;
+    s.pp1 = s.p1; s.pp3 = s.p3; s.pp5 = s.p5;
+    o1 = fmaf(RG_PREV_1, s.p1, o1);
+    o3 = fmaf(RG_PREV_3, s.p3, o3);
+    o5 = fmaf(RG_PREV_5, s.p5, o5);
+    s.p1 = o1; s.p3 = o3; s.p5 = o5;
+    return (o1 + o3) + o5;
+}
+
+template <int Q>
+__device__ __forceinline__ void hscan_chunk(const float* __restrict__ s_ref, const float* __restrict__ s_dis,
+                                            float* __restrict__ s_out, HState& st, float (&hist)[12])
+{
+    float win[12 + kHCols];
+#pragma unroll
+    for (int i = 0; i < 12; i++) win[i] = hist[i];
+#pragma unroll
+    for (int gI = 0; gI < kHCols / 4; gI++) {
+        float4 a, d;
+        if (Q == 0 || Q == 2 || Q == 3) a = *reinterpret_cast<const float4*>(s_ref + 4 * gI);
+        if (Q == 1 || Q == 2 || Q == 4) d = *reinterpret_cast<const float4*>(s_dis + 4 * gI);
+        float pr[4];
+        if (Q == 0) { pr[0] = a.x * a.x; pr[1] = a.y * a.y; pr[2] = a.z * a.z; pr[3] = a.w * a.w; }
+        if (Q == 1) { pr[0] = d.x * d.x; pr[1] = d.y * d.y; pr[2] = d.z * d.z; pr[3] = d.w * d.w; }
+        if (Q == 2) { pr[0] = a.x * d.x; pr[1] = a.y * d.y; pr[2] = a.z * d.z; pr[3] = a.w * d.w; }
+        if (Q == 3) { pr[0] = a.x; pr[1] = a.y; pr[2] = a.z; pr[3] = a.w; }
+        if (Q == 4) { pr[0] = d.x; pr[1] = d.y; pr[2] = d.z; pr[3] = d.w; }
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            win[12 + 4 * gI + j] = pr[j];
+            o[j] = hstep(st, win[4 * gI + j + 2], pr[j]);  // left tap = 10 columns back
+        }
+        *reinterpret_cast<float4*>(s_out + 4 * gI) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) hist[i] = win[kHCols + i];
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kHThreads) k_hpass(const __grid_constant__ Geo g, const __grid_constant__ BatchIn in, const float* __restrict__ lin_base,
+                                                     float* __restrict__ hb_base)
+{
+    extern __shared__ __align__(16) float smem[];
+    float* s_in = smem;
+    float* s_out = smem + kHSmemIn;
+
+    const int frame = blockIdx.y;
+    int item = blockIdx.x, s = 0;
+    while (item >= g.sc[s].n_bands) { item -= g.sc[s].n_bands; s++; }
+    const ScaleDesc sd = g.sc[s];
+    const int row0 = item * kHRows;
+    const float* lin_slot = lin_base + (size_t)frame * g.lin_stride;
+    float* hb = hb_base + (size_t)frame * g.hb_stride + sd.hb_off;
+    const size_t plane = (size_t)sd.h * sd.pitch;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // convert role
+    const int cimg = tid >> 8, cq = tid & 255, cqy = cq >> 4, cqx = cq & 15;
+    // scan role
+    const int q = warp / 3, ch = warp - 3 * q;
+    HState st = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float hist[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) hist[i] = 0.f;
+
+    const int nchunks = (sd.w + kHCols - 1) / kHCols + 1;
+
+    auto convert = [&](int k, int buf) {
+        const int c0 = kHCols * k + 4;
+        float* dst = s_in + ((buf * 2 + cimg) * 3) * kHRows * kHPitch;
+#pragma unroll
+        for (int iy = 0; iy < 2; iy++)
+#pragma unroll
+            for (int ix = 0; ix < 2; ix++) {
+                int lx = 2 * cqx + ix, ly = 2 * cqy + iy;
+                int x = c0 + lx, y = row0 + ly;
+                float X = 0.f, Y = 0.f, B = 0.f;
+                if (x >= 0 && x < sd.w && y < sd.h) {
+                    float r, gg, b;
+                    load_linear<FMT>(g, in, lin_slot, frame, s, cimg, x, y, r, gg, b);
+                    linear_to_xyb(r, gg, b, X, Y, B);
+                }
+                dst[(0 * kHRows + ly) * kHPitch + lx] = X;
+                dst[(1 * kHRows + ly) * kHPitch + lx] = Y;
+                dst[(2 * kHRows + ly) * kHPitch + lx] = B;
+            }
+    };
+
+    convert(-1, 0);
+    __syncthreads();
+    for (int kk = 0; kk < nchunks; kk++) {
+        const int k = kk - 1, buf = kk & 1;
+        if (kk + 1 < nchunks) convert(k + 1, buf ^ 1);
+        if (warp < 15) {
+            const float* s_ref = s_in + (((buf * 2 + 0) * 3 + ch) * kHRows + lane) * kHPitch;
+            const float* s_dis = s_in + (((buf * 2 + 1) * 3 + ch) * kHRows + lane) * kHPitch;
+            float* so = s_out + (warp * kHRows + lane) * kHPitch;
+            switch (q) {
+            case 0: hscan_chunk<0>(s_ref, s_dis, so, st, hist); break;
+            case 1: hscan_chunk<1>(s_ref, s_dis, so, st, hist); break;
+            case 2: hscan_chunk<2>(s_ref, s_dis, so, st, hist); break;
+            case 3: hscan_chunk<3>(s_ref, s_dis, so, st, hist); break;
+            default: hscan_chunk<4>(s_ref, s_dis, so, st, hist); break;
+            }
+        }
+        __syncthreads();
+        if (k >= 0) {
+            for (int idx = tid; idx < 15 * kHRows * (kHCols / 4); idx += kHThreads) {
+                int p = idx >> 8, r = (idx >> 3) & 31, g4 = idx & 7;
+                int row = row0 + r, col = kHCols * k + 4 * g4;
+                if (row < sd.h && col < sd.w)
+                    *reinterpret_cast<float4*>(hb + p * plane + (size_t)row * sd.pitch + col) =
+                        *reinterpret_cast<const float4*>(s_out + (p * kHRows + r) * kHPitch + 4 * g4);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_vpass: vertical recursive Gaussian + error maps + partial sums.
+// Replaces the second blur_plane_pass_fused launch, 2 nppiTranspose, compute_error_maps
+// (ssimulacra2-cuda-kernel/src/error_maps.rs:4-60) and the 6 x {nppiSum, nppiSqr, nppiSqr_I, nppiSum}
+// reductions (ssimulacra2-cuda/src/lib.rs:372-447).  Follows vertical_pass cpu.rs:1054-1115,
+// ssim_map cpu.rs:581-638 and edge_diff_map cpu.rs:640-683 (f64 tails included).
+//
+// CTA = one 64-column strip of one scale of one frame; 192 threads = (channel c, column x);
+// each thread runs the 5 filters of its (c, x) down the column and accumulates 6 f64 sums.
+// Rows are processed 3 per iteration: thread (c, x) first converts the source pixel
+// (x, row n0 + c) of both images to XYB (all 3 channels) into shared memory, then, after one
+// barrier, every thread advances its filters 3 steps and evaluates the maps for its channel.
+// ------------------------------------------------------------------------------------------
+constexpr int kVCols = 64;
+constexpr int kVThreads = 3 * kVCols;
+constexpr int kVRing = 10;
+
+struct VState {
+    float p1, p3, p5, pp1, pp3, pp5;
+};
+
+__device__ __forceinline__ float vstep(VState& s, float top, float bottom)
+{
+    float sum = top + bottom;
+    float a1 = fmaf(s.p1, -RG_PREV_1, s.pp1);
+    float a3 = fmaf(s.p3, -RG_PREV_3, s.pp3);
+    float a5 = fmaf(s.p5, -RG_PREV_5, s.pp5);
+    float o1 = fmaf(sum, RG_IN_1, -a1);
+    float o3 = fmaf(sum, RG_IN_3, -a3);
+    float o5 = fmaf(sum, RG_IN_5, -a5);
+    s.pp1 = s.p1; s.pp3 = s.p3; s.pp5 = s.p5;
+    s.p1 = o1; s.p3 = o3; s.p5 = o5;
+    return (o1 + o3) + o5;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kVThreads) k_vpass(const __grid_constant__ Geo g, const __grid_constant__ BatchIn in, const float* __restrict__ lin_base,
+                                                     const float* __restrict__ hb_base, double* __restrict__ partials)
+{
+    __shared__ float ring[kVRing][5][kVThreads];
+    __shared__ float sxyb[2][2][3][3][kVCols];  // [buf][img][channel][row-in-iteration][x]
+    __shared__ double red[kVThreads / 32][6];
+
+    const int frame = blockIdx.y;
+    int item = blockIdx.x, s = 0;
+    while (item >= g.sc[s].n_strips) { item -= g.sc[s].n_strips; s++; }
+    const ScaleDesc sd = g.sc[s];
+    const float* lin_slot = lin_base + (size_t)frame * g.lin_stride;
+    const float* hb = hb_base + (size_t)frame * g.hb_stride + sd.hb_off;
+    const size_t plane = (size_t)sd.h * sd.pitch;
+
+    const int tid = threadIdx.x, tx = tid % kVCols, c = tid / kVCols;
+    const int x = item * kVCols + tx;
+    const bool active = x < sd.w;
+    const int H = sd.h;
+
+    VState st[5];
+#pragma unroll
+    for (int qi = 0; qi < 5; qi++) st[qi] = VState{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < kVRing; i++)
+#pragma unroll
+        for (int qi = 0; qi < 5; qi++) ring[i][qi][tid] = 0.f;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+
+    const float* col = hb + (size_t)c * plane + x;  // plane (q*3 + c) = col + q*3*plane
+    const int nsteps = H + 4;
+    int slot = 0;
+    for (int t0 = 0, it = 0; t0 < nsteps; t0 += 3, it++) {
+        const int buf = it & 1;
+        // phase 1: XYB of row n = t0 + c - 4, both images
+        {
+            int n = t0 + c - 4;
+            if (active && n >= 0 && n < H) {
+#pragma unroll
+                for (int img = 0; img < 2; img++) {
+                    float r, gg, b, X, Y, B;
+                    load_linear<FMT>(g, in, lin_slot, frame, s, img, x, n, r, gg, b);
+                    linear_to_xyb(r, gg, b, X, Y, B);
+                    sxyb[buf][img][0][c][tx] = X;
+                    sxyb[buf][img][1][c][tx] = Y;
+                    sxyb[buf][img][2][c][tx] = B;
+                }
+            }
+        }
+        // right taps of the 3 steps
+        float v[3][5];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            int t = t0 + r;
+            bool ld = active && t < H;
+#pragma unroll
+            for (int qi = 0; qi < 5; qi++) v[r][qi] = ld ? __ldg(col + (size_t)qi * 3 * plane + (size_t)t * sd.pitch) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            int t = t0 + r;
+            if (t < nsteps) {
+                float o[5];
+#pragma unroll
+                for (int qi = 0; qi < 5; qi++) {
+                    float old = ring[slot][qi][tid];
+                    ring[slot][qi][tid] = v[r][qi];
+                    o[qi] = vstep(st[qi], old, v[r][qi]);
+                }
+                slot = (slot == kVRing - 1) ? 0 : slot + 1;
+                int n = t - 4;
+                if (active && n >= 0) {
+                    const float C2 = 0.0009f;
+                    float s11 = o[0], s22 = o[1], s12 = o[2], mu1 = o[3], mu2 = o[4];
+                    float mu11 = mu1 * mu1, mu22 = mu2 * mu2, mu12 = mu1 * mu2;
+                    float mu_diff = mu1 - mu2;
+                    float num_m = fmaf(mu_diff, -mu_diff, 1.0f);
+                    float num_s = fmaf(2.0f, s12 - mu12, C2);
+                    float denom_s = ((s11 - mu11) + (s22 - mu22)) + C2;
+                    double d = 1.0 - (double)((num_m * num_s) / denom_s);
+                    d = d > 0.0 ? d : 0.0;
+                    acc[0] += d;
+                    double d2 = d * d;
+                    acc[1] += d2 * d2;
+
+                    float ref = sxyb[buf][0][c][r][tx], dis = sxyb[buf][1][c][r][tx];
+                    double d1 = (1.0 + (double)fabsf(dis - mu2)) / (1.0 + (double)fabsf(ref - mu1)) - 1.0;
+                    double art = d1 > 0.0 ? d1 : 0.0;
+                    double det = -d1 > 0.0 ? -d1 : 0.0;
+                    acc[2] += art;
+                    double a2 = art * art;
+                    acc[3] += a2 * a2;
+                    acc[4] += det;
+                    double l2 = det * det;
+                    acc[5] += l2 * l2;
+                }
+            }
+        }
+    }
+    // block reduction: warps are channel-uniform (64 columns = 2 warps per channel)
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        double vsum = acc[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) vsum += __shfl_down_sync(0xffffffffu, vsum, off);
+        if ((tid & 31) == 0) red[tid >> 5][k] = vsum;
+    }
+    __syncthreads();
+    if (tid < 18) {
+        int cc = tid / 6, k = tid % 6;
+        double vsum = red[2 * cc][k] + red[2 * cc + 1][k];
+        partials[((size_t)frame * g.total_strips + sd.strip0 + item) * 18 + cc * 6 + k] = vsum;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_finalize: partial sums -> 108 norms -> score.  Replaces the host-side
+// Ssimulacra2::post_process_scores (ssimulacra2-cuda/src/lib.rs:449-623); follows
+// Msssim::score cpu.rs:728-871 (weight order [channel][scale][L1,L4][ssim,artifact,detail]).
+// One CTA per frame.
+// ------------------------------------------------------------------------------------------
+__device__ const double kWeight[108] = {
+    0.0, 0.0007376606707406586, 0.0, 0.0, 0.0007793481682867309, 0.0,
+    0.0, 0.0004371155730107379, 0.0, 1.1041726426657346, 0.00066284834129271, 0.00015231632783718752,
+    0.0, 0.0016406437456599754, 0.0, 1.8422455520539298, 11.441172603757666, 0.0,
+    0.0007989109436015163, 0.000176816438078653, 0.0, 1.8787594979546387, 10.94906990605142, 0.0,
+    0.0007289346991508072, 0.9677937080626833, 0.0, 0.00014003424285435884, 0.9981766977854967, 0.00031949755934435053,
+    0.0004550992113792063, 0.0, 0.0, 0.0013648766163243398, 0.0, 0.0,
+    0.0, 0.0, 0.0, 7.466890328078848, 0.0, 17.445833984131262,
+    0.0006235601634041466, 0.0, 0.0, 6.683678146179332, 0.00037724407979611296, 1.027889937768264,
+    225.20515300849274, 0.0, 0.0, 19.213238186143016, 0.0011401524586618361, 0.001237755635509985,
+    176.39317598450694, 0.0, 0.0, 24.43300999870476, 0.28520802612117757, 0.0004485436923833408,
+    0.0, 0.0, 0.0, 34.77906344483772, 44.835625328877896, 0.0,
+    0.0, 0.0, 0.0, 0.0, 0.0, 0.0,
+    0.0, 0.0008680556573291698, 0.0, 0.0, 0.0, 0.0,
+    0.0, 0.0005313191874358747, 0.0, 0.00016533814161379112, 0.0, 0.0,
+    0.0, 0.0, 0.0, 0.0004179171803251336, 0.0017290828234722833, 0.0,
+    0.0020827005846636437, 0.0, 0.0, 8.826982764996862, 23.19243343998926, 0.0,
+    95.1080498811086, 0.9863978034400682, 0.9834382792465353, 0.0012286405048278493, 171.2667255897307, 0.9807858872435379,
+    0.0, 0.0, 0.0, 0.0005130064588990679, 0.0, 0.00010854057858411537,
+};
+
+__global__ void __launch_bounds__(128) k_finalize(const __grid_constant__ Geo g, const double* __restrict__ partials,
+                                                  double* __restrict__ norms_out, double* __restrict__ scores_ring,
+                                                  unsigned long long first_ticket, unsigned long long ring_cap,
+                                                  double* __restrict__ scores_out)
+{
+    __shared__ double norms[108];
+    const int frame = blockIdx.x, tid = threadIdx.x;
+    if (tid < 108) norms[tid] = 0.0;
+    __syncthreads();
+    if (tid < 108) {
+        // tid = s*18 + c*6 + k, k: 0 ssim L1, 1 ssim L4, 2 art L1, 3 art L4, 4 det L1, 5 det L4
+        int s = tid / 18, c = (tid / 6) % 3, k = tid % 6;
+        if (s < g.nscales) {
+            const ScaleDesc& sd = g.sc[s];
+            const double* p = partials + ((size_t)frame * g.total_strips + sd.strip0) * 18 + c * 6 + k;
+            double sum = 0.0;
+            for (int i = 0; i < sd.n_strips; i++) sum += p[(size_t)i * 18];
+            double one_per_pixels = 1.0 / (double)((size_t)sd.w * sd.h);
+            double v = one_per_pixels * sum;
+            int m = k >> 1, n = k & 1;
+            if (n) v = sqrt(sqrt(v));
+            norms[c * 36 + s * 6 + n * 3 + m] = v;
+        }
+    }
+    __syncthreads();
+    if (tid < 108) norms_out[(size_t)frame * 108 + tid] = norms[tid];
+    if (tid == 0) {
+        // cpu.rs:840-868; with fewer than 6 scales the weight cursor is dense, as in the reference.
+        double ssim = 0.0;
+        int i = 0;
+        for (int c = 0; c < 3; c++)
+            for (int s = 0; s < g.nscales; s++)
+                for (int n = 0; n < 2; n++)
+                    for (int m = 0; m < 3; m++) {
+                        ssim = fma(kWeight[i], fabs(norms[c * 36 + s * 6 + n * 3 + m]), ssim);
+                        i++;
+                    }
+        ssim *= 0.9562382616834844;
+        ssim = fma(6.248496625763138e-5 * ssim * ssim, ssim,
+                   fma(2.326765642916932, ssim, -0.020884521182843837 * ssim * ssim));
+        if (ssim > 0.0)
+            ssim = fma(pow(ssim, 0.6276336467831387), -10.0, 100.0);
+        else
+            ssim = 100.0;
+        scores_out[frame] = ssim;
+        scores_ring[(first_ticket + frame) % ring_cap] = ssim;
+    }
+}
+
+}  // namespace ssimu2

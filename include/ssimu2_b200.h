@@ -138,10 +138,13 @@ typedef struct {
 } ssimu2_info;
 int ssimu2_get_info(const ssimu2_t *h, ssimu2_info *info);
 /* Copy an intermediate plane set of the batch slot that served `ticket` to host memory.
- * what = 0: linear pyramid level `scale` (>= 1): float[2][3][h][w]  (ref planes, then dis)
+ * what = 0: XYB planes of `scale`:                float[2][3][h][w]  (ref X,Y,B then dis X,Y,B)
  * what = 1: H-pass output of `scale`:            float[15][h][w]    (s11,s22,s12,mu1,mu2) x 3 channels
  * Only valid until that slot is reused (i.e. right after ssimu2_get_score). */
 int ssimu2_debug_read(ssimu2_t *h, uint64_t ticket, int what, int scale, float *out, size_t out_floats);
+/* Run the device build of the bit-exact libm restatements over an array (op 0: cbrtf(x),
+ * op 1: powf(x, y)); host pointers.  Lets the tests compare the GPU arithmetic with libm bit for bit. */
+int ssimu2_debug_math(int op, const float *in, float y, float *out, size_t n);
 /* Average device time (ms) of the last completed batch per kernel: pyramid, hpass, vpass, finalize. */
 int ssimu2_last_batch_ms(ssimu2_t *h, float ms[4]);
 

@@ -1,0 +1,277 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): every one of the 108 per-scale / per-channel norms within 1e-4
+relative, the final score within 0.01 absolute.  Because the filter inputs are reproduced bit for
+bit (exact_math.cuh) the intermediate planes are additionally required to be IDENTICAL to the
+oracle's, which is what keeps the norms far inside the bar.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+NORM_RTOL = 1e-4   # north_star: per-scale/per-channel norms within 1e-4 relative
+SCORE_ATOL = 0.01  # north_star: final score within 0.01 absolute
+
+
+def _tm():
+    import turbo_metrics_b200 as tm
+    return tm
+
+
+def _assert_norms(norms, ref_norms, score, ref_score):
+    ref_norms = np.asarray(ref_norms)
+    # norms of exactly 0 in the oracle (identical inputs) must be exactly 0 here too
+    denom = np.maximum(np.abs(ref_norms), 1e-300)
+    rel = np.abs(norms - ref_norms) / denom
+    rel[ref_norms == 0] = np.abs(norms[ref_norms == 0])
+    assert rel.max() <= NORM_RTOL, f"max rel norm err {rel.max():.3e} at {rel.argmax()}"
+    assert abs(score - ref_score) <= SCORE_ATOL, (score, ref_score)
+    return rel.max()
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+# ------------------------------------------------------------------------------------------
+def test_device_libm_restatements_match_host_libm(exact_math_host):
+    """Device cbrtf / powf == this box's libm, bit for bit, on the ranges the pipeline uses."""
+    from turbo_metrics_b200 import _lib
+    lib = _lib.lib()
+    rng = np.random.default_rng(11)
+    x = np.concatenate([
+        rng.uniform(0.0037, 1.01, 3_000_000).astype(np.float32),
+        np.arange(int(np.float32(0.25).view(np.uint32)), int(np.float32(0.25).view(np.uint32)) + (1 << 21),
+                  dtype=np.uint32).view(np.float32),
+        np.array([0.0, 1.0, 0.0037930734, 8.0, 27.0], np.float32)])
+    out = np.empty_like(x)
+    ref = np.empty_like(x)
+    fp = C.POINTER(C.c_float)
+    assert lib.ssimu2_debug_math(0, x.ctypes.data_as(fp), 0.0, out.ctypes.data_as(fp), x.size) == 0
+    exact_math_host.libm_cbrtf_array(x.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p), C.c_size_t(x.size))
+    assert np.array_equal(_bits(out), _bits(ref)), f"{(_bits(out) != _bits(ref)).sum()} cbrtf mismatches"
+    for y in [float(np.float32(1.0) / np.float32(0.45)), 2.4]:
+        xb = rng.uniform(0.07, 1.3, 3_000_000).astype(np.float32)
+        out = np.empty_like(xb)
+        ref = np.empty_like(xb)
+        assert lib.ssimu2_debug_math(1, xb.ctypes.data_as(fp), y, out.ctypes.data_as(fp), xb.size) == 0
+        exact_math_host.libm_powf_array(xb.ctypes.data_as(C.c_void_p), C.c_float(y), ref.ctypes.data_as(C.c_void_p),
+                                        C.c_size_t(xb.size))
+        assert np.array_equal(_bits(out), _bits(ref)), f"{(_bits(out) != _bits(ref)).sum()} powf mismatches (y={y})"
+
+
+# ------------------------------------------------------------------------------------------
+def _oracle_stages(oracle, ref_lin, dis_lin, nscales):
+    """XYB planes and H-pass planes of every scale, from the oracle's own building blocks."""
+    xyb, hb = [], []
+    a, b = ref_lin, dis_lin
+    for s in range(nscales):
+        if s > 0:
+            a, b = oracle.downscale_by_2(a), oracle.downscale_by_2(b)
+        xa, xb = oracle.linear_to_xyb(a), oracle.linear_to_xyb(b)
+        xyb.append(np.concatenate([xa, xb], axis=0))
+        planes = []
+        for q in (xa * xa, xb * xb, xa * xb, xa, xb):
+            for c in range(3):
+                planes.append(oracle.blur_horizontal(q[c]))
+        hb.append(np.stack(planes))
+    return xyb, hb
+
+
+@pytest.mark.parametrize("w,h", [(160, 96), (203, 131)])
+def test_intermediate_planes_are_bit_identical_srgb8(oracle, w, h):
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    r, d = synth.make_pair_srgb8(w, h, frame=3, seed=5)
+    with tm.Ssimulacra2(w, h, tm.PixelFormat.SRGB8, batch=1, ring=1) as m:
+        rg, dg = r.cuda(), d.cuda()
+        t = m.compute(tm.DeviceFrame.packed(rg), tm.DeviceFrame.packed(dg))
+        score = m.get_score(t)
+        norms = m.get_norms(t)
+        ns = m.info().nscales
+        xyb_o, hb_o = _oracle_stages(oracle, oracle.linear_from_srgb8(r.numpy()), oracle.linear_from_srgb8(d.numpy()), ns)
+        for s in range(ns):
+            assert np.array_equal(_bits(m.debug_read(t, 0, s)), _bits(xyb_o[s])), f"XYB planes differ at scale {s}"
+            assert np.array_equal(_bits(m.debug_read(t, 1, s)), _bits(hb_o[s])), f"H-pass planes differ at scale {s}"
+    so, no, nso = oracle.ssimu2_srgb8(r.numpy(), d.numpy())
+    assert nso == ns
+    _assert_norms(norms, no, score, so)
+
+
+@pytest.mark.parametrize("bits", [8, 16])
+def test_intermediate_planes_are_bit_identical_yuv(oracle, bits):
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    w, h = 192, 108
+    rb, db, pitch, ch = synth.make_pair_yuv420(w, h, bits, frame=2, seed=9)
+    fmt = tm.PixelFormat.NV12 if bits == 8 else tm.PixelFormat.P016
+    with tm.Ssimulacra2(w, h, fmt, batch=1, ring=1) as m:
+        rg, dg = rb.cuda(), db.cuda()
+        t = m.compute(tm.DeviceFrame.yuv420(rg, pitch, ch), tm.DeviceFrame.yuv420(dg, pitch, ch))
+        score, norms, ns = m.get_score(t), m.get_norms(t), m.info().nscales
+        a = oracle.linear_from_yuv420(rb.numpy(), pitch, ch, w, h, bits)
+        b = oracle.linear_from_yuv420(db.numpy(), pitch, ch, w, h, bits)
+        xyb_o, hb_o = _oracle_stages(oracle, a, b, ns)
+        for s in range(ns):
+            assert np.array_equal(_bits(m.debug_read(t, 0, s)), _bits(xyb_o[s])), f"XYB planes differ at scale {s}"
+            assert np.array_equal(_bits(m.debug_read(t, 1, s)), _bits(hb_o[s])), f"H-pass planes differ at scale {s}"
+    so, no, _ = oracle.ssimu2_linear_planar(a, b)
+    _assert_norms(norms, no, score, so)
+
+
+# ------------------------------------------------------------------------------------------
+CASES = [
+    ("srgb8", 512, 512), ("srgb8", 64, 64), ("srgb8", 9, 300), ("srgb8", 301, 8), ("srgb8", 257, 255),
+    ("nv12", 640, 360), ("nv12", 1920, 1080), ("nv12", 66, 34),
+    ("p016", 640, 360), ("p016", 960, 540),
+    ("linear", 320, 200), ("srgb16", 200, 120), ("srgbf32", 200, 120),
+]
+
+
+def _make(kind, w, h, frame, seed, oracle):
+    """-> (ref_frame_builder(device tensors), oracle (score, norms, ns))"""
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    if kind in ("nv12", "p016"):
+        bits = 8 if kind == "nv12" else 16
+        rb, db, pitch, ch = synth.make_pair_yuv420(w, h, bits, frame=frame, seed=seed)
+        res = oracle.ssimu2_yuv420(rb.numpy(), db.numpy(), pitch, ch, w, h, bits)
+        fmt = tm.PixelFormat.NV12 if bits == 8 else tm.PixelFormat.P016
+        return fmt, (lambda t: tm.DeviceFrame.yuv420(t, pitch, ch)), rb, db, res
+    if kind == "srgb8":
+        r, d = synth.make_pair_srgb8(w, h, frame=frame, seed=seed)
+        return tm.PixelFormat.SRGB8, tm.DeviceFrame.packed, r, d, oracle.ssimu2_srgb8(r.numpy(), d.numpy())
+    if kind == "linear":
+        r, d = synth.make_pair_linearf32(w, h, frame=frame, seed=seed)
+        return tm.PixelFormat.LINEARF32, tm.DeviceFrame.packed, r, d, oracle.ssimu2_linearf32(r.numpy(), d.numpy())
+    r8, d8 = synth.make_pair_srgb8(w, h, frame=frame, seed=seed)
+    if kind == "srgb16":
+        r = (r8.to(torch.int32) * 257).to(torch.int16)  # bit pattern of u16 0..65535
+        d = (d8.to(torch.int32) * 257 + 13).clamp(0, 65535).to(torch.int16)
+        rn, dn = r.numpy().view(np.uint16), d.numpy().view(np.uint16)
+        res = oracle.ssimu2_linear_planar(oracle.linear_from_srgb16(rn), oracle.linear_from_srgb16(dn))
+        return tm.PixelFormat.SRGB16, tm.DeviceFrame.packed, r, d, res
+    r, d = r8.to(torch.float32) / 255.0, (d8.to(torch.float32) / 255.0 * 0.98 + 0.01)
+    res = oracle.ssimu2_linear_planar(oracle.linear_from_srgbf32(r.numpy()), oracle.linear_from_srgbf32(d.numpy()))
+    return tm.PixelFormat.SRGBF32, tm.DeviceFrame.packed, r, d, res
+
+
+@pytest.mark.parametrize("kind,w,h", CASES)
+def test_score_and_norms_match_oracle(oracle, kind, w, h):
+    tm = _tm()
+    fmt, mk, r, d, (so, no, nso) = _make(kind, w, h, frame=1, seed=3, oracle=oracle)
+    with tm.Ssimulacra2(w, h, fmt, batch=2, ring=2) as m:
+        rg, dg = r.cuda(), d.cuda()
+        t = m.compute(mk(rg), mk(dg))
+        score = m.get_score(t)
+        norms = m.get_norms(t)
+        assert m.info().nscales == nso
+    _assert_norms(norms, no, score, so)
+
+
+def test_identical_frames_score_100():
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    r, _ = synth.make_pair_srgb8(256, 256, frame=0, seed=1)
+    with tm.Ssimulacra2(256, 256, tm.PixelFormat.SRGB8) as m:
+        rg = r.cuda()
+        s = m.compute_sync(tm.DeviceFrame.packed(rg), tm.DeviceFrame.packed(rg))
+        assert s == 100.0
+
+
+def test_bt601_matrices_and_full_range(oracle):
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    w, h = 320, 180
+    rb, db, pitch, ch = synth.make_pair_yuv420(w, h, 8, frame=4, seed=2)
+    for matrix, name in [(tm.ColorMatrix.BT601_525, "bt601_525"), (tm.ColorMatrix.BT601_625, "bt601_625")]:
+        for full in (False, True):
+            so, no, _ = oracle.ssimu2_yuv420(rb.numpy(), db.numpy(), pitch, ch, w, h, 8, name, full)
+            with tm.Ssimulacra2(w, h, tm.PixelFormat.NV12, matrix=matrix, full_range=full) as m:
+                rg, dg = rb.cuda(), db.cuda()
+                t = m.compute(tm.DeviceFrame.yuv420(rg, pitch, ch), tm.DeviceFrame.yuv420(dg, pitch, ch))
+                _assert_norms(m.get_norms(t), no, m.get_score(t), so)
+
+
+def test_batches_ring_and_ticket_order(oracle):
+    """37 distinct pairs through batch=4 x ring=3: tickets come back in submission order, every score
+    equals the oracle's, and a partial last batch is flushed by get_score."""
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    w, h, n = 160, 120, 37
+    pairs = [synth.make_pair_srgb8(w, h, frame=i, seed=21) for i in range(n)]
+    expect = [oracle.ssimu2_srgb8(r.numpy(), d.numpy())[0] for r, d in pairs]
+    dev = [(r.cuda(), d.cuda()) for r, d in pairs]
+    with tm.Ssimulacra2(w, h, tm.PixelFormat.SRGB8, batch=4, ring=3) as m:
+        tickets = [m.compute(tm.DeviceFrame.packed(r), tm.DeviceFrame.packed(d)) for r, d in dev]
+        assert tickets == list(range(n))
+        got = [m.get_score(t) for t in tickets]
+        # device-side score stream holds the same values
+        ptr, cap = m.scores_device()
+        class _Ring:  # zero-copy view of the device score ring
+            __cuda_array_interface__ = {"shape": (cap,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        torch.cuda.synchronize()
+        assert torch.as_tensor(_Ring(), device="cuda")[:n].cpu().tolist() == got
+    assert max(abs(a - b) for a, b in zip(got, expect)) <= SCORE_ATOL
+    assert len(set(round(x, 6) for x in got)) > n // 2  # really distinct inputs
+
+
+def test_host_frames_entry_point(oracle):
+    """compute_from_cpu (Ssimulacra2::compute_from_cpu_srgb_sync, lib.rs:232-250) on pinned host buffers."""
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    w, h = 640, 360
+    rb, db, pitch, ch = synth.make_pair_yuv420(w, h, 16, frame=6, seed=4)
+    so, no, _ = oracle.ssimu2_yuv420(rb.numpy(), db.numpy(), pitch, ch, w, h, 16)
+    rp, dp = rb.pin_memory(), db.pin_memory()
+    with tm.Ssimulacra2(w, h, tm.PixelFormat.P016, batch=2, ring=2) as m:
+        ts = [m.compute_from_cpu(tm.DeviceFrame.yuv420(rp, pitch, ch), tm.DeviceFrame.yuv420(dp, pitch, ch)) for _ in range(5)]
+        scores = [m.get_score(t) for t in ts]
+        _assert_norms(m.get_norms(ts[-1]), no, scores[-1], so)
+    assert all(s == scores[0] for s in scores)
+
+
+def test_caller_stream_ordering(oracle):
+    """Frames produced on the caller's stream right before submit are seen by the scorer."""
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    w, h = 256, 144
+    r, d = synth.make_pair_srgb8(w, h, frame=9, seed=8)
+    so = oracle.ssimu2_srgb8(r.numpy(), d.numpy())[0]
+    side = torch.cuda.Stream()
+    with tm.Ssimulacra2(w, h, tm.PixelFormat.SRGB8, batch=1, ring=2) as m:
+        rg = torch.zeros_like(r, device="cuda")
+        dg = torch.zeros_like(d, device="cuda")
+        rp, dp = r.pin_memory(), d.pin_memory()
+        big = torch.empty(64 << 20, device="cuda")
+        with torch.cuda.stream(side):
+            for _ in range(10):
+                big.normal_()           # keep the stream busy so an unordered read would see zeros
+            rg.copy_(rp, non_blocking=True)
+            dg.copy_(dp, non_blocking=True)
+            t = m.compute(tm.DeviceFrame.packed(rg), tm.DeviceFrame.packed(dg), stream=side)
+        assert abs(m.get_score(t) - so) <= SCORE_ATOL
+
+
+def test_property_checks_at_full_size():
+    """4K P016 (BASELINE config 3), where the oracle would take minutes: size-independent properties.
+    identical -> 100; the score does not depend on the batch slot or on the neighbours in the batch;
+    a more distorted frame scores lower."""
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    w, h = 3840, 2160
+    rb, db, pitch, ch = synth.make_pair_yuv420(w, h, 16, frame=0, seed=1, device="cuda")
+    rb2, db2, _, _ = synth.make_pair_yuv420(w, h, 16, frame=1, seed=1, device="cuda")
+    F = lambda t: tm.DeviceFrame.yuv420(t, pitch, ch)
+    with tm.Ssimulacra2(w, h, tm.PixelFormat.P016, batch=4, ring=2) as m:
+        t = [m.compute(F(rb), F(db)), m.compute(F(rb), F(rb)), m.compute(F(rb2), F(db2)), m.compute(F(rb), F(db)),
+             m.compute(F(rb2), F(db2)), m.compute(F(rb), F(db2))]
+        s = [m.get_score(x) for x in t]
+    assert s[1] == 100.0
+    assert s[0] == s[3] and s[2] == s[4]
+    assert 0 < s[0] < 100 and 0 < s[2] < 100
+    assert s[5] < min(s[0], s[2])  # unrelated frame is far worse than its own distorted version

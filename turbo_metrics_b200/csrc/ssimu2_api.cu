@@ -36,7 +36,7 @@ struct Slot {
     cudaEvent_t ev_in = nullptr;      // dependency on the submitter's stream
     cudaEvent_t ev_done = nullptr;    // batch complete (results on host)
     cudaEvent_t ev_k[5] = {};         // per-kernel timing marks
-    float* lin = nullptr;             // [batch] pyramids
+    float* xyb = nullptr;             // [batch] XYB planes of all scales
     float* hb = nullptr;              // [batch] H-pass planes
     double* partials = nullptr;       // [batch][total_strips][18]
     double* norms_d = nullptr;        // [batch][108]
@@ -136,11 +136,12 @@ static void build_geo(ssimu2_handle* h)
 {
     Geo& g = h->geo;
     int w = (int)h->cfg.width, hh = (int)h->cfg.height;
-    long long lin_off = 0, hb_off = 0;
+    long long xyb_off = 0, hb_off = 0;
     int strips = 0, ns = 0;
     unsigned long long sum_px = 0, sum_px_ge1 = 0;
     for (int s = 0; s < kMaxScales; s++) {
-        if (w < 8 || hh < 8) break;  // cpu.rs:359
+        if (w < 8 || hh < 8) break;  // cpu.rs:359: tested on the size BEFORE this scale's downscale
+        if (s > 0) { w = (w + 1) / 2; hh = (hh + 1) / 2; }
         ScaleDesc& d = g.sc[s];
         d.w = w; d.h = hh;
         d.pitch = (w + 31) / 32 * 32;
@@ -148,18 +149,17 @@ static void build_geo(ssimu2_handle* h)
         d.n_strips = (w + kVCols - 1) / kVCols;
         d.strip0 = strips;
         strips += d.n_strips;
-        d.lin_off = lin_off;
-        if (s >= 1) lin_off += 6LL * hh * d.pitch;
+        d.xyb_off = xyb_off;
+        xyb_off += 6LL * hh * d.pitch;
         d.hb_off = hb_off;
         hb_off += 15LL * hh * d.pitch;
         sum_px += (unsigned long long)w * hh;
         if (s >= 1) sum_px_ge1 += (unsigned long long)w * hh;
         ns++;
-        w = (w + 1) / 2; hh = (hh + 1) / 2;
     }
     g.nscales = ns;
     g.total_strips = strips;
-    g.lin_stride = lin_off > 0 ? lin_off : 32;
+    g.xyb_stride = xyb_off;
     g.hb_stride = hb_off;
     g.items_h = 0; g.items_v = 0;
     for (int s = 0; s < ns; s++) { g.items_h += g.sc[s].n_bands; g.items_v += g.sc[s].n_strips; }
@@ -175,19 +175,18 @@ static int launch_batch_fmt(ssimu2_handle* h, Slot& sl)
     const uint32_t n = sl.count;
     cudaStream_t st = sl.stream;
     if (sl.timed) cudaEventRecord(sl.ev_k[0], st);
-    if (g.nscales > 1) {
+    {
         dim3 grid((g.sc[0].w + 63) / 64, (g.sc[0].h + 63) / 64, n);
-        k_pyramid<FMT><<<grid, 256, 0, st>>>(g, sl.in, sl.lin);
-        h->launches++;
+        k_frontend<FMT><<<grid, 256, 0, st>>>(g, sl.in, sl.xyb);
     }
     if (sl.timed) cudaEventRecord(sl.ev_k[1], st);
-    k_hpass<FMT><<<dim3(g.items_h, n), kHThreads, kHSmemBytes, st>>>(g, sl.in, sl.lin, sl.hb);
+    k_hpass<<<dim3(g.items_h, n), kHThreads, kHSmemBytes, st>>>(g, sl.xyb, sl.hb);
     if (sl.timed) cudaEventRecord(sl.ev_k[2], st);
-    k_vpass<FMT><<<dim3(g.items_v, n), kVThreads, 0, st>>>(g, sl.in, sl.lin, sl.hb, sl.partials);
+    k_vpass<<<dim3(g.items_v, n), kVThreads, 0, st>>>(g, sl.xyb, sl.hb, sl.partials);
     if (sl.timed) cudaEventRecord(sl.ev_k[3], st);
     k_finalize<<<n, 128, 0, st>>>(g, sl.partials, sl.norms_d, h->scores_ring_d, sl.first_ticket, kResultCap, sl.scores_d);
     if (sl.timed) cudaEventRecord(sl.ev_k[4], st);
-    h->launches += 3;
+    h->launches += 4;
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(sl.scores_h, sl.scores_d, n * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(sl.norms_h, sl.norms_d, (size_t)n * 108 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -358,30 +357,25 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
     CR(cudaMalloc(&h->scores_ring_d, kResultCap * sizeof(double)));
     CR(cudaMemset(h->scores_ring_d, 0, kResultCap * sizeof(double)));
     h->device_bytes += kResultCap * sizeof(double);
-    {
-        static const void* hfn[6] = {(const void*)k_hpass<kNV12>,   (const void*)k_hpass<kP016>,
-                                     (const void*)k_hpass<kSRGB8>,  (const void*)k_hpass<kSRGB16>,
-                                     (const void*)k_hpass<kSRGBF32>, (const void*)k_hpass<kLINEARF32>};
-        CR(cudaFuncSetAttribute(hfn[cfg->format], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBytes));
-    }
+    CR(cudaFuncSetAttribute((const void*)k_hpass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBytes));
     for (uint32_t i = 0; i < h->ring; i++) {
         Slot& sl = h->slots[i];
         const Geo& g = h->geo;
-        size_t lin_b = (size_t)g.lin_stride * h->batch * sizeof(float);
+        size_t xyb_b = (size_t)g.xyb_stride * h->batch * sizeof(float);
         size_t hb_b = (size_t)g.hb_stride * h->batch * sizeof(float);
         size_t part_b = (size_t)g.total_strips * 18 * h->batch * sizeof(double);
         CR(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         CR(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
         CR(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
         for (int k = 0; k < 5; k++) CR(cudaEventCreate(&sl.ev_k[k]));
-        CR(cudaMalloc(&sl.lin, lin_b));
+        CR(cudaMalloc(&sl.xyb, xyb_b));
         CR(cudaMalloc(&sl.hb, hb_b));
         CR(cudaMalloc(&sl.partials, part_b));
         CR(cudaMalloc(&sl.norms_d, (size_t)h->batch * 108 * sizeof(double)));
         CR(cudaMalloc(&sl.scores_d, (size_t)h->batch * sizeof(double)));
         CR(cudaMallocHost(&sl.norms_h, (size_t)h->batch * 108 * sizeof(double)));
         CR(cudaMallocHost(&sl.scores_h, (size_t)h->batch * sizeof(double)));
-        h->device_bytes += lin_b + hb_b + part_b + (size_t)h->batch * 109 * sizeof(double);
+        h->device_bytes += xyb_b + hb_b + part_b + (size_t)h->batch * 109 * sizeof(double);
         sl.timed = getenv("SSIMU2_NO_TIMING") == nullptr;
     }
     *out = h;
@@ -402,7 +396,7 @@ int ssimu2_destroy(ssimu2_t* h)
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
         for (int k = 0; k < 5; k++)
             if (sl.ev_k[k]) cudaEventDestroy(sl.ev_k[k]);
-        cudaFree(sl.lin); cudaFree(sl.hb); cudaFree(sl.partials); cudaFree(sl.norms_d); cudaFree(sl.scores_d);
+        cudaFree(sl.xyb); cudaFree(sl.hb); cudaFree(sl.partials); cudaFree(sl.norms_d); cudaFree(sl.scores_d);
         cudaFree(sl.staging);
         if (sl.norms_h) cudaFreeHost(sl.norms_h);
         if (sl.scores_h) cudaFreeHost(sl.scores_h);
@@ -605,9 +599,8 @@ int ssimu2_debug_read(ssimu2_t* h, uint64_t ticket, int what, int scale, float* 
     int planes;
     const float* src;
     if (what == 0) {
-        if (scale < 1) return SSIMU2_E_INVALID;
         planes = 6;
-        src = sl.lin + idx * h->geo.lin_stride + sd.lin_off;
+        src = sl.xyb + idx * h->geo.xyb_stride + sd.xyb_off;
     } else if (what == 1) {
         planes = 15;
         src = sl.hb + idx * h->geo.hb_stride + sd.hb_off;
@@ -618,6 +611,27 @@ int ssimu2_debug_read(ssimu2_t* h, uint64_t ticket, int what, int scale, float* 
     CU_TRY(cudaMemcpy2D(out, (size_t)sd.w * sizeof(float), src, (size_t)sd.pitch * sizeof(float),
                         (size_t)sd.w * sizeof(float), (size_t)planes * sd.h, cudaMemcpyDeviceToHost));
     return SSIMU2_OK;
+}
+
+int ssimu2_debug_math(int op, const float* in, float y, float* out, size_t n)
+{
+    if (!in || !out || op < 0 || op > 1) return SSIMU2_E_INVALID;
+    if (n == 0) return SSIMU2_OK;
+    float *din = nullptr, *dout = nullptr;
+    if (cudaMalloc(&din, n * sizeof(float)) != cudaSuccess || cudaMalloc(&dout, n * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(din);
+        return SSIMU2_E_NOMEM;
+    }
+    int rc = (int)cudaMemcpy(din, in, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (!rc) {
+        k_debug_math<<<(unsigned)((n + 255) / 256), 256>>>(op, din, y, dout, n);
+        rc = (int)cudaGetLastError();
+    }
+    if (!rc) rc = (int)cudaMemcpy(out, dout, n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(din);
+    cudaFree(dout);
+    return rc;
 }
 
 int ssimu2_last_batch_ms(ssimu2_t* h, float ms[4])

@@ -1,20 +1,23 @@
 // ssimu2_kernels.cuh -- device code of the B200-native SSIMULACRA2 frame-pair scorer (sm_100a).
 //
 // Pipeline per batch of frame pairs (4 launches, every launch covers all frames and all 6 scales):
-//   k_pyramid  : source pair -> linear RGB -> levels 1..5 of the 2x box pyramid (planar f32)
-//   k_hpass    : per scale: (source | pyramid level) -> XYB -> 5 products -> HORIZONTAL recursive
-//                Gaussian of {ref^2, dis^2, ref*dis, ref, dis} x 3 channels -> 15 planes
+//   k_frontend : source pair -> linear RGB -> 2x box pyramid (kept on chip) -> XYB planes of all scales
+//   k_hpass    : per scale: XYB -> 5 products -> HORIZONTAL recursive Gaussian of
+//                {ref^2, dis^2, ref*dis, ref, dis} x 3 channels -> 15 planes
 //   k_vpass    : per scale: VERTICAL recursive Gaussian of the 15 planes, fused with the SSIM /
 //                artifact / detail-loss maps and their L1 / L4 partial sums (f64)
 //   k_finalize : partial sums -> 108 norms -> weighted sum -> score (f64)
 //
-// Arithmetic contract: every operation that feeds the recursive filters replicates, operation for
-// operation, the reference's CPU implementation (crates/ssimulacra2-cuda/examples/cpu.rs) so that
-// the IIR outputs are bit-identical given identical inputs; compile with -fmad=false, fused ops are
-// explicit fmaf().  The GPU reference kernels this replaces are cited at each function.
+// Arithmetic contract: everything that feeds the recursive filters replicates, operation for
+// operation, the reference's CPU implementation (crates/ssimulacra2-cuda/examples/cpu.rs), including
+// its libm cbrtf / powf (exact_math.cuh), so the filter inputs and outputs are bit-identical to the
+// CPU path; compile with -fmad=false, fused ops are explicit fmaf()/fma().  The GPU reference
+// kernels each function replaces are cited at the function.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "exact_math.cuh"
 
 namespace ssimu2 {
 
@@ -28,7 +31,7 @@ struct ScaleDesc {
     int n_bands;           // H-pass work items (32-row bands)
     int n_strips;          // V-pass work items (column strips)
     int strip0;            // index of this scale's first strip in the partial-sum table
-    long long lin_off;     // float offset of level s (s >= 1) inside a slot's pyramid buffer: [2][3][h][pitch]
+    long long xyb_off;     // float offset of scale s inside a slot's XYB buffer: [2 img][3 ch][h][pitch]
     long long hb_off;      // float offset of scale s inside a slot's H-pass buffer: [15][h][pitch]
 };
 
@@ -42,7 +45,7 @@ struct Geo {
     int nscales;
     int items_h, items_v;        // work items per frame (all scales)
     int total_strips;            // partial-sum rows per frame
-    long long lin_stride;        // floats per slot
+    long long xyb_stride;        // floats per slot
     long long hb_stride;         // floats per slot
     YuvCoef coef;
 };
@@ -78,26 +81,29 @@ __device__ const float kSrgb8Lut[256] = {
 // ------------------------------------------------------------------------------------------
 // colour front-end
 // ------------------------------------------------------------------------------------------
+__device__ const exact_math::PowfTables kPowfTablesInit = {{EM_POWF_LOG2_TAB}, {EM_EXP2F_TAB}};
+
 // BT709::eotf, cuda-colorspace-kernel/src/lib.rs:220-236 (same body for the BT601 variants).
-// The reference uses __nv_fast_powf; the accurate powf keeps us within an ulp or two of the oracle.
-__device__ __forceinline__ float bt709_eotf(float v)
+// The reference uses __nv_fast_powf (not reproducible on a CPU); the oracle and this kernel both use
+// glibc's powf, bit for bit (exact_math.cuh).
+__device__ __forceinline__ float bt709_eotf(float v, const exact_math::PowfTables& T)
 {
     const float BETA = 0.018053968510807f;
     const float ALPHA = 1.0f + 5.5f * BETA;
     const float THRESHOLD = 0.08124285829863521110029445797874f;
     if (v >= THRESHOLD)
-        return powf((v + (ALPHA - 1.0f)) / ALPHA, 1.0f / 0.45f);
+        return exact_math::powf_glibc((v + (ALPHA - 1.0f)) / ALPHA, 1.0f / 0.45f, T);
     return v / 4.5f;
 }
 
 // srgb_inverse_oetf, cuda-colorspace-kernel/src/srgb.rs:40-48.
-__device__ __forceinline__ float srgb_inverse_oetf(float x)
+__device__ __forceinline__ float srgb_inverse_oetf(float x, const exact_math::PowfTables& T)
 {
     const float SRGB_ALPHA = 1.0550107f;
     const float SRGB_BETA = 0.0030412825f;
     if (x < 12.92f * SRGB_BETA)
         return x / 12.92f;
-    return powf((x + (SRGB_ALPHA - 1.0f)) / SRGB_ALPHA, 2.4f);
+    return exact_math::powf_glibc((x + (SRGB_ALPHA - 1.0f)) / SRGB_ALPHA, 2.4f, T);
 }
 
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
@@ -106,7 +112,8 @@ __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f),
 // (cuda-colorspace-kernel/src/biplanar.rs:7-70), srgb_to_linear_u8_lookup / srgb_to_linear::<16> /
 // srgb_to_linear_f32 (srgb.rs:50-127).  x, y must be inside the frame.
 template <int FMT>
-__device__ __forceinline__ void load_px(const FrameIn& f, int x, int y, const YuvCoef& k, float& r, float& g, float& b)
+__device__ __forceinline__ void load_px(const FrameIn& f, int x, int y, const YuvCoef& k, const exact_math::PowfTables& T,
+                                        float& r, float& g, float& b)
 {
     if constexpr (FMT == kNV12 || FMT == kP016) {
         int Y, cbi, cri;
@@ -127,9 +134,9 @@ __device__ __forceinline__ void load_px(const FrameIn& f, int x, int y, const Yu
         float g_ = fmaf(k.g1, cb, k.g2 * cr);
         float b_ = k.b * cb;
         float luma = (float)(max(Y, k.luma_min) - k.luma_min) * k.y;
-        r = clamp01(bt709_eotf(luma + r_));
-        g = clamp01(bt709_eotf(luma + g_));
-        b = clamp01(bt709_eotf(luma + b_));
+        r = clamp01(bt709_eotf(luma + r_, T));
+        g = clamp01(bt709_eotf(luma + g_, T));
+        b = clamp01(bt709_eotf(luma + b_, T));
     } else if constexpr (FMT == kSRGB8) {
         const uint8_t* p = f.p0 + (size_t)y * f.pitch + 3 * x;
         r = kSrgb8Lut[__ldg(p)];
@@ -137,19 +144,20 @@ __device__ __forceinline__ void load_px(const FrameIn& f, int x, int y, const Yu
         b = kSrgb8Lut[__ldg(p + 2)];
     } else if constexpr (FMT == kSRGB16) {
         const uint16_t* p = reinterpret_cast<const uint16_t*>(f.p0 + (size_t)y * f.pitch) + 3 * x;
-        r = srgb_inverse_oetf((float)__ldg(p) / 65535.0f);
-        g = srgb_inverse_oetf((float)__ldg(p + 1) / 65535.0f);
-        b = srgb_inverse_oetf((float)__ldg(p + 2) / 65535.0f);
+        r = srgb_inverse_oetf((float)__ldg(p) / 65535.0f, T);
+        g = srgb_inverse_oetf((float)__ldg(p + 1) / 65535.0f, T);
+        b = srgb_inverse_oetf((float)__ldg(p + 2) / 65535.0f, T);
     } else {
         const float* p = reinterpret_cast<const float*>(f.p0 + (size_t)y * f.pitch) + 3 * x;
         r = __ldg(p); g = __ldg(p + 1); b = __ldg(p + 2);
         if constexpr (FMT == kSRGBF32) {
-            r = srgb_inverse_oetf(r); g = srgb_inverse_oetf(g); b = srgb_inverse_oetf(b);
+            r = srgb_inverse_oetf(r, T); g = srgb_inverse_oetf(g, T); b = srgb_inverse_oetf(b, T);
         }
     }
 }
 
-// linear RGB -> rescaled XYB.  cpu.rs:421-496 (== ssimulacra2-cuda-kernel/src/xyb.rs:3-102).
+// linear RGB -> rescaled XYB.  cpu.rs:421-496 (== ssimulacra2-cuda-kernel/src/xyb.rs:3-102),
+// with the CPU path's libm cbrtf reproduced exactly.
 __device__ __forceinline__ void linear_to_xyb(float r, float g, float b, float& X, float& Y, float& B)
 {
     const float K_M02 = 0.078f, K_M00 = 0.30f, K_M01 = 1.0f - K_M02 - K_M00;
@@ -160,9 +168,9 @@ __device__ __forceinline__ void linear_to_xyb(float r, float g, float b, float& 
     float rg = fmaf(K_M00, r, fmaf(K_M01, g, fmaf(K_M02, b, K_B0)));
     float gr = fmaf(K_M10, r, fmaf(K_M11, g, fmaf(K_M12, b, K_B0)));
     float bb = fmaf(K_M20, r, fmaf(K_M21, g, fmaf(K_M22, b, K_B0)));
-    rg = cbrtf(fmaxf(rg, 0.0f)) - K_B0_ROOT;
-    gr = cbrtf(fmaxf(gr, 0.0f)) - K_B0_ROOT;
-    bb = cbrtf(fmaxf(bb, 0.0f)) - K_B0_ROOT;
+    rg = exact_math::cbrtf_glibc(fmaxf(rg, 0.0f)) - K_B0_ROOT;
+    gr = exact_math::cbrtf_glibc(fmaxf(gr, 0.0f)) - K_B0_ROOT;
+    bb = exact_math::cbrtf_glibc(fmaxf(bb, 0.0f)) - K_B0_ROOT;
     float x = 0.5f * (rg - gr);
     float y = 0.5f * (rg + gr);
     X = fmaf(x, 14.0f, 0.42f);
@@ -170,39 +178,42 @@ __device__ __forceinline__ void linear_to_xyb(float r, float g, float b, float& 
     B = (bb - y) + 0.55f;
 }
 
-// Linear RGB of pixel (x, y) of image `img` (0 = ref, 1 = dis) at scale s: the source frame at
-// scale 0, the pyramid level otherwise.
-template <int FMT>
-__device__ __forceinline__ void load_linear(const Geo& g, const BatchIn& in, const float* lin_slot, int frame, int s,
-                                            int img, int x, int y, float& r, float& gg, float& b)
+// ------------------------------------------------------------------------------------------
+// k_frontend: colour conversion + linear-RGB pyramid + XYB of every scale.
+// Replaces the colour conversion kernels, downscale_by_2 (ssimulacra2-cuda-kernel/src/downscale.rs:4-35,
+// host loop ssimulacra2-cuda/src/lib.rs:162-183) and linear_to_xyb_packed (xyb.rs:82-102, lib.rs:188-210);
+// follows cpu.rs:545-579 (box sum order (0,0),(1,0),(0,1),(1,1), edge clamp min(src-1), x0.25) and
+// cpu.rs:363-377 (downscale in LINEAR RGB, XYB recomputed per scale).
+// One CTA = one 64x64 source tile of one frame, both images; 256 threads, thread = 4x4 source px.
+// The pyramid levels never leave the chip: only XYB planes are written.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float box4(float a, float b, float c, float d) { return ((((0.0f + a) + b) + c) + d) * 0.25f; }
+
+__device__ __forceinline__ void store_xyb(float* plane0, size_t plane, size_t off, float r, float g, float b)
 {
-    if (s == 0) {
-        load_px<FMT>(img ? in.dis[frame] : in.ref[frame], x, y, g.coef, r, gg, b);
-    } else {
-        const ScaleDesc& sd = g.sc[s];
-        size_t plane = (size_t)sd.h * sd.pitch;
-        const float* p = lin_slot + sd.lin_off + (size_t)img * 3 * plane + (size_t)y * sd.pitch + x;
-        r = __ldg(p); gg = __ldg(p + plane); b = __ldg(p + 2 * plane);
-    }
+    float X, Y, B;
+    linear_to_xyb(r, g, b, X, Y, B);
+    plane0[off] = X;
+    plane0[plane + off] = Y;
+    plane0[2 * plane + off] = B;
 }
 
-// ------------------------------------------------------------------------------------------
-// k_pyramid: levels 1..5 of the linear-RGB pyramid.  Replaces downscale_by_2
-// (ssimulacra2-cuda-kernel/src/downscale.rs:4-35, host loop ssimulacra2-cuda/src/lib.rs:162-183)
-// and the colour conversion kernels; follows cpu.rs:545-579 (sum order (0,0),(1,0),(0,1),(1,1),
-// edge clamp min(src-1), x0.25).
-// One CTA = one 64x64 source tile of one frame, both images; 256 threads, thread = 4x4 source px.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float box4(float a, float b, float c, float d) { return (((0.0f + a) + b) + c + d) * 0.25f; }
-
 template <int FMT>
-__global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Geo g, const __grid_constant__ BatchIn in, float* __restrict__ lin_base)
+__global__ void __launch_bounds__(256) k_frontend(const __grid_constant__ Geo g, const __grid_constant__ BatchIn in,
+                                                  float* __restrict__ xyb_base)
 {
+    __shared__ exact_math::PowfTables T;
     __shared__ float s2[6][16][16];
     __shared__ float s3[6][8][8];
     __shared__ float s4[6][4][4];
+    {
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(&kPowfTablesInit);
+        uint64_t* dst = reinterpret_cast<uint64_t*>(&T);
+        for (int i = threadIdx.x; i < (int)(sizeof(exact_math::PowfTables) / 8); i += 256) dst[i] = src[i];
+    }
+    __syncthreads();
     const int frame = blockIdx.z;
-    float* lin_slot = lin_base + (size_t)frame * g.lin_stride;
+    float* xyb_slot = xyb_base + (size_t)frame * g.xyb_stride;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int W0 = g.sc[0].w, H0 = g.sc[0].h;
     const int bx = blockIdx.x * 64 + tx * 4, by = blockIdx.y * 64 + ty * 4;  // source block origin
@@ -210,135 +221,171 @@ __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Geo g, 
 
     for (int img = 0; img < 2; img++) {
         const FrameIn& f = img ? in.dis[frame] : in.ref[frame];
-        float l1[3][2][2];
-        const int W1 = g.sc[1].w, H1 = g.sc[1].h;
-        // level 1: 2x2 outputs per thread
+        // ---- scale 0: 4x4 source pixels -> linear (registers) -> XYB planes
+        float lin[3][4][4];
+        {
+            const ScaleDesc& sd = g.sc[0];
+            const size_t plane = (size_t)sd.h * sd.pitch;
+            float* dst = xyb_slot + sd.xyb_off + (size_t)img * 3 * plane;
 #pragma unroll
-        for (int j = 0; j < 2; j++)
+            for (int j = 0; j < 4; j++) {
+                const int y = by + j;
+                float X[4], Y[4], B[4];
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
-                int ox = bx / 2 + i, oy = by / 2 + j;
-                float acc[3][4];
-                bool valid = ns > 1 && ox < W1 && oy < H1;
-                if (valid) {
-#pragma unroll
-                    for (int iy = 0; iy < 2; iy++)
-#pragma unroll
-                        for (int ix = 0; ix < 2; ix++) {
-                            int x = min(2 * ox + ix, W0 - 1), y = min(2 * oy + iy, H0 - 1);
-                            load_px<FMT>(f, x, y, g.coef, acc[0][iy * 2 + ix], acc[1][iy * 2 + ix], acc[2][iy * 2 + ix]);
-                        }
+                for (int i = 0; i < 4; i++) {
+                    const int x = bx + i;
+                    float r = 0.f, gg = 0.f, b = 0.f;
+                    X[i] = Y[i] = B[i] = 0.f;
+                    if (x < W0 && y < H0) {
+                        load_px<FMT>(f, x, y, g.coef, T, r, gg, b);
+                        linear_to_xyb(r, gg, b, X[i], Y[i], B[i]);
+                    }
+                    lin[0][j][i] = r; lin[1][j][i] = gg; lin[2][j][i] = b;
                 }
+                if (y < H0) {
+                    const size_t off = (size_t)y * sd.pitch + bx;
+                    if (bx + 3 < W0) {
+                        *reinterpret_cast<float4*>(dst + off) = make_float4(X[0], X[1], X[2], X[3]);
+                        *reinterpret_cast<float4*>(dst + plane + off) = make_float4(Y[0], Y[1], Y[2], Y[3]);
+                        *reinterpret_cast<float4*>(dst + 2 * plane + off) = make_float4(B[0], B[1], B[2], B[3]);
+                    } else {
 #pragma unroll
-                for (int c = 0; c < 3; c++)
-                    l1[c][j][i] = valid ? box4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]) : 0.0f;
-            }
-        if (ns > 1) {
-            const ScaleDesc& sd = g.sc[1];
-            size_t plane = (size_t)sd.h * sd.pitch;
-            float* dst = lin_slot + sd.lin_off + (size_t)img * 3 * plane;
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-#pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    int ox = bx / 2, oy = by / 2 + j;
-                    if (oy < H1) {
-                        if (ox + 1 < W1)
-                            *reinterpret_cast<float2*>(dst + c * plane + (size_t)oy * sd.pitch + ox) =
-                                make_float2(l1[c][j][0], l1[c][j][1]);
-                        else if (ox < W1)
-                            dst[c * plane + (size_t)oy * sd.pitch + ox] = l1[c][j][0];
+                        for (int i = 0; i < 4; i++)
+                            if (bx + i < W0) {
+                                dst[off + i] = X[i]; dst[plane + off + i] = Y[i]; dst[2 * plane + off + i] = B[i];
+                            }
                     }
                 }
-        }
-        // level 2: one output per thread, from registers
-        if (ns > 2) {
-            const ScaleDesc& sd = g.sc[2];
-            int ox = bx / 4, oy = by / 4;
-            bool valid = ox < sd.w && oy < sd.h;
-            int i1 = (2 * ox + 1 <= W1 - 1) ? 1 : 0, j1 = (2 * oy + 1 <= H1 - 1) ? 1 : 0;
-            size_t plane = (size_t)sd.h * sd.pitch;
-            float* dst = lin_slot + sd.lin_off + (size_t)img * 3 * plane;
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                float v = 0.0f;
-                if (valid) {
-                    float a = l1[c][0][0], b = i1 ? l1[c][0][1] : l1[c][0][0];
-                    float cc = j1 ? l1[c][1][0] : l1[c][0][0];
-                    float d = j1 ? (i1 ? l1[c][1][1] : l1[c][1][0]) : (i1 ? l1[c][0][1] : l1[c][0][0]);
-                    v = box4(a, b, cc, d);
-                    dst[c * plane + (size_t)oy * sd.pitch + ox] = v;
-                }
-                s2[img * 3 + c][ty][tx] = v;
             }
         }
+        // ---- level 1: 2x2 outputs per thread
+        float l1[3][2][2];
+        const int W1 = g.sc[1].w, H1 = g.sc[1].h;
+        if (ns > 1) {
+            const ScaleDesc& sd = g.sc[1];
+            const size_t plane = (size_t)sd.h * sd.pitch;
+            float* dst = xyb_slot + sd.xyb_off + (size_t)img * 3 * plane;
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const int ox = bx / 2 + i, oy = by / 2 + j;
+                    const bool valid = ox < W1 && oy < H1;
+                    const bool cx = (bx + 2 * i + 1 <= W0 - 1), cy = (by + 2 * j + 1 <= H0 - 1);
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        float a = lin[c][2 * j][2 * i];
+                        float b = cx ? lin[c][2 * j][2 * i + 1] : a;
+                        float cc = cy ? lin[c][2 * j + 1][2 * i] : a;
+                        float d = cy ? (cx ? lin[c][2 * j + 1][2 * i + 1] : lin[c][2 * j + 1][2 * i]) : b;
+                        l1[c][j][i] = valid ? box4(a, b, cc, d) : 0.0f;
+                    }
+                    if (valid) store_xyb(dst, plane, (size_t)oy * sd.pitch + ox, l1[0][j][i], l1[1][j][i], l1[2][j][i]);
+                }
+        }
+        // ---- level 2: one output per thread, from registers
+        if (ns > 2) {
+            const ScaleDesc& sd = g.sc[2];
+            const int ox = bx / 4, oy = by / 4;
+            const bool valid = ox < sd.w && oy < sd.h;
+            const bool cx = (2 * ox + 1 <= W1 - 1), cy = (2 * oy + 1 <= H1 - 1);
+            const size_t plane = (size_t)sd.h * sd.pitch;
+            float* dst = xyb_slot + sd.xyb_off + (size_t)img * 3 * plane;
+            float v[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                float a = l1[c][0][0];
+                float b = cx ? l1[c][0][1] : a;
+                float cc = cy ? l1[c][1][0] : a;
+                float d = cy ? (cx ? l1[c][1][1] : l1[c][1][0]) : b;
+                v[c] = valid ? box4(a, b, cc, d) : 0.0f;
+                s2[img * 3 + c][ty][tx] = v[c];
+            }
+            if (valid) store_xyb(dst, plane, (size_t)oy * sd.pitch + ox, v[0], v[1], v[2]);
+        }
     }
-    // levels 3..5 through shared memory (6 = 2 images x 3 channels)
+    // ---- levels 3..5 through shared memory; one thread = one output pixel of one image
     if (ns > 3) {
         __syncthreads();
         const ScaleDesc& sp = g.sc[2];
         const ScaleDesc& sd = g.sc[3];
-        size_t plane = (size_t)sd.h * sd.pitch;
-        for (int idx = threadIdx.x; idx < 6 * 64; idx += 256) {
-            int pc = idx >> 6, ly = (idx >> 3) & 7, lx = idx & 7;
-            int ox = blockIdx.x * 8 + lx, oy = blockIdx.y * 8 + ly;
-            float v = 0.0f;
-            if (ox < sd.w && oy < sd.h) {
-                int i1 = (2 * ox + 1 <= sp.w - 1) ? 1 : 0, j1 = (2 * oy + 1 <= sp.h - 1) ? 1 : 0;
-                v = box4(s2[pc][2 * ly][2 * lx], s2[pc][2 * ly][2 * lx + i1], s2[pc][2 * ly + j1][2 * lx],
-                         s2[pc][2 * ly + j1][2 * lx + i1]);
-                lin_slot[sd.lin_off + (size_t)pc * plane + (size_t)oy * sd.pitch + ox] = v;
+        const size_t plane = (size_t)sd.h * sd.pitch;
+        if (threadIdx.x < 128) {
+            const int img = threadIdx.x >> 6, ly = (threadIdx.x >> 3) & 7, lx = threadIdx.x & 7;
+            const int ox = blockIdx.x * 8 + lx, oy = blockIdx.y * 8 + ly;
+            const bool valid = ox < sd.w && oy < sd.h;
+            const int i1 = (2 * ox + 1 <= sp.w - 1) ? 1 : 0, j1 = (2 * oy + 1 <= sp.h - 1) ? 1 : 0;
+            float v[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const int pc = img * 3 + c;
+                v[c] = valid ? box4(s2[pc][2 * ly][2 * lx], s2[pc][2 * ly][2 * lx + i1], s2[pc][2 * ly + j1][2 * lx],
+                                    s2[pc][2 * ly + j1][2 * lx + i1])
+                             : 0.0f;
+                s3[pc][ly][lx] = v[c];
             }
-            s3[pc][ly][lx] = v;
+            if (valid)
+                store_xyb(xyb_slot + sd.xyb_off + (size_t)img * 3 * plane, plane, (size_t)oy * sd.pitch + ox, v[0], v[1], v[2]);
         }
     }
     if (ns > 4) {
         __syncthreads();
         const ScaleDesc& sp = g.sc[3];
         const ScaleDesc& sd = g.sc[4];
-        size_t plane = (size_t)sd.h * sd.pitch;
-        for (int idx = threadIdx.x; idx < 6 * 16; idx += 256) {
-            int pc = idx >> 4, ly = (idx >> 2) & 3, lx = idx & 3;
-            int ox = blockIdx.x * 4 + lx, oy = blockIdx.y * 4 + ly;
-            float v = 0.0f;
-            if (ox < sd.w && oy < sd.h) {
-                int i1 = (2 * ox + 1 <= sp.w - 1) ? 1 : 0, j1 = (2 * oy + 1 <= sp.h - 1) ? 1 : 0;
-                v = box4(s3[pc][2 * ly][2 * lx], s3[pc][2 * ly][2 * lx + i1], s3[pc][2 * ly + j1][2 * lx],
-                         s3[pc][2 * ly + j1][2 * lx + i1]);
-                lin_slot[sd.lin_off + (size_t)pc * plane + (size_t)oy * sd.pitch + ox] = v;
+        const size_t plane = (size_t)sd.h * sd.pitch;
+        if (threadIdx.x < 32) {
+            const int img = threadIdx.x >> 4, ly = (threadIdx.x >> 2) & 3, lx = threadIdx.x & 3;
+            const int ox = blockIdx.x * 4 + lx, oy = blockIdx.y * 4 + ly;
+            const bool valid = ox < sd.w && oy < sd.h;
+            const int i1 = (2 * ox + 1 <= sp.w - 1) ? 1 : 0, j1 = (2 * oy + 1 <= sp.h - 1) ? 1 : 0;
+            float v[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const int pc = img * 3 + c;
+                v[c] = valid ? box4(s3[pc][2 * ly][2 * lx], s3[pc][2 * ly][2 * lx + i1], s3[pc][2 * ly + j1][2 * lx],
+                                    s3[pc][2 * ly + j1][2 * lx + i1])
+                             : 0.0f;
+                s4[pc][ly][lx] = v[c];
             }
-            s4[pc][ly][lx] = v;
+            if (valid)
+                store_xyb(xyb_slot + sd.xyb_off + (size_t)img * 3 * plane, plane, (size_t)oy * sd.pitch + ox, v[0], v[1], v[2]);
         }
     }
     if (ns > 5) {
         __syncthreads();
         const ScaleDesc& sp = g.sc[4];
         const ScaleDesc& sd = g.sc[5];
-        size_t plane = (size_t)sd.h * sd.pitch;
-        for (int idx = threadIdx.x; idx < 6 * 4; idx += 256) {
-            int pc = idx >> 2, ly = (idx >> 1) & 1, lx = idx & 1;
-            int ox = blockIdx.x * 2 + lx, oy = blockIdx.y * 2 + ly;
+        const size_t plane = (size_t)sd.h * sd.pitch;
+        if (threadIdx.x < 8) {
+            const int img = threadIdx.x >> 2, ly = (threadIdx.x >> 1) & 1, lx = threadIdx.x & 1;
+            const int ox = blockIdx.x * 2 + lx, oy = blockIdx.y * 2 + ly;
             if (ox < sd.w && oy < sd.h) {
-                int i1 = (2 * ox + 1 <= sp.w - 1) ? 1 : 0, j1 = (2 * oy + 1 <= sp.h - 1) ? 1 : 0;
-                float v = box4(s4[pc][2 * ly][2 * lx], s4[pc][2 * ly][2 * lx + i1], s4[pc][2 * ly + j1][2 * lx],
-                               s4[pc][2 * ly + j1][2 * lx + i1]);
-                lin_slot[sd.lin_off + (size_t)pc * plane + (size_t)oy * sd.pitch + ox] = v;
+                const int i1 = (2 * ox + 1 <= sp.w - 1) ? 1 : 0, j1 = (2 * oy + 1 <= sp.h - 1) ? 1 : 0;
+                float v[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const int pc = img * 3 + c;
+                    v[c] = box4(s4[pc][2 * ly][2 * lx], s4[pc][2 * ly][2 * lx + i1], s4[pc][2 * ly + j1][2 * lx],
+                                s4[pc][2 * ly + j1][2 * lx + i1]);
+                }
+                store_xyb(xyb_slot + sd.xyb_off + (size_t)img * 3 * plane, plane, (size_t)oy * sd.pitch + ox, v[0], v[1], v[2]);
             }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// k_hpass: XYB + products + horizontal recursive Gaussian.
-// Replaces linear_to_xyb_packed (xyb.rs:82-102), nppiMul x3 (ssimulacra2-cuda/src/lib.rs:300-317)
-// and one of the two blur_plane_pass_fused launches + its nppiTranspose x5 (lib.rs:328-361).
-// Follows RecursiveGaussian::horizontal_row, cpu.rs:967-1022.
+// k_hpass: products + horizontal recursive Gaussian.
+// Replaces nppiMul x3 (ssimulacra2-cuda/src/lib.rs:300-317) and one of the two
+// blur_plane_pass_fused launches + its nppiTranspose x5 (lib.rs:328-361).
+// Follows image_multiply cpu.rs:537-543 and RecursiveGaussian::horizontal_row cpu.rs:967-1022.
 //
 // CTA = one 32-row band of one scale of one frame; 512 threads.
-//   convert : thread = one 2x2 quad of one image of the 32x32 chunk -> XYB -> smem (zero outside the row)
-//   scan    : warp p (0..14) = plane (quantity q = p/3, channel c = p%3), lane = row; walks the chunk
-//             4 columns per 128-bit smem access, filter state in registers across chunks
-//   store   : all threads, 128-bit coalesced stores of the 15x32x32 output tile
+//   load  : all threads, 128-bit coalesced loads of the next 6 x 32 x 32 XYB chunk into registers
+//           (zero outside the row = the filter's zero padding), parked in shared memory after the scan
+//   scan  : warp p (0..14) = plane (quantity q = p/3, channel c = p%3), lane = row; walks the chunk
+//           4 columns per 128-bit smem access, filter state in registers across chunks
+//   store : all threads, 128-bit coalesced stores of the 15 x 32 x 32 output tile
 // Step t consumes x[t] (right tap, index n+4) and x[t-10] (left tap, n-6) and emits y[t-4]
 // (n = t-4, cpu.rs:976-984).  Chunk k (k = -1, 0, ...) covers steps 32k+4 .. 32k+35, i.e. outputs
 // 32k .. 32k+31; chunk -1 only warms the state with x[0..3] (its other inputs are the zero padding).
@@ -347,9 +394,10 @@ constexpr int kHRows = 32;
 constexpr int kHCols = 32;
 constexpr int kHPitch = 36;  // floats; 144 B = 9 x 16 B -> conflict-free 128-bit row-per-lane access
 constexpr int kHThreads = 512;
-constexpr int kHSmemIn = 2 * 2 * 3 * kHRows * kHPitch;  // [buf][img][ch][row][col]
-constexpr int kHSmemOut = 15 * kHRows * kHPitch;        // [plane][row][col]
+constexpr int kHSmemIn = 2 * 6 * kHRows * kHPitch;  // [buf][img*3+ch][row][col]
+constexpr int kHSmemOut = 15 * kHRows * kHPitch;    // [plane][row][col]
 constexpr size_t kHSmemBytes = (size_t)(kHSmemIn + kHSmemOut) * sizeof(float);
+constexpr int kHLoadsPerThread = 6 * kHRows * (kHCols / 4) / kHThreads;  // 3
 
 struct HState {
     float p1, p3, p5, pp1, pp3, pp5;
@@ -400,8 +448,7 @@ __device__ __forceinline__ void hscan_chunk(const float* __restrict__ s_ref, con
     for (int i = 0; i < 12; i++) hist[i] = win[kHCols + i];
 }
 
-template <int FMT>
-__global__ void __launch_bounds__(kHThreads) k_hpass(const __grid_constant__ Geo g, const __grid_constant__ BatchIn in, const float* __restrict__ lin_base,
+__global__ void __launch_bounds__(kHThreads) k_hpass(const __grid_constant__ Geo g, const float* __restrict__ xyb_base,
                                                      float* __restrict__ hb_base)
 {
     extern __shared__ __align__(16) float smem[];
@@ -413,51 +460,55 @@ __global__ void __launch_bounds__(kHThreads) k_hpass(const __grid_constant__ Geo
     while (item >= g.sc[s].n_bands) { item -= g.sc[s].n_bands; s++; }
     const ScaleDesc sd = g.sc[s];
     const int row0 = item * kHRows;
-    const float* lin_slot = lin_base + (size_t)frame * g.lin_stride;
-    float* hb = hb_base + (size_t)frame * g.hb_stride + sd.hb_off;
     const size_t plane = (size_t)sd.h * sd.pitch;
+    const float* xyb = xyb_base + (size_t)frame * g.xyb_stride + sd.xyb_off;
+    float* hb = hb_base + (size_t)frame * g.hb_stride + sd.hb_off;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // convert role
-    const int cimg = tid >> 8, cq = tid & 255, cqy = cq >> 4, cqx = cq & 15;
-    // scan role
-    const int q = warp / 3, ch = warp - 3 * q;
+    const int q = warp / 3, ch = warp - 3 * q;  // scan role
     HState st = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float hist[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) hist[i] = 0.f;
 
     const int nchunks = (sd.w + kHCols - 1) / kHCols + 1;
+    float4 pre[kHLoadsPerThread];
 
-    auto convert = [&](int k, int buf) {
+    auto load_chunk = [&](int k) {  // global -> registers
         const int c0 = kHCols * k + 4;
-        float* dst = s_in + ((buf * 2 + cimg) * 3) * kHRows * kHPitch;
 #pragma unroll
-        for (int iy = 0; iy < 2; iy++)
-#pragma unroll
-            for (int ix = 0; ix < 2; ix++) {
-                int lx = 2 * cqx + ix, ly = 2 * cqy + iy;
-                int x = c0 + lx, y = row0 + ly;
-                float X = 0.f, Y = 0.f, B = 0.f;
-                if (x >= 0 && x < sd.w && y < sd.h) {
-                    float r, gg, b;
-                    load_linear<FMT>(g, in, lin_slot, frame, s, cimg, x, y, r, gg, b);
-                    linear_to_xyb(r, gg, b, X, Y, B);
-                }
-                dst[(0 * kHRows + ly) * kHPitch + lx] = X;
-                dst[(1 * kHRows + ly) * kHPitch + lx] = Y;
-                dst[(2 * kHRows + ly) * kHPitch + lx] = B;
+        for (int i = 0; i < kHLoadsPerThread; i++) {
+            const int idx = tid + i * kHThreads;
+            const int p6 = idx >> 8, r = (idx >> 3) & 31, g4 = idx & 7;
+            const int row = row0 + r, col = c0 + 4 * g4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < sd.h && col >= 0 && col < sd.w) {
+                v = __ldg(reinterpret_cast<const float4*>(xyb + p6 * plane + (size_t)row * sd.pitch + col));
+                if (col + 1 >= sd.w) v.y = 0.f;
+                if (col + 2 >= sd.w) v.z = 0.f;
+                if (col + 3 >= sd.w) v.w = 0.f;
             }
+            pre[i] = v;
+        }
+    };
+    auto park_chunk = [&](int buf) {  // registers -> shared
+#pragma unroll
+        for (int i = 0; i < kHLoadsPerThread; i++) {
+            const int idx = tid + i * kHThreads;
+            const int p6 = idx >> 8, r = (idx >> 3) & 31, g4 = idx & 7;
+            *reinterpret_cast<float4*>(s_in + ((buf * 6 + p6) * kHRows + r) * kHPitch + 4 * g4) = pre[i];
+        }
     };
 
-    convert(-1, 0);
+    load_chunk(-1);
+    park_chunk(0);
     __syncthreads();
     for (int kk = 0; kk < nchunks; kk++) {
         const int k = kk - 1, buf = kk & 1;
-        if (kk + 1 < nchunks) convert(k + 1, buf ^ 1);
+        if (kk + 1 < nchunks) load_chunk(k + 1);
         if (warp < 15) {
-            const float* s_ref = s_in + (((buf * 2 + 0) * 3 + ch) * kHRows + lane) * kHPitch;
-            const float* s_dis = s_in + (((buf * 2 + 1) * 3 + ch) * kHRows + lane) * kHPitch;
+            const float* s_ref = s_in + ((buf * 6 + ch) * kHRows + lane) * kHPitch;
+            const float* s_dis = s_in + ((buf * 6 + 3 + ch) * kHRows + lane) * kHPitch;
             float* so = s_out + (warp * kHRows + lane) * kHPitch;
             switch (q) {
             case 0: hscan_chunk<0>(s_ref, s_dis, so, st, hist); break;
@@ -467,6 +518,7 @@ __global__ void __launch_bounds__(kHThreads) k_hpass(const __grid_constant__ Geo
             default: hscan_chunk<4>(s_ref, s_dis, so, st, hist); break;
             }
         }
+        if (kk + 1 < nchunks) park_chunk(buf ^ 1);
         __syncthreads();
         if (k >= 0) {
             for (int idx = tid; idx < 15 * kHRows * (kHCols / 4); idx += kHThreads) {
@@ -489,14 +541,15 @@ __global__ void __launch_bounds__(kHThreads) k_hpass(const __grid_constant__ Geo
 // ssim_map cpu.rs:581-638 and edge_diff_map cpu.rs:640-683 (f64 tails included).
 //
 // CTA = one 64-column strip of one scale of one frame; 192 threads = (channel c, column x);
-// each thread runs the 5 filters of its (c, x) down the column and accumulates 6 f64 sums.
-// Rows are processed 3 per iteration: thread (c, x) first converts the source pixel
-// (x, row n0 + c) of both images to XYB (all 3 channels) into shared memory, then, after one
-// barrier, every thread advances its filters 3 steps and evaluates the maps for its channel.
+// each thread runs the 5 filters of its (c, x) down the column, evaluates the three maps for its
+// channel at every output row and accumulates 6 f64 sums.  Rows are processed kVUnroll per
+// iteration so that 7*kVUnroll independent loads are in flight per thread; the 10-row delay line
+// of each filter is a per-thread ring in shared memory (no barriers in the main loop).
 // ------------------------------------------------------------------------------------------
 constexpr int kVCols = 64;
 constexpr int kVThreads = 3 * kVCols;
 constexpr int kVRing = 10;
+constexpr int kVUnroll = 4;
 
 struct VState {
     float p1, p3, p5, pp1, pp3, pp5;
@@ -516,21 +569,19 @@ __device__ __forceinline__ float vstep(VState& s, float top, float bottom)
     return (o1 + o3) + o5;
 }
 
-template <int FMT>
-__global__ void __launch_bounds__(kVThreads) k_vpass(const __grid_constant__ Geo g, const __grid_constant__ BatchIn in, const float* __restrict__ lin_base,
+__global__ void __launch_bounds__(kVThreads) k_vpass(const __grid_constant__ Geo g, const float* __restrict__ xyb_base,
                                                      const float* __restrict__ hb_base, double* __restrict__ partials)
 {
     __shared__ float ring[kVRing][5][kVThreads];
-    __shared__ float sxyb[2][2][3][3][kVCols];  // [buf][img][channel][row-in-iteration][x]
     __shared__ double red[kVThreads / 32][6];
 
     const int frame = blockIdx.y;
     int item = blockIdx.x, s = 0;
     while (item >= g.sc[s].n_strips) { item -= g.sc[s].n_strips; s++; }
     const ScaleDesc sd = g.sc[s];
-    const float* lin_slot = lin_base + (size_t)frame * g.lin_stride;
-    const float* hb = hb_base + (size_t)frame * g.hb_stride + sd.hb_off;
     const size_t plane = (size_t)sd.h * sd.pitch;
+    const float* xyb = xyb_base + (size_t)frame * g.xyb_stride + sd.xyb_off;
+    const float* hb = hb_base + (size_t)frame * g.hb_stride + sd.hb_off;
 
     const int tid = threadIdx.x, tx = tid % kVCols, c = tid / kVCols;
     const int x = item * kVCols + tx;
@@ -546,39 +597,26 @@ __global__ void __launch_bounds__(kVThreads) k_vpass(const __grid_constant__ Geo
         for (int qi = 0; qi < 5; qi++) ring[i][qi][tid] = 0.f;
     double acc[6] = {0, 0, 0, 0, 0, 0};
 
-    const float* col = hb + (size_t)c * plane + x;  // plane (q*3 + c) = col + q*3*plane
+    const float* col = hb + (size_t)c * plane + x;          // plane (q*3 + c) = col + q*3*plane
+    const float* xr = xyb + (size_t)c * plane + x;          // ref channel c
+    const float* xd = xyb + (size_t)(3 + c) * plane + x;    // dis channel c
     const int nsteps = H + 4;
     int slot = 0;
-    for (int t0 = 0, it = 0; t0 < nsteps; t0 += 3, it++) {
-        const int buf = it & 1;
-        // phase 1: XYB of row n = t0 + c - 4, both images
-        {
-            int n = t0 + c - 4;
-            if (active && n >= 0 && n < H) {
+    for (int t0 = 0; t0 < nsteps; t0 += kVUnroll) {
+        float v[kVUnroll][5], pr[kVUnroll], pd[kVUnroll];
 #pragma unroll
-                for (int img = 0; img < 2; img++) {
-                    float r, gg, b, X, Y, B;
-                    load_linear<FMT>(g, in, lin_slot, frame, s, img, x, n, r, gg, b);
-                    linear_to_xyb(r, gg, b, X, Y, B);
-                    sxyb[buf][img][0][c][tx] = X;
-                    sxyb[buf][img][1][c][tx] = Y;
-                    sxyb[buf][img][2][c][tx] = B;
-                }
-            }
-        }
-        // right taps of the 3 steps
-        float v[3][5];
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            int t = t0 + r;
-            bool ld = active && t < H;
+        for (int r = 0; r < kVUnroll; r++) {
+            const int t = t0 + r, n = t - 4;
+            const bool ld = active && t < H;
 #pragma unroll
             for (int qi = 0; qi < 5; qi++) v[r][qi] = ld ? __ldg(col + (size_t)qi * 3 * plane + (size_t)t * sd.pitch) : 0.f;
+            const bool lx = active && n >= 0 && n < H;
+            pr[r] = lx ? __ldg(xr + (size_t)n * sd.pitch) : 0.f;
+            pd[r] = lx ? __ldg(xd + (size_t)n * sd.pitch) : 0.f;
         }
-        __syncthreads();
 #pragma unroll
-        for (int r = 0; r < 3; r++) {
-            int t = t0 + r;
+        for (int r = 0; r < kVUnroll; r++) {
+            const int t = t0 + r;
             if (t < nsteps) {
                 float o[5];
 #pragma unroll
@@ -588,7 +626,7 @@ __global__ void __launch_bounds__(kVThreads) k_vpass(const __grid_constant__ Geo
                     o[qi] = vstep(st[qi], old, v[r][qi]);
                 }
                 slot = (slot == kVRing - 1) ? 0 : slot + 1;
-                int n = t - 4;
+                const int n = t - 4;
                 if (active && n >= 0) {
                     const float C2 = 0.0009f;
                     float s11 = o[0], s22 = o[1], s12 = o[2], mu1 = o[3], mu2 = o[4];
@@ -603,8 +641,7 @@ __global__ void __launch_bounds__(kVThreads) k_vpass(const __grid_constant__ Geo
                     double d2 = d * d;
                     acc[1] += d2 * d2;
 
-                    float ref = sxyb[buf][0][c][r][tx], dis = sxyb[buf][1][c][r][tx];
-                    double d1 = (1.0 + (double)fabsf(dis - mu2)) / (1.0 + (double)fabsf(ref - mu1)) - 1.0;
+                    double d1 = (1.0 + (double)fabsf(pd[r] - mu2)) / (1.0 + (double)fabsf(pr[r] - mu1)) - 1.0;
                     double art = d1 > 0.0 ? d1 : 0.0;
                     double det = -d1 > 0.0 ? -d1 : 0.0;
                     acc[2] += art;
@@ -707,6 +744,14 @@ __global__ void __launch_bounds__(128) k_finalize(const __grid_constant__ Geo g,
         scores_out[frame] = ssim;
         scores_ring[(first_ticket + frame) % ring_cap] = ssim;
     }
+}
+
+// Test hook: the device build of exact_math.cuh over an array (op 0 = cbrtf, 1 = powf(x, y)).
+__global__ void k_debug_math(int op, const float* __restrict__ in, float y, float* __restrict__ out, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = op == 0 ? exact_math::cbrtf_glibc(in[i]) : exact_math::powf_glibc(in[i], y, kPowfTablesInit);
 }
 
 }  // namespace ssimu2

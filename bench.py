@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- SSIMULACRA2 frame-pairs/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 4k|1080p|512] [--impl ours|reference]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over the workload's frame sequence (300 synthetic pairs per GPU,
+SURVEY.md section 8d).  Frames are sharded over the ranks with no data-path collective (weak scaling:
+every rank scores its own 300 pairs); only scalar scores leave a GPU.
+
+  value      pairs/s with the frames already resident in HBM when the timed region starts
+             (device frames through the C ABI, ssimu2_submit_batch + ssimu2_get_score)
+  e2e        the same metric through the host-frame entry point of the C ABI (ssimu2_submit_host):
+             pinned HOST buffers, host->device copies and the score read-back inside the timed region
+  roofline   dominant kernel: algorithmic bytes per launch / its CUDA-event duration (events recorded by
+             the library on the stream the kernel runs on), against MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (a port of the reference's examples/cpu.rs; the Rust reference cannot be
+             built here) on the host cores, one pair per thread, bounded sample
+--impl reference times that oracle alone, on the same config, as the reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (w, h, kind, bits, description)
+    "4k": (3840, 2160, "yuv", 16, "4K 10-bit YUV420 (P016) BT.709 limited, 300 synthetic pairs per GPU (BASELINE configs[2]/[3])"),
+    "1080p": (1920, 1080, "yuv", 8, "1080p 8-bit YUV420 (NV12) BT.709 limited, 300 synthetic pairs per GPU (BASELINE configs[1])"),
+    "512": (512, 512, "srgb8", 8, "512 synthetic 512x512 sRGB8 pairs, small-frame path (BASELINE configs[4])"),
+}
+PAIRS_PER_STEP = {"4k": 300, "1080p": 300, "512": 512}
+DISTINCT = {"4k": 32, "1080p": 64, "512": 128}   # distinct pairs cycled through a step (>> 126 MB L2)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # the samples span idle gaps too: take the median of the upper half as "under load"
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU oracle arm
+def oracle_pairs_per_s(workload, n_pairs, threads):
+    """Score n_pairs synthetic pairs with the CPU oracle, one pair per thread; returns pairs/s."""
+    import torch  # noqa: F401
+    from oracle import oracle
+    from turbo_metrics_b200 import synth
+    w, h, kind, bits, _ = WORKLOADS[workload]
+    oracle.lib()
+    if kind == "yuv":
+        rb, db, pitch, ch = synth.make_pair_yuv420(w, h, bits, frame=0, seed=1)
+        rn, dn = rb.numpy(), db.numpy()
+        job = lambda: oracle.ssimu2_yuv420(rn, dn, pitch, ch, w, h, bits)[0]
+    else:
+        r, d = synth.make_pair_srgb8(w, h, frame=0, seed=1)
+        rn, dn = r.numpy(), d.numpy()
+        job = lambda: oracle.ssimu2_srgb8(rn, dn)[0]
+    out = [None] * n_pairs
+    idx = iter(range(n_pairs))
+    lock = threading.Lock()
+
+    def worker():
+        while True:
+            with lock:
+                i = next(idx, None)
+            if i is None:
+                return
+            out[i] = job()
+    ts = [threading.Thread(target=worker) for _ in range(min(threads, n_pairs))]
+    t0 = time.perf_counter()
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    dt = time.perf_counter() - t0
+    return n_pairs / dt, dt, out[0]
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = min(cores, 32)
+    w, h, kind, bits, desc = WORKLOADS[args.workload]
+    sample = threads if args.workload != "512" else threads * 8
+    for _ in range(args.warmup):
+        oracle_pairs_per_s(args.workload, max(1, min(sample, 2)), threads)
+    vals, secs = [], 0.0
+    for _ in range(args.steps):
+        v, dt, _ = oracle_pairs_per_s(args.workload, sample, threads)
+        vals.append(v); secs += dt
+    value = sample * args.steps / secs
+    line = {
+        "impl": "reference", "metric": "ssimulacra2_frame_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+        "config": {"workload": desc, "width": w, "height": h, "note": "reference Rust crate cannot be built here (no rustc); "
+                   "this is the C port of its examples/cpu.rs + biplanar.rs (oracle/), one pair per host thread"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} pairs per step x {args.steps} steps of the same {w}x{h} workload"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import turbo_metrics_b200 as tm
+    from turbo_metrics_b200 import synth
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    w, h, kind, bits, desc = WORKLOADS[args.workload]
+    n_pairs, n_distinct = PAIRS_PER_STEP[args.workload], DISTINCT[args.workload]
+    fmt = {("yuv", 8): tm.PixelFormat.NV12, ("yuv", 16): tm.PixelFormat.P016, ("srgb8", 8): tm.PixelFormat.SRGB8}[(kind, bits)]
+
+    # ---- synthetic frames, resident in HBM (each rank its own shard: seed includes the rank)
+    dev_frames, host_frames = [], []
+    for i in range(n_distinct):
+        if kind == "yuv":
+            rb, db, pitch, ch = synth.make_pair_yuv420(w, h, bits, frame=i, seed=1 + rank, device=dev)
+            mk = lambda t: tm.DeviceFrame.yuv420(t, pitch, ch)
+        else:
+            rb, db = synth.make_pair_srgb8(w, h, frame=i, seed=1 + rank, device=dev)
+            mk = tm.DeviceFrame.packed
+        dev_frames.append((rb, db))
+    n_host = min(n_distinct, 16)
+    for i in range(n_host):
+        host_frames.append((dev_frames[i][0].cpu().pin_memory(), dev_frames[i][1].cpu().pin_memory()))
+    frame_bytes = dev_frames[0][0].numel() * dev_frames[0][0].element_size()
+    refs = [mk(dev_frames[i % n_distinct][0]) for i in range(n_pairs)]
+    diss = [mk(dev_frames[i % n_distinct][1]) for i in range(n_pairs)]
+    hrefs = [mk(host_frames[i % n_host][0]) for i in range(n_pairs)]
+    hdiss = [mk(host_frames[i % n_host][1]) for i in range(n_pairs)]
+
+    m = tm.Ssimulacra2(w, h, fmt, device=local_rank, batch=args.batch, ring=args.ring)
+    info = m.info()
+    alg_bytes = info.alg_bytes_per_pair
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        ts = m.compute_batch(refs, diss, stream)
+        m.flush()
+        return [m.get_score(t) for t in (ts[0], ts[-1])], ts
+
+    def step_host():
+        ts = [m.compute_from_cpu(a, b) for a, b in zip(hrefs, hdiss)]
+        m.flush()
+        return [m.get_score(t) for t in (ts[0], ts[-1])], ts
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        # get_score() has synchronised every batch stream with the host; mark the end on the device clock
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        barrier()
+        ms_event = max(e0.elapsed_time(e1), 0.0)
+        # every batch stream waits on the submit stream (so all work starts after e0) and get_score() has
+        # synchronised every batch with the host before e1 is recorded: the CUDA-event interval covers the whole
+        # region; the host clock around the same synchronised region is kept as a cross-check, larger one wins
+        ms = max(ms_event, wall * 1000.0)
+        timed.last = {"event_ms": ms_event, "wall_ms": wall * 1000.0}
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step_device()
+    l0 = m.info().kernel_launches
+    m.kernel_ms(reset=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_device, args.steps)
+    timing = dict(timed.last)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = m.info().kernel_launches - l0
+    value = world * n_pairs * args.steps / (ms / 1000.0)
+
+    # ---- e2e: host frames through the C ABI
+    for _ in range(max(1, args.warmup // 2)):
+        step_host()
+    e2e_steps = max(1, min(args.steps, 3))
+    ms_e2e = timed(step_host, e2e_steps)
+    e2e_value = world * n_pairs * e2e_steps / (ms_e2e / 1000.0)
+
+    # ---- parity spot check of the timed configuration (rank 0, tiny cost): scores are finite and the
+    # first pair of the sequence equals its own re-run in another batch slot
+    (s_first, s_last), _ = step_device()
+    assert 0.0 < s_first < 100.0 and 0.0 < s_last < 100.0, (s_first, s_last)
+
+    # ---- per-kernel device time without cross-stream overlap: same batch size, ring = 1
+    m.close()
+    m1 = tm.Ssimulacra2(w, h, fmt, device=local_rank, batch=args.batch, ring=1)
+    for _ in range(2):
+        ts = m1.compute_batch(refs[:4 * args.batch], diss[:4 * args.batch], stream)
+        [m1.get_score(t) for t in ts]
+    m1.kernel_ms(reset=True)
+    ts = m1.compute_batch(refs, diss, stream)
+    sc = [m1.get_score(t) for t in ts]
+    kms, kbatches, kpairs = m1.kernel_ms()
+    m1.close()
+    assert sc[0] == s_first, "score depends on the batch slot"
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    names = ["k_frontend", "k_hpass", "k_vpass", "k_finalize"]
+    px = [info.width[s] * info.height[s] for s in range(info.nscales)]
+    in0 = {"4k": 6, "1080p": 3, "512": 6}[args.workload]
+    # algorithmic bytes per pair per kernel (DESIGN.md "Roofline accounting"; they sum to B_alg)
+    pass_bytes = 60 * sum(px) + in0 * px[0] + 24 * sum(px[1:])
+    kalg = {"k_frontend": 24 * sum(px[1:]), "k_hpass": pass_bytes, "k_vpass": pass_bytes, "k_finalize": 0}
+    assert sum(kalg.values()) == alg_bytes, (sum(kalg.values()), alg_bytes)
+    dom = max(range(3), key=lambda k: kms[k])
+    per_launch_ms = kms[dom] / kbatches
+    pairs_per_launch = kpairs / kbatches
+    achieved = kalg[names[dom]] * pairs_per_launch / (per_launch_ms / 1e3) / 1e9
+    pipeline_gbs = alg_bytes * value / world / 1e9
+    roof = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src,
+            "kernel_ms_per_launch": {n: kms[k] / kbatches for k, n in enumerate(names)},
+            "pairs_per_launch": pairs_per_launch,
+            "pipeline": {"alg_bytes_per_pair": alg_bytes, "achieved": pipeline_gbs, "frac": pipeline_gbs / peak,
+                         "note": "B_alg (SURVEY 8d) x pairs/s per GPU / peak"}}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    if os.path.exists(traffic_file):
+        tr = json.load(open(traffic_file)).get(args.workload, {})
+        if names[dom] in tr:
+            roof["traffic"] = tr[names[dom]] * pairs_per_launch   # bytes per launch from the ncu --set full capture
+
+    cores = os.cpu_count() or 1
+    threads = min(cores, 32)
+    sample = max(2, min(threads, 16)) if args.workload != "512" else threads * 8
+    if args.no_cpu_baseline:
+        cpu = {"value": None, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": "skipped (--no-cpu-baseline)"}
+    else:
+        cv, cdt, _ = oracle_pairs_per_s(args.workload, sample, threads)
+        cpu = {"value": cv, "unit": "pairs/s", "cores": min(threads, sample), "kind": "port",
+               "sample": f"{sample} pairs of the same {w}x{h} workload, one pair per thread, {cdt:.1f} s"}
+
+    line = {
+        "metric": "ssimulacra2_frame_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (+f64 seed/tails)", "data": "synthetic",
+        "config": {"workload": desc, "width": w, "height": h, "pairs_per_step_per_gpu": n_pairs, "distinct_pairs": n_distinct,
+                   "batch": info.batch, "ring": info.ring,
+                   "l2": f"inputs cycle through {n_distinct} distinct pairs = {2 * frame_bytes * n_distinct / 1e6:.0f} MB per GPU (> 126 MB L2); "
+                         "intermediates are 0.9 GB per pair",
+                   "parallelism": f"frame-sharded x{world}, no collective"},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 2 * frame_bytes * n_pairs, "d2h_bytes_per_step": 8 * n_pairs * 109,
+                "steps": e2e_steps, "note": "ssimu2_submit_host from pinned host buffers; PCIe-bound"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "timing": timing,
+        "scores": {"first": s_first, "last": s_last},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="4k", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--ring", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -147,6 +147,9 @@ int ssimu2_debug_read(ssimu2_t *h, uint64_t ticket, int what, int scale, float *
 int ssimu2_debug_math(int op, const float *in, float y, float *out, size_t n);
 /* Average device time (ms) of the last completed batch per kernel: pyramid, hpass, vpass, finalize. */
 int ssimu2_last_batch_ms(ssimu2_t *h, float ms[4]);
+/* Device time (ms, CUDA events on the batch's own stream) summed per kernel over every batch
+ * completed so far: frontend, hpass, vpass, finalize; optional counters; reset != 0 clears them. */
+int ssimu2_kernel_ms(ssimu2_t *h, double ms_total[4], uint64_t *batches, uint64_t *pairs, int reset);
 
 #ifdef __cplusplus
 }

@@ -53,6 +53,7 @@ SYMBOLS = {
     "ssimu2_debug_read": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_size_t]),
     "ssimu2_debug_math": (C.c_int, [C.c_int, C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float), C.c_size_t]),
     "ssimu2_last_batch_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "ssimu2_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]),
 }
 
 _lib = None

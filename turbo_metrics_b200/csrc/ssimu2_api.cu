@@ -70,6 +70,8 @@ struct ssimu2_handle {
     size_t staging_frame_bytes = 0;
     uint64_t launches = 0;
     float last_ms[4] = {0, 0, 0, 0};
+    double total_ms[4] = {0, 0, 0, 0};  // per-kernel device time summed over harvested batches
+    uint64_t timed_batches = 0, timed_pairs = 0;
     uint64_t alg_bytes = 0;
 };
 
@@ -228,7 +230,12 @@ static int harvest(ssimu2_handle* h, uint32_t si)
         h->res_slot[r] = (int32_t)si;
     }
     if (sl.timed) {
-        for (int k = 0; k < 4; k++) cudaEventElapsedTime(&h->last_ms[k], sl.ev_k[k], sl.ev_k[k + 1]);
+        for (int k = 0; k < 4; k++) {
+            cudaEventElapsedTime(&h->last_ms[k], sl.ev_k[k], sl.ev_k[k + 1]);
+            h->total_ms[k] += h->last_ms[k];
+        }
+        h->timed_batches++;
+        h->timed_pairs += sl.count;
     }
     sl.inflight = false;
     sl.count = 0;
@@ -638,6 +645,19 @@ int ssimu2_last_batch_ms(ssimu2_t* h, float ms[4])
 {
     if (!h || !ms) return SSIMU2_E_INVALID;
     memcpy(ms, h->last_ms, sizeof(h->last_ms));
+    return SSIMU2_OK;
+}
+
+int ssimu2_kernel_ms(ssimu2_t* h, double ms_total[4], uint64_t* batches, uint64_t* pairs, int reset)
+{
+    if (!h || !ms_total) return SSIMU2_E_INVALID;
+    for (int k = 0; k < 4; k++) ms_total[k] = h->total_ms[k];
+    if (batches) *batches = h->timed_batches;
+    if (pairs) *pairs = h->timed_pairs;
+    if (reset) {
+        for (int k = 0; k < 4; k++) h->total_ms[k] = 0;
+        h->timed_batches = h->timed_pairs = 0;
+    }
     return SSIMU2_OK;
 }
 

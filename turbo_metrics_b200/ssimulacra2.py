@@ -204,6 +204,13 @@ class Ssimulacra2:
                                            out.size), "ssimu2_debug_read")
         return out
 
+    def kernel_ms(self, reset: bool = False):
+        """-> (ms_total[4] for frontend/hpass/vpass/finalize, batches, pairs) since the last reset."""
+        ms = (C.c_double * 4)()
+        b, p = C.c_uint64(), C.c_uint64()
+        check(_lib.lib().ssimu2_kernel_ms(self._h, ms, C.byref(b), C.byref(p), int(reset)), "ssimu2_kernel_ms")
+        return list(ms), b.value, p.value
+
     def last_batch_ms(self):
         ms = (C.c_float * 4)()
         check(_lib.lib().ssimu2_last_batch_ms(self._h, ms), "ssimu2_last_batch_ms")

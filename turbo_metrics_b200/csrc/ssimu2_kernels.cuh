@@ -394,10 +394,11 @@ constexpr int kHRows = 32;
 constexpr int kHCols = 32;
 constexpr int kHPitch = 36;  // floats; 144 B = 9 x 16 B -> conflict-free 128-bit row-per-lane access
 constexpr int kHThreads = 512;
-constexpr int kHSmemIn = 2 * 6 * kHRows * kHPitch;  // [buf][img*3+ch][row][col]
-constexpr int kHSmemOut = 15 * kHRows * kHPitch;    // [plane][row][col]
-constexpr size_t kHSmemBytes = (size_t)(kHSmemIn + kHSmemOut) * sizeof(float);
-constexpr int kHLoadsPerThread = 6 * kHRows * (kHCols / 4) / kHThreads;  // 3
+constexpr int kHSmemIn = 6 * kHRows * kHPitch;   // [img*3+ch][row][col]
+constexpr int kHSmemOut = 15 * kHRows * kHPitch;  // [plane][row][col]
+constexpr size_t kHSmemBytes = (size_t)(kHSmemIn + kHSmemOut) * sizeof(float);  // 96.8 KB -> 2 CTAs per SM
+constexpr int kHLoadsPerThread = 6 * kHRows * (kHCols / 4) / kHThreads;    // 3
+constexpr int kHStoresPerThread = (15 * kHRows * (kHCols / 4) + kHThreads - 1) / kHThreads;  // 8 (last one half-populated)
 
 struct HState {
     float p1, p3, p5, pp1, pp3, pp5;
@@ -448,8 +449,8 @@ __device__ __forceinline__ void hscan_chunk(const float* __restrict__ s_ref, con
     for (int i = 0; i < 12; i++) hist[i] = win[kHCols + i];
 }
 
-__global__ void __launch_bounds__(kHThreads) k_hpass(const __grid_constant__ Geo g, const float* __restrict__ xyb_base,
-                                                     float* __restrict__ hb_base)
+__global__ void __launch_bounds__(kHThreads, 2) k_hpass(const __grid_constant__ Geo g, const float* __restrict__ xyb_base,
+                                                        float* __restrict__ hb_base)
 {
     extern __shared__ __align__(16) float smem[];
     float* s_in = smem;
@@ -463,6 +464,7 @@ __global__ void __launch_bounds__(kHThreads) k_hpass(const __grid_constant__ Geo
     const size_t plane = (size_t)sd.h * sd.pitch;
     const float* xyb = xyb_base + (size_t)frame * g.xyb_stride + sd.xyb_off;
     float* hb = hb_base + (size_t)frame * g.hb_stride + sd.hb_off;
+    const int W = sd.w;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp / 3, ch = warp - 3 * q;  // scan role
@@ -471,44 +473,47 @@ __global__ void __launch_bounds__(kHThreads) k_hpass(const __grid_constant__ Geo
 #pragma unroll
     for (int i = 0; i < 12; i++) hist[i] = 0.f;
 
-    const int nchunks = (sd.w + kHCols - 1) / kHCols + 1;
+    // copy roles: every index below is loop-invariant; only the column offset of the chunk changes.
+    // tile element idx = tid + i*512 -> (plane idx>>8, row (idx>>3)&31, 4-column group idx&7)
+    const int g4 = tid & 7, r0 = (tid >> 3) & 31, pl0 = tid >> 8;  // idx = tid: plane 0/1; +512 per i: plane += 2
+    const bool row_ok = row0 + r0 < sd.h;
+    const float* gin = xyb + (size_t)pl0 * plane + (size_t)(row0 + r0) * sd.pitch + 4 * g4;  // + 2*i*plane + c0
+    float* gout = hb + (size_t)pl0 * plane + (size_t)(row0 + r0) * sd.pitch + 4 * g4;        // + 2*i*plane + 32k
+    const int s_off = (pl0 * kHRows + r0) * kHPitch + 4 * g4;                                // + 2*i*kHRows*kHPitch
+
+    const int nchunks = (W + kHCols - 1) / kHCols + 1;
     float4 pre[kHLoadsPerThread];
 
     auto load_chunk = [&](int k) {  // global -> registers
-        const int c0 = kHCols * k + 4;
+        const int col = kHCols * k + 4 + 4 * g4;
+        const bool ok = row_ok && col >= 0 && col < W;
 #pragma unroll
         for (int i = 0; i < kHLoadsPerThread; i++) {
-            const int idx = tid + i * kHThreads;
-            const int p6 = idx >> 8, r = (idx >> 3) & 31, g4 = idx & 7;
-            const int row = row0 + r, col = c0 + 4 * g4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < sd.h && col >= 0 && col < sd.w) {
-                v = __ldg(reinterpret_cast<const float4*>(xyb + p6 * plane + (size_t)row * sd.pitch + col));
-                if (col + 1 >= sd.w) v.y = 0.f;
-                if (col + 2 >= sd.w) v.z = 0.f;
-                if (col + 3 >= sd.w) v.w = 0.f;
+            if (ok) {
+                v = __ldg(reinterpret_cast<const float4*>(gin + (size_t)(2 * i) * plane + (kHCols * k + 4)));
+                if (col + 1 >= W) v.y = 0.f;
+                if (col + 2 >= W) v.z = 0.f;
+                if (col + 3 >= W) v.w = 0.f;
             }
             pre[i] = v;
         }
     };
-    auto park_chunk = [&](int buf) {  // registers -> shared
+    auto park_chunk = [&]() {  // registers -> shared
 #pragma unroll
-        for (int i = 0; i < kHLoadsPerThread; i++) {
-            const int idx = tid + i * kHThreads;
-            const int p6 = idx >> 8, r = (idx >> 3) & 31, g4 = idx & 7;
-            *reinterpret_cast<float4*>(s_in + ((buf * 6 + p6) * kHRows + r) * kHPitch + 4 * g4) = pre[i];
-        }
+        for (int i = 0; i < kHLoadsPerThread; i++)
+            *reinterpret_cast<float4*>(s_in + s_off + 2 * i * kHRows * kHPitch) = pre[i];
     };
 
     load_chunk(-1);
-    park_chunk(0);
+    park_chunk();
     __syncthreads();
     for (int kk = 0; kk < nchunks; kk++) {
-        const int k = kk - 1, buf = kk & 1;
+        const int k = kk - 1;
         if (kk + 1 < nchunks) load_chunk(k + 1);
         if (warp < 15) {
-            const float* s_ref = s_in + ((buf * 6 + ch) * kHRows + lane) * kHPitch;
-            const float* s_dis = s_in + ((buf * 6 + 3 + ch) * kHRows + lane) * kHPitch;
+            const float* s_ref = s_in + (ch * kHRows + lane) * kHPitch;
+            const float* s_dis = s_in + ((3 + ch) * kHRows + lane) * kHPitch;
             float* so = s_out + (warp * kHRows + lane) * kHPitch;
             switch (q) {
             case 0: hscan_chunk<0>(s_ref, s_dis, so, st, hist); break;
@@ -518,15 +523,14 @@ __global__ void __launch_bounds__(kHThreads) k_hpass(const __grid_constant__ Geo
             default: hscan_chunk<4>(s_ref, s_dis, so, st, hist); break;
             }
         }
-        if (kk + 1 < nchunks) park_chunk(buf ^ 1);
         __syncthreads();
-        if (k >= 0) {
-            for (int idx = tid; idx < 15 * kHRows * (kHCols / 4); idx += kHThreads) {
-                int p = idx >> 8, r = (idx >> 3) & 31, g4 = idx & 7;
-                int row = row0 + r, col = kHCols * k + 4 * g4;
-                if (row < sd.h && col < sd.w)
-                    *reinterpret_cast<float4*>(hb + p * plane + (size_t)row * sd.pitch + col) =
-                        *reinterpret_cast<const float4*>(s_out + (p * kHRows + r) * kHPitch + 4 * g4);
+        if (kk + 1 < nchunks) park_chunk();
+        if (k >= 0 && row_ok && kHCols * k + 4 * g4 < W) {
+#pragma unroll
+            for (int i = 0; i < kHStoresPerThread; i++) {
+                if (2 * i + pl0 < 15)
+                    *reinterpret_cast<float4*>(gout + (size_t)(2 * i) * plane + kHCols * k) =
+                        *reinterpret_cast<const float4*>(s_out + s_off + 2 * i * kHRows * kHPitch);
             }
         }
         __syncthreads();
@@ -549,7 +553,7 @@ __global__ void __launch_bounds__(kHThreads) k_hpass(const __grid_constant__ Geo
 constexpr int kVCols = 64;
 constexpr int kVThreads = 3 * kVCols;
 constexpr int kVRing = 10;
-constexpr int kVUnroll = 4;
+constexpr int kVSub = 5;  // rows per load batch (7 * kVSub independent loads in flight per thread)
 
 struct VState {
     float p1, p3, p5, pp1, pp3, pp5;
@@ -569,10 +573,60 @@ __device__ __forceinline__ float vstep(VState& s, float top, float bottom)
     return (o1 + o3) + o5;
 }
 
-__global__ void __launch_bounds__(kVThreads) k_vpass(const __grid_constant__ Geo g, const float* __restrict__ xyb_base,
-                                                     const float* __restrict__ hb_base, double* __restrict__ partials)
+// Correctly rounded f32 quotient for operands in the normal range (no zero / inf / nan / subnormal
+// handling): reciprocal seed + one Newton step + Markstein's residual correction.  Checked against
+// IEEE division on the device by tests/test_gpu_parity.py::test_device_division.
+__device__ __forceinline__ float div_rn_normal(float n, float d)
 {
-    __shared__ float ring[kVRing][5][kVThreads];
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    float e = fmaf(-d, r, 1.0f);
+    r = fmaf(r, e, r);
+    float q = n * r;
+    float rem = fmaf(-d, q, n);
+    return fmaf(rem, r, q);
+}
+
+// The three error maps of one (pixel, channel) and their contributions to the six sums.
+// SSIM' term: cpu.rs:604-631 -- identical f32 arithmetic up to the quotient q; d = 1 - q is then
+// formed in f32 (exact whenever q is in [0.5, 2], i.e. wherever d is small) instead of f64.
+// Edge terms: cpu.rs:658-674 computes (1+|dis-mu2|)/(1+|ref-mu1|) - 1 in f64; here the algebraically
+// equal (a-b)/(1+b) in f32, which keeps a RELATIVE error of ~2e-7 on every term (the f32 form of the
+// original expression would not).  Nothing downstream amplifies these errors: they enter the sums
+// directly, 3 orders of magnitude under the 1e-4 bar.
+__device__ __forceinline__ void error_maps(const float (&o)[5], float ref, float dis, float (&part)[6])
+{
+    const float C2 = 0.0009f;
+    const float s11 = o[0], s22 = o[1], s12 = o[2], mu1 = o[3], mu2 = o[4];
+    const float mu11 = mu1 * mu1, mu22 = mu2 * mu2, mu12 = mu1 * mu2;
+    const float mu_diff = mu1 - mu2;
+    const float num_m = fmaf(mu_diff, -mu_diff, 1.0f);
+    const float num_s = fmaf(2.0f, s12 - mu12, C2);
+    const float denom_s = ((s11 - mu11) + (s22 - mu22)) + C2;
+    const float q = div_rn_normal(num_m * num_s, denom_s);
+    const float d = fmaxf(1.0f - q, 0.0f);
+    part[0] += d;
+    const float d2 = d * d;
+    part[1] = fmaf(d2, d2, part[1]);
+
+    const float a = fabsf(dis - mu2), b = fabsf(ref - mu1);
+    const float den = 1.0f + b;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+    r = fmaf(r, fmaf(-den, r, 1.0f), r);
+    const float d1 = (a - b) * r;
+    const float e2 = d1 * d1, e4 = e2 * e2;
+    const bool pos = d1 > 0.0f;
+    part[2] += pos ? d1 : 0.0f;      // artifact
+    part[3] += pos ? e4 : 0.0f;
+    part[4] += pos ? 0.0f : -d1;     // detail lost
+    part[5] += pos ? 0.0f : e4;
+}
+
+__global__ void __launch_bounds__(kVThreads, 2) k_vpass(const __grid_constant__ Geo g, const float* __restrict__ xyb_base,
+                                                        const float* __restrict__ hb_base, double* __restrict__ partials)
+{
+    __shared__ float ring[kVRing * 5 * kVThreads];
     __shared__ double red[kVThreads / 32][6];
 
     const int frame = blockIdx.y;
@@ -584,80 +638,98 @@ __global__ void __launch_bounds__(kVThreads) k_vpass(const __grid_constant__ Geo
     const float* hb = hb_base + (size_t)frame * g.hb_stride + sd.hb_off;
 
     const int tid = threadIdx.x, tx = tid % kVCols, c = tid / kVCols;
-    const int x = item * kVCols + tx;
-    const bool active = x < sd.w;
-    const int H = sd.h;
+    const int xq = item * kVCols + tx;
+    const bool active = xq < sd.w;
+    const int x = active ? xq : sd.w - 1;  // idle lanes shadow the last column; their sums are dropped
+    const int H = sd.h, pitch = sd.pitch;
 
     VState st[5];
 #pragma unroll
     for (int qi = 0; qi < 5; qi++) st[qi] = VState{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float* rp = ring + tid;  // element (slot, q) at rp[(slot * 5 + q) * kVThreads]
 #pragma unroll
-    for (int i = 0; i < kVRing; i++)
-#pragma unroll
-        for (int qi = 0; qi < 5; qi++) ring[i][qi][tid] = 0.f;
+    for (int i = 0; i < kVRing * 5; i++) rp[i * kVThreads] = 0.f;
     double acc[6] = {0, 0, 0, 0, 0, 0};
 
-    const float* col = hb + (size_t)c * plane + x;          // plane (q*3 + c) = col + q*3*plane
-    const float* xr = xyb + (size_t)c * plane + x;          // ref channel c
-    const float* xd = xyb + (size_t)(3 + c) * plane + x;    // dis channel c
-    const int nsteps = H + 4;
-    int slot = 0;
-    for (int t0 = 0; t0 < nsteps; t0 += kVUnroll) {
-        float v[kVUnroll][5], pr[kVUnroll], pd[kVUnroll];
+    // row pointers: p[q] walks plane (q*3 + c) of the H-pass output at row t, pr / pd walk the XYB planes of
+    // channel c at row n = t - 4
+    const float* p[5];
 #pragma unroll
-        for (int r = 0; r < kVUnroll; r++) {
-            const int t = t0 + r, n = t - 4;
-            const bool ld = active && t < H;
+    for (int qi = 0; qi < 5; qi++) p[qi] = hb + (size_t)(qi * 3 + c) * plane + x;
+    const float* pr = xyb + (size_t)c * plane + x;
+    const float* pd = xyb + (size_t)(3 + c) * plane + x;
+
+    // generic step (any t): used for the first 4 rows (no output yet), the tail, and tiny images
+    int t = 0, slot = 0;
+    auto slow_step = [&]() {
+        float v[5], part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, o[5];
+        const bool ld = t < H;
 #pragma unroll
-            for (int qi = 0; qi < 5; qi++) v[r][qi] = ld ? __ldg(col + (size_t)qi * 3 * plane + (size_t)t * sd.pitch) : 0.f;
-            const bool lx = active && n >= 0 && n < H;
-            pr[r] = lx ? __ldg(xr + (size_t)n * sd.pitch) : 0.f;
-            pd[r] = lx ? __ldg(xd + (size_t)n * sd.pitch) : 0.f;
+        for (int qi = 0; qi < 5; qi++) {
+            v[qi] = ld ? __ldg(p[qi]) : 0.f;
+            p[qi] += pitch;
         }
+        float* rs = rp + slot * 5 * kVThreads;
 #pragma unroll
-        for (int r = 0; r < kVUnroll; r++) {
-            const int t = t0 + r;
-            if (t < nsteps) {
+        for (int qi = 0; qi < 5; qi++) {
+            const float old = rs[qi * kVThreads];
+            rs[qi * kVThreads] = v[qi];
+            o[qi] = vstep(st[qi], old, v[qi]);
+        }
+        if (t >= 4) {
+            const float fr = __ldg(pr), fd = __ldg(pd);
+            pr += pitch; pd += pitch;
+            error_maps(o, fr, fd, part);
+#pragma unroll
+            for (int k = 0; k < 6; k++) acc[k] += (double)part[k];
+        }
+        slot = (slot == kVRing - 1) ? 0 : slot + 1;
+        t++;
+    };
+
+    const int nsteps = H + 4;
+    while (t < 4 && t < nsteps) slow_step();
+    // main loop: t = 4 (mod 10) at the top, rows t .. t+9 all inside the image, ring slots static
+    while (t + kVRing <= H) {
+#pragma unroll
+        for (int half = 0; half < kVRing / kVSub; half++) {
+            float v[kVSub][5], fr[kVSub], fd[kVSub];
+#pragma unroll
+            for (int r = 0; r < kVSub; r++) {
+#pragma unroll
+                for (int qi = 0; qi < 5; qi++) {
+                    v[r][qi] = __ldg(p[qi]);
+                    p[qi] += pitch;
+                }
+                fr[r] = __ldg(pr); fd[r] = __ldg(pd);
+                pr += pitch; pd += pitch;
+            }
+            float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int r = 0; r < kVSub; r++) {
+                constexpr int kBase = 4;  // slot of the first row of a group
+                const int sl = (kBase + half * kVSub + r) % kVRing;
+                float* rs = rp + sl * 5 * kVThreads;
                 float o[5];
 #pragma unroll
                 for (int qi = 0; qi < 5; qi++) {
-                    float old = ring[slot][qi][tid];
-                    ring[slot][qi][tid] = v[r][qi];
+                    const float old = rs[qi * kVThreads];
+                    rs[qi * kVThreads] = v[r][qi];
                     o[qi] = vstep(st[qi], old, v[r][qi]);
                 }
-                slot = (slot == kVRing - 1) ? 0 : slot + 1;
-                const int n = t - 4;
-                if (active && n >= 0) {
-                    const float C2 = 0.0009f;
-                    float s11 = o[0], s22 = o[1], s12 = o[2], mu1 = o[3], mu2 = o[4];
-                    float mu11 = mu1 * mu1, mu22 = mu2 * mu2, mu12 = mu1 * mu2;
-                    float mu_diff = mu1 - mu2;
-                    float num_m = fmaf(mu_diff, -mu_diff, 1.0f);
-                    float num_s = fmaf(2.0f, s12 - mu12, C2);
-                    float denom_s = ((s11 - mu11) + (s22 - mu22)) + C2;
-                    double d = 1.0 - (double)((num_m * num_s) / denom_s);
-                    d = d > 0.0 ? d : 0.0;
-                    acc[0] += d;
-                    double d2 = d * d;
-                    acc[1] += d2 * d2;
-
-                    double d1 = (1.0 + (double)fabsf(pd[r] - mu2)) / (1.0 + (double)fabsf(pr[r] - mu1)) - 1.0;
-                    double art = d1 > 0.0 ? d1 : 0.0;
-                    double det = -d1 > 0.0 ? -d1 : 0.0;
-                    acc[2] += art;
-                    double a2 = art * art;
-                    acc[3] += a2 * a2;
-                    acc[4] += det;
-                    double l2 = det * det;
-                    acc[5] += l2 * l2;
-                }
+                error_maps(o, fr[r], fd[r], part);
             }
+#pragma unroll
+            for (int k = 0; k < 6; k++) acc[k] += (double)part[k];
         }
+        t += kVRing;  // slot is unchanged: a whole turn of the ring
     }
+    while (t < nsteps) slow_step();
+
     // block reduction: warps are channel-uniform (64 columns = 2 warps per channel)
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-        double vsum = acc[k];
+        double vsum = active ? acc[k] : 0.0;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) vsum += __shfl_down_sync(0xffffffffu, vsum, off);
         if ((tid & 31) == 0) red[tid >> 5][k] = vsum;

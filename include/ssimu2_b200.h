@@ -142,8 +142,10 @@ int ssimu2_get_info(const ssimu2_t *h, ssimu2_info *info);
  * what = 1: H-pass output of `scale`:            float[15][h][w]    (s11,s22,s12,mu1,mu2) x 3 channels
  * Only valid until that slot is reused (i.e. right after ssimu2_get_score). */
 int ssimu2_debug_read(ssimu2_t *h, uint64_t ticket, int what, int scale, float *out, size_t out_floats);
-/* Run the device build of the bit-exact libm restatements over an array (op 0: cbrtf(x),
- * op 1: powf(x, y)); host pointers.  Lets the tests compare the GPU arithmetic with libm bit for bit. */
+/* Run the device arithmetic helpers over an array (host pointers) so the tests can compare them bit for
+ * bit with libm / IEEE division:  op 0: out[i] = cbrtf(in[i]);  op 1: powf(in[i], y);  op 2: in[i] / y (f32);
+ * op 3: `in` holds n (num, den) pairs of DOUBLES, `out` n doubles: num / den;
+ * op 4: `in` holds n (num, den) pairs of floats: the V-pass quotient. */
 int ssimu2_debug_math(int op, const float *in, float y, float *out, size_t n);
 /* Average device time (ms) of the last completed batch per kernel: pyramid, hpass, vpass, finalize. */
 int ssimu2_last_batch_ms(ssimu2_t *h, float ms[4]);

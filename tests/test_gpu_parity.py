@@ -64,6 +64,40 @@ def test_device_libm_restatements_match_host_libm(exact_math_host):
         assert np.array_equal(_bits(out), _bits(ref)), f"{(_bits(out) != _bits(ref)).sum()} powf mismatches (y={y})"
 
 
+def test_device_divisions_are_ieee():
+    """The hand-rolled divisions (reciprocal seed + Newton + residual correction, no special-case paths) give
+    the IEEE quotient on the operand ranges the pipeline produces."""
+    from turbo_metrics_b200 import _lib
+    lib = _lib.lib()
+    fp = C.POINTER(C.c_float)
+    rng = np.random.default_rng(5)
+    # f32: EOTF argument / ALPHA   (cuda-colorspace-kernel/src/lib.rs:229, srgb.rs:46)
+    for alpha in (np.float32(1.0) + np.float32(5.5) * np.float32(0.018053968510807), np.float32(1.0550107)):
+        x = np.concatenate([rng.uniform(0.05, 1.6, 4_000_000).astype(np.float32),
+                            np.arange(int(np.float32(0.5).view(np.uint32)), int(np.float32(0.5).view(np.uint32)) + (1 << 22),
+                                      dtype=np.uint32).view(np.float32)])
+        out = np.empty_like(x)
+        assert lib.ssimu2_debug_math(2, x.ctypes.data_as(fp), float(alpha), out.ctypes.data_as(fp), x.size) == 0
+        assert np.array_equal(_bits(out), _bits(x / alpha))
+    # f32: the SSIM quotient (cpu.rs:627): numerator in [-2e-3, 2.5], denominator in [5e-4, 2]
+    n = 4_000_000
+    nd = np.empty((n, 2), np.float32)
+    nd[:, 0] = rng.uniform(-2e-3, 2.5, n) * rng.choice([1.0, 1e-2, 1e-3], n)
+    nd[:, 1] = np.exp(rng.uniform(np.log(5e-4), np.log(2.0), n))
+    out = np.empty(n, np.float32)
+    assert lib.ssimu2_debug_math(4, nd.ctypes.data_as(fp), 0.0, out.ctypes.data_as(fp), n) == 0
+    ref = nd[:, 0] / nd[:, 1]
+    ok = (_bits(out) == _bits(ref)) | (np.abs(ref) < 1e-30)   # flush-to-zero territory is irrelevant here
+    assert ok.all(), f"{(~ok).sum()} f32 quotient mismatches"
+    # f64: the Halley step of cbrtf: num in [1.2, 3.1], den in [1.4, 3.1]
+    pairs = np.empty((n, 2), np.float64)
+    pairs[:, 0] = rng.uniform(1.0, 3.2, n)
+    pairs[:, 1] = rng.uniform(1.2, 3.2, n)
+    outd = np.empty(n, np.float64)
+    assert lib.ssimu2_debug_math(3, pairs.ctypes.data_as(fp), 0.0, outd.ctypes.data_as(fp), n) == 0
+    assert np.array_equal(outd.view(np.uint64), (pairs[:, 0] / pairs[:, 1]).view(np.uint64))
+
+
 # ------------------------------------------------------------------------------------------
 def _oracle_stages(oracle, ref_lin, dis_lin, nscales):
     """XYB planes and H-pass planes of every scale, from the oracle's own building blocks."""

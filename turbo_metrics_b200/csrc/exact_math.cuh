@@ -89,19 +89,78 @@ EM_HD double u2d(uint64_t u)
 #endif
 }
 
+// ---- exactly rounded divisions without the library's special-case paths ----------------------------
+// Operands must be normal and the quotient far from over/underflow (true for every use below).
+// Device: reciprocal seed (MUFU) + Newton + Markstein's residual correction; host: the IEEE operator.
+// Both device forms are compared with IEEE division over the operand ranges the pipeline produces by
+// tests/test_gpu_parity.py::test_device_divisions_are_ieee.
+EM_HD double ddiv_normal(double n, double d)
+{
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    double q = n * y;
+    const double r = fma(-d, q, n);
+    return fma(r, y, q);
+#else
+    return n / d;
+#endif
+}
+
+EM_HD float fdiv_normal(float n, float d)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    const float e = fmaf(-d, r, 1.0f);
+    r = fmaf(r, e, r);
+    const float q = n * r;
+    const float rem = fmaf(-d, q, n);
+    return fmaf(rem, r, q);
+#else
+    return n / d;
+#endif
+}
+
+// factor[2 + e % 3] * 2^(e / 3) of glibc's cbrtf for the biased exponent byte eb (e = eb - 126, C
+// truncating division): the exact double by which the Halley result is scaled.  A 256-entry table of
+// these (CbrtScale) replaces the integer division, the 5-way switch and ldexpf.
+EM_HD double cbrt_scale_entry(int eb)
+{
+    const int e = eb - 126;
+    const int q3 = e / 3, r3 = e - 3 * q3;
+    uint64_t f;
+    switch (r3) {
+    case -2: f = 0x3fe428a2f98d728aull; break;  // 0x1.428a2f98d728ap-1 = 1 / 2^(2/3)
+    case -1: f = 0x3fe965fea53d6e3cull; break;  // 0x1.965fea53d6e3cp-1 = 1 / 2^(1/3)
+    case 0: f = 0x3ff0000000000000ull; break;
+    case 1: f = 0x3ff428a2f98d728bull; break;   // 0x1.428a2f98d728bp+0 = 2^(1/3)
+    default: f = 0x3ff965fea53d6e3dull; break;  // 0x1.965fea53d6e3dp+0 = 2^(2/3)
+    }
+    return u2d(f + ((uint64_t)(int64_t)q3 << 52));
+}
+
+struct CbrtScale {
+    double tab[256];
+};
+
 // glibc 2.39 cbrtf.  Bit-exact for every finite x; zero / inf / nan return x + x like glibc;
 // subnormals take the platform cbrtf (never produced by the pipeline: the opsin bias keeps the
-// argument >= 0.0037).
-EM_HD float cbrtf_glibc(float x)
+// argument >= 0.0037).  `S` may be null (host / cold paths): the scale is then computed in place.
+EM_HD float cbrtf_glibc(float x, const CbrtScale* S = nullptr)
 {
     const uint32_t ix = f2u(x) & 0x7fffffffu;
     if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
         if (ix == 0 || ix >= 0x7f800000u) return x + x;
         return ::cbrtf(x);
     }
-    // frexpf: |x| = xm * 2^e, xm in [0.5, 1)
-    const int e = (int)(ix >> 23) - 126;
-    const double xm = (double)u2f((ix & 0x007fffffu) | 0x3f000000u);
+    // frexpf: |x| = xm * 2^e, xm in [0.5, 1); the double of xm is built directly from the mantissa bits
+    const uint32_t m = ix & 0x007fffffu;
+    const double xm = u2d(((uint64_t)(0x3fe00000u | (m >> 3)) << 32) | (uint64_t)(m << 29));
     // u = 0.4926... + (0.6975... - 0.1915... * xm) * xm   (mulsd, subsd, mulsd, addsd; then cvtsd2ss)
     double t = 0x1.8832490c2feddp-3 * xm;
     t = 0x1.6527f4927f555p-1 - t;
@@ -110,23 +169,14 @@ EM_HD float cbrtf_glibc(float x)
     const float u = (float)t;
     const float t2 = (u * u) * u;
     const double t2d = (double)t2, ud = (double)u;
-    // ym = u * (t2 + 2.0 * xm) / (2.0 * t2 + xm) * factor[2 + e % 3]
+    // ym = u * (t2 + 2.0 * xm) / (2.0 * t2 + xm) * factor[2 + e % 3], then ldexpf(ym, e / 3): the power of
+    // two commutes with the rounding to float, so both scalings are one multiplication by an exact double
     double num = (xm + xm) + t2d;
     num = num * ud;
     const double den = (t2d + t2d) + xm;
-    const int q3 = e / 3, r3 = e - 3 * q3;  // C semantics: truncation toward zero
-    double f;
-    switch (r3) {
-    case -2: f = 0x1.428a2f98d728ap-1; break;   // 1 / 2^(2/3)
-    case -1: f = 0x1.965fea53d6e3cp-1; break;   // 1 / 2^(1/3)
-    case 0: f = 1.0; break;
-    case 1: f = 0x1.428a2f98d728bp+0; break;    // 2^(1/3)
-    default: f = 0x1.965fea53d6e3dp+0; break;   // 2^(2/3)
-    }
-    const float ym = (float)((num / den) * f);
-    // ldexpf(+-ym, e / 3): exact scaling by a power of two (no subnormal results for normal inputs)
-    const float scale = u2f((uint32_t)(127 + q3) << 23);
-    const float r = ym * scale;
+    const int eb = (int)(ix >> 23);
+    const double f = S ? S->tab[eb] : cbrt_scale_entry(eb);
+    const float r = (float)(ddiv_normal(num, den) * f);
     return (f2u(x) >> 31) ? -r : r;
 }
 

@@ -179,7 +179,7 @@ static int launch_batch_fmt(ssimu2_handle* h, Slot& sl)
     if (sl.timed) cudaEventRecord(sl.ev_k[0], st);
     {
         dim3 grid((g.sc[0].w + 63) / 64, (g.sc[0].h + 63) / 64, n);
-        k_frontend<FMT><<<grid, 256, 0, st>>>(g, sl.in, sl.xyb);
+        k_frontend<FMT><<<grid, kFThreads, kFSmemBytes, st>>>(g, sl.in, sl.xyb);
     }
     if (sl.timed) cudaEventRecord(sl.ev_k[1], st);
     k_hpass<<<dim3(g.items_h, n), kHThreads, kHSmemBytes, st>>>(g, sl.xyb, sl.hb);
@@ -365,6 +365,12 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
     CR(cudaMemset(h->scores_ring_d, 0, kResultCap * sizeof(double)));
     h->device_bytes += kResultCap * sizeof(double);
     CR(cudaFuncSetAttribute((const void*)k_hpass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBytes));
+    {
+        static const void* ffn[6] = {(const void*)k_frontend<kNV12>,    (const void*)k_frontend<kP016>,
+                                     (const void*)k_frontend<kSRGB8>,   (const void*)k_frontend<kSRGB16>,
+                                     (const void*)k_frontend<kSRGBF32>, (const void*)k_frontend<kLINEARF32>};
+        CR(cudaFuncSetAttribute(ffn[cfg->format], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmemBytes));
+    }
     for (uint32_t i = 0; i < h->ring; i++) {
         Slot& sl = h->slots[i];
         const Geo& g = h->geo;
@@ -622,20 +628,21 @@ int ssimu2_debug_read(ssimu2_t* h, uint64_t ticket, int what, int scale, float* 
 
 int ssimu2_debug_math(int op, const float* in, float y, float* out, size_t n)
 {
-    if (!in || !out || op < 0 || op > 1) return SSIMU2_E_INVALID;
+    if (!in || !out || op < 0 || op > 4) return SSIMU2_E_INVALID;
     if (n == 0) return SSIMU2_OK;
+    const size_t in_b = op == 3 ? n * 16 : (op == 4 ? n * 8 : n * 4), out_b = op == 3 ? n * 8 : n * 4;
     float *din = nullptr, *dout = nullptr;
-    if (cudaMalloc(&din, n * sizeof(float)) != cudaSuccess || cudaMalloc(&dout, n * sizeof(float)) != cudaSuccess) {
+    if (cudaMalloc(&din, in_b) != cudaSuccess || cudaMalloc(&dout, out_b) != cudaSuccess) {
         cudaGetLastError();
         cudaFree(din);
         return SSIMU2_E_NOMEM;
     }
-    int rc = (int)cudaMemcpy(din, in, n * sizeof(float), cudaMemcpyHostToDevice);
+    int rc = (int)cudaMemcpy(din, in, in_b, cudaMemcpyHostToDevice);
     if (!rc) {
         k_debug_math<<<(unsigned)((n + 255) / 256), 256>>>(op, din, y, dout, n);
         rc = (int)cudaGetLastError();
     }
-    if (!rc) rc = (int)cudaMemcpy(out, dout, n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (!rc) rc = (int)cudaMemcpy(out, dout, out_b, cudaMemcpyDeviceToHost);
     cudaFree(din);
     cudaFree(dout);
     return rc;

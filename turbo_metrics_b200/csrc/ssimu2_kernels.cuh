@@ -92,7 +92,7 @@ __device__ __forceinline__ float bt709_eotf(float v, const exact_math::PowfTable
     const float ALPHA = 1.0f + 5.5f * BETA;
     const float THRESHOLD = 0.08124285829863521110029445797874f;
     if (v >= THRESHOLD)
-        return exact_math::powf_glibc((v + (ALPHA - 1.0f)) / ALPHA, 1.0f / 0.45f, T);
+        return exact_math::powf_glibc(exact_math::fdiv_normal(v + (ALPHA - 1.0f), ALPHA), 1.0f / 0.45f, T);
     return v / 4.5f;
 }
 
@@ -103,7 +103,7 @@ __device__ __forceinline__ float srgb_inverse_oetf(float x, const exact_math::Po
     const float SRGB_BETA = 0.0030412825f;
     if (x < 12.92f * SRGB_BETA)
         return x / 12.92f;
-    return exact_math::powf_glibc((x + (SRGB_ALPHA - 1.0f)) / SRGB_ALPHA, 2.4f, T);
+    return exact_math::powf_glibc(exact_math::fdiv_normal(x + (SRGB_ALPHA - 1.0f), SRGB_ALPHA), 2.4f, T);
 }
 
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
@@ -158,7 +158,8 @@ __device__ __forceinline__ void load_px(const FrameIn& f, int x, int y, const Yu
 
 // linear RGB -> rescaled XYB.  cpu.rs:421-496 (== ssimulacra2-cuda-kernel/src/xyb.rs:3-102),
 // with the CPU path's libm cbrtf reproduced exactly.
-__device__ __forceinline__ void linear_to_xyb(float r, float g, float b, float& X, float& Y, float& B)
+__device__ __forceinline__ void linear_to_xyb(float r, float g, float b, const exact_math::CbrtScale& S, float& X, float& Y,
+                                              float& B)
 {
     const float K_M02 = 0.078f, K_M00 = 0.30f, K_M01 = 1.0f - K_M02 - K_M00;
     const float K_M12 = 0.078f, K_M10 = 0.23f, K_M11 = 1.0f - K_M12 - K_M10;
@@ -168,9 +169,9 @@ __device__ __forceinline__ void linear_to_xyb(float r, float g, float b, float& 
     float rg = fmaf(K_M00, r, fmaf(K_M01, g, fmaf(K_M02, b, K_B0)));
     float gr = fmaf(K_M10, r, fmaf(K_M11, g, fmaf(K_M12, b, K_B0)));
     float bb = fmaf(K_M20, r, fmaf(K_M21, g, fmaf(K_M22, b, K_B0)));
-    rg = exact_math::cbrtf_glibc(fmaxf(rg, 0.0f)) - K_B0_ROOT;
-    gr = exact_math::cbrtf_glibc(fmaxf(gr, 0.0f)) - K_B0_ROOT;
-    bb = exact_math::cbrtf_glibc(fmaxf(bb, 0.0f)) - K_B0_ROOT;
+    rg = exact_math::cbrtf_glibc(fmaxf(rg, 0.0f), &S) - K_B0_ROOT;
+    gr = exact_math::cbrtf_glibc(fmaxf(gr, 0.0f), &S) - K_B0_ROOT;
+    bb = exact_math::cbrtf_glibc(fmaxf(bb, 0.0f), &S) - K_B0_ROOT;
     float x = 0.5f * (rg - gr);
     float y = 0.5f * (rg + gr);
     X = fmaf(x, 14.0f, 0.42f);
@@ -184,193 +185,124 @@ __device__ __forceinline__ void linear_to_xyb(float r, float g, float b, float& 
 // host loop ssimulacra2-cuda/src/lib.rs:162-183) and linear_to_xyb_packed (xyb.rs:82-102, lib.rs:188-210);
 // follows cpu.rs:545-579 (box sum order (0,0),(1,0),(0,1),(1,1), edge clamp min(src-1), x0.25) and
 // cpu.rs:363-377 (downscale in LINEAR RGB, XYB recomputed per scale).
-// One CTA = one 64x64 source tile of one frame, both images; 256 threads, thread = 4x4 source px.
-// The pyramid levels never leave the chip: only XYB planes are written.
 // ------------------------------------------------------------------------------------------
+// One CTA = one 64x64 source tile of one frame, both images (one after the other); 256 threads.
+// The linear-RGB tile and its 5 pyramid levels live in shared memory; only XYB planes are written.
+// All pixel loops are rolled (one inlined copy of the powf / cbrtf bodies each) to keep the kernel
+// inside the instruction cache.
 __device__ __forceinline__ float box4(float a, float b, float c, float d) { return ((((0.0f + a) + b) + c) + d) * 0.25f; }
 
-__device__ __forceinline__ void store_xyb(float* plane0, size_t plane, size_t off, float r, float g, float b)
+constexpr int kFTile = 64;
+constexpr int kFThreads = 256;
+// shared linear-RGB levels: [3][side][side + 1]
+constexpr int kFOff0 = 0;
+constexpr int kFOff1 = kFOff0 + 3 * 64 * 65;
+constexpr int kFOff2 = kFOff1 + 3 * 32 * 33;
+constexpr int kFOff3 = kFOff2 + 3 * 16 * 17;
+constexpr int kFOff4 = kFOff3 + 3 * 8 * 9;
+constexpr int kFSmemFloats = kFOff4 + 3 * 4 * 5;
+constexpr size_t kFSmemBytes = (size_t)kFSmemFloats * sizeof(float);  // 65.4 KB
+
+// One 2x downscale step inside the tile: src level (side 2n, global size srcW x srcH) -> dst level (side n),
+// XYB of the dst level written to global.  cpu.rs:545-579 (sum order (0,0),(1,0),(0,1),(1,1); clamp; x0.25).
+template <int N, bool KEEP>
+__device__ __forceinline__ void down_level(const float* __restrict__ src, float* __restrict__ dst, int srcW, int srcH,
+                                           int ox0, int oy0, const ScaleDesc& sd, float* __restrict__ gdst,
+                                           const exact_math::CbrtScale& S)
 {
-    float X, Y, B;
-    linear_to_xyb(r, g, b, X, Y, B);
-    plane0[off] = X;
-    plane0[plane + off] = Y;
-    plane0[2 * plane + off] = B;
+    constexpr int SP = 2 * N + 1, DP = N + 1;
+    const size_t plane = (size_t)sd.h * sd.pitch;
+#pragma unroll 1
+    for (int idx = threadIdx.x; idx < N * N; idx += kFThreads) {
+        const int lx = idx % N, ly = idx / N;
+        const int ox = ox0 + lx, oy = oy0 + ly;
+        const bool valid = ox < sd.w && oy < sd.h;
+        const int i1 = (2 * ox + 1 <= srcW - 1) ? 1 : 0, j1 = (2 * oy + 1 <= srcH - 1) ? 1 : 0;
+        float v[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float* p = src + (c * 2 * N + 2 * ly) * SP + 2 * lx;
+            v[c] = valid ? box4(p[0], p[i1], p[j1 * SP], p[j1 * SP + i1]) : 0.0f;
+            if (KEEP) dst[(c * N + ly) * DP + lx] = v[c];
+        }
+        if (valid) {
+            float X, Y, B;
+            linear_to_xyb(v[0], v[1], v[2], S, X, Y, B);
+            const size_t off = (size_t)oy * sd.pitch + ox;
+            gdst[off] = X; gdst[plane + off] = Y; gdst[2 * plane + off] = B;
+        }
+    }
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(256) k_frontend(const __grid_constant__ Geo g, const __grid_constant__ BatchIn in,
-                                                  float* __restrict__ xyb_base)
+__global__ void __launch_bounds__(kFThreads) k_frontend(const __grid_constant__ Geo g, const __grid_constant__ BatchIn in,
+                                                        float* __restrict__ xyb_base)
 {
+    extern __shared__ __align__(16) float fs[];
     __shared__ exact_math::PowfTables T;
-    __shared__ float s2[6][16][16];
-    __shared__ float s3[6][8][8];
-    __shared__ float s4[6][4][4];
+    __shared__ exact_math::CbrtScale S;
     {
         const uint64_t* src = reinterpret_cast<const uint64_t*>(&kPowfTablesInit);
         uint64_t* dst = reinterpret_cast<uint64_t*>(&T);
-        for (int i = threadIdx.x; i < (int)(sizeof(exact_math::PowfTables) / 8); i += 256) dst[i] = src[i];
+        for (int i = threadIdx.x; i < (int)(sizeof(exact_math::PowfTables) / 8); i += kFThreads) dst[i] = src[i];
+        S.tab[threadIdx.x] = exact_math::cbrt_scale_entry(threadIdx.x);
     }
     __syncthreads();
     const int frame = blockIdx.z;
     float* xyb_slot = xyb_base + (size_t)frame * g.xyb_stride;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int W0 = g.sc[0].w, H0 = g.sc[0].h;
-    const int bx = blockIdx.x * 64 + tx * 4, by = blockIdx.y * 64 + ty * 4;  // source block origin
+    const int X0 = blockIdx.x * kFTile, Y0 = blockIdx.y * kFTile;
     const int ns = g.nscales;
 
     for (int img = 0; img < 2; img++) {
         const FrameIn& f = img ? in.dis[frame] : in.ref[frame];
-        // ---- scale 0: 4x4 source pixels -> linear (registers) -> XYB planes
-        float lin[3][4][4];
+        // ---- scale 0: source -> linear RGB (shared) -> XYB (global); thread = column lx, rows ly0 + 4k
         {
             const ScaleDesc& sd = g.sc[0];
             const size_t plane = (size_t)sd.h * sd.pitch;
-            float* dst = xyb_slot + sd.xyb_off + (size_t)img * 3 * plane;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int y = by + j;
-                float X[4], Y[4], B[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int x = bx + i;
-                    float r = 0.f, gg = 0.f, b = 0.f;
-                    X[i] = Y[i] = B[i] = 0.f;
-                    if (x < W0 && y < H0) {
-                        load_px<FMT>(f, x, y, g.coef, T, r, gg, b);
-                        linear_to_xyb(r, gg, b, X[i], Y[i], B[i]);
-                    }
-                    lin[0][j][i] = r; lin[1][j][i] = gg; lin[2][j][i] = b;
+            float* gdst = xyb_slot + sd.xyb_off + (size_t)img * 3 * plane;
+            const int lx = threadIdx.x & 63, x = X0 + lx;
+#pragma unroll 1
+            for (int k = 0; k < kFTile / 4; k++) {
+                const int ly = (threadIdx.x >> 6) + 4 * k, y = Y0 + ly;
+                float r = 0.f, gg = 0.f, b = 0.f;
+                if (x < W0 && y < H0) {
+                    load_px<FMT>(f, x, y, g.coef, T, r, gg, b);
+                    float X, Y, B;
+                    linear_to_xyb(r, gg, b, S, X, Y, B);
+                    const size_t off = (size_t)y * sd.pitch + x;
+                    gdst[off] = X; gdst[plane + off] = Y; gdst[2 * plane + off] = B;
                 }
-                if (y < H0) {
-                    const size_t off = (size_t)y * sd.pitch + bx;
-                    if (bx + 3 < W0) {
-                        *reinterpret_cast<float4*>(dst + off) = make_float4(X[0], X[1], X[2], X[3]);
-                        *reinterpret_cast<float4*>(dst + plane + off) = make_float4(Y[0], Y[1], Y[2], Y[3]);
-                        *reinterpret_cast<float4*>(dst + 2 * plane + off) = make_float4(B[0], B[1], B[2], B[3]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; i++)
-                            if (bx + i < W0) {
-                                dst[off + i] = X[i]; dst[plane + off + i] = Y[i]; dst[2 * plane + off + i] = B[i];
-                            }
-                    }
-                }
+                fs[kFOff0 + (0 * 64 + ly) * 65 + lx] = r;
+                fs[kFOff0 + (1 * 64 + ly) * 65 + lx] = gg;
+                fs[kFOff0 + (2 * 64 + ly) * 65 + lx] = b;
             }
         }
-        // ---- level 1: 2x2 outputs per thread
-        float l1[3][2][2];
-        const int W1 = g.sc[1].w, H1 = g.sc[1].h;
+        auto gplane = [&](int s) {
+            const ScaleDesc& sd = g.sc[s];
+            return xyb_slot + sd.xyb_off + (size_t)img * 3 * (size_t)sd.h * sd.pitch;
+        };
         if (ns > 1) {
-            const ScaleDesc& sd = g.sc[1];
-            const size_t plane = (size_t)sd.h * sd.pitch;
-            float* dst = xyb_slot + sd.xyb_off + (size_t)img * 3 * plane;
-#pragma unroll
-            for (int j = 0; j < 2; j++)
-#pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    const int ox = bx / 2 + i, oy = by / 2 + j;
-                    const bool valid = ox < W1 && oy < H1;
-                    const bool cx = (bx + 2 * i + 1 <= W0 - 1), cy = (by + 2 * j + 1 <= H0 - 1);
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        float a = lin[c][2 * j][2 * i];
-                        float b = cx ? lin[c][2 * j][2 * i + 1] : a;
-                        float cc = cy ? lin[c][2 * j + 1][2 * i] : a;
-                        float d = cy ? (cx ? lin[c][2 * j + 1][2 * i + 1] : lin[c][2 * j + 1][2 * i]) : b;
-                        l1[c][j][i] = valid ? box4(a, b, cc, d) : 0.0f;
-                    }
-                    if (valid) store_xyb(dst, plane, (size_t)oy * sd.pitch + ox, l1[0][j][i], l1[1][j][i], l1[2][j][i]);
-                }
+            __syncthreads();
+            down_level<32, true>(fs + kFOff0, fs + kFOff1, W0, H0, X0 / 2, Y0 / 2, g.sc[1], gplane(1), S);
         }
-        // ---- level 2: one output per thread, from registers
         if (ns > 2) {
-            const ScaleDesc& sd = g.sc[2];
-            const int ox = bx / 4, oy = by / 4;
-            const bool valid = ox < sd.w && oy < sd.h;
-            const bool cx = (2 * ox + 1 <= W1 - 1), cy = (2 * oy + 1 <= H1 - 1);
-            const size_t plane = (size_t)sd.h * sd.pitch;
-            float* dst = xyb_slot + sd.xyb_off + (size_t)img * 3 * plane;
-            float v[3];
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                float a = l1[c][0][0];
-                float b = cx ? l1[c][0][1] : a;
-                float cc = cy ? l1[c][1][0] : a;
-                float d = cy ? (cx ? l1[c][1][1] : l1[c][1][0]) : b;
-                v[c] = valid ? box4(a, b, cc, d) : 0.0f;
-                s2[img * 3 + c][ty][tx] = v[c];
-            }
-            if (valid) store_xyb(dst, plane, (size_t)oy * sd.pitch + ox, v[0], v[1], v[2]);
+            __syncthreads();
+            down_level<16, true>(fs + kFOff1, fs + kFOff2, g.sc[1].w, g.sc[1].h, X0 / 4, Y0 / 4, g.sc[2], gplane(2), S);
         }
-    }
-    // ---- levels 3..5 through shared memory; one thread = one output pixel of one image
-    if (ns > 3) {
-        __syncthreads();
-        const ScaleDesc& sp = g.sc[2];
-        const ScaleDesc& sd = g.sc[3];
-        const size_t plane = (size_t)sd.h * sd.pitch;
-        if (threadIdx.x < 128) {
-            const int img = threadIdx.x >> 6, ly = (threadIdx.x >> 3) & 7, lx = threadIdx.x & 7;
-            const int ox = blockIdx.x * 8 + lx, oy = blockIdx.y * 8 + ly;
-            const bool valid = ox < sd.w && oy < sd.h;
-            const int i1 = (2 * ox + 1 <= sp.w - 1) ? 1 : 0, j1 = (2 * oy + 1 <= sp.h - 1) ? 1 : 0;
-            float v[3];
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const int pc = img * 3 + c;
-                v[c] = valid ? box4(s2[pc][2 * ly][2 * lx], s2[pc][2 * ly][2 * lx + i1], s2[pc][2 * ly + j1][2 * lx],
-                                    s2[pc][2 * ly + j1][2 * lx + i1])
-                             : 0.0f;
-                s3[pc][ly][lx] = v[c];
-            }
-            if (valid)
-                store_xyb(xyb_slot + sd.xyb_off + (size_t)img * 3 * plane, plane, (size_t)oy * sd.pitch + ox, v[0], v[1], v[2]);
+        if (ns > 3) {
+            __syncthreads();
+            down_level<8, true>(fs + kFOff2, fs + kFOff3, g.sc[2].w, g.sc[2].h, X0 / 8, Y0 / 8, g.sc[3], gplane(3), S);
         }
-    }
-    if (ns > 4) {
-        __syncthreads();
-        const ScaleDesc& sp = g.sc[3];
-        const ScaleDesc& sd = g.sc[4];
-        const size_t plane = (size_t)sd.h * sd.pitch;
-        if (threadIdx.x < 32) {
-            const int img = threadIdx.x >> 4, ly = (threadIdx.x >> 2) & 3, lx = threadIdx.x & 3;
-            const int ox = blockIdx.x * 4 + lx, oy = blockIdx.y * 4 + ly;
-            const bool valid = ox < sd.w && oy < sd.h;
-            const int i1 = (2 * ox + 1 <= sp.w - 1) ? 1 : 0, j1 = (2 * oy + 1 <= sp.h - 1) ? 1 : 0;
-            float v[3];
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const int pc = img * 3 + c;
-                v[c] = valid ? box4(s3[pc][2 * ly][2 * lx], s3[pc][2 * ly][2 * lx + i1], s3[pc][2 * ly + j1][2 * lx],
-                                    s3[pc][2 * ly + j1][2 * lx + i1])
-                             : 0.0f;
-                s4[pc][ly][lx] = v[c];
-            }
-            if (valid)
-                store_xyb(xyb_slot + sd.xyb_off + (size_t)img * 3 * plane, plane, (size_t)oy * sd.pitch + ox, v[0], v[1], v[2]);
+        if (ns > 4) {
+            __syncthreads();
+            down_level<4, true>(fs + kFOff3, fs + kFOff4, g.sc[3].w, g.sc[3].h, X0 / 16, Y0 / 16, g.sc[4], gplane(4), S);
         }
-    }
-    if (ns > 5) {
-        __syncthreads();
-        const ScaleDesc& sp = g.sc[4];
-        const ScaleDesc& sd = g.sc[5];
-        const size_t plane = (size_t)sd.h * sd.pitch;
-        if (threadIdx.x < 8) {
-            const int img = threadIdx.x >> 2, ly = (threadIdx.x >> 1) & 1, lx = threadIdx.x & 1;
-            const int ox = blockIdx.x * 2 + lx, oy = blockIdx.y * 2 + ly;
-            if (ox < sd.w && oy < sd.h) {
-                const int i1 = (2 * ox + 1 <= sp.w - 1) ? 1 : 0, j1 = (2 * oy + 1 <= sp.h - 1) ? 1 : 0;
-                float v[3];
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const int pc = img * 3 + c;
-                    v[c] = box4(s4[pc][2 * ly][2 * lx], s4[pc][2 * ly][2 * lx + i1], s4[pc][2 * ly + j1][2 * lx],
-                                s4[pc][2 * ly + j1][2 * lx + i1]);
-                }
-                store_xyb(xyb_slot + sd.xyb_off + (size_t)img * 3 * plane, plane, (size_t)oy * sd.pitch + ox, v[0], v[1], v[2]);
-            }
+        if (ns > 5) {
+            __syncthreads();
+            down_level<2, false>(fs + kFOff4, nullptr, g.sc[4].w, g.sc[4].h, X0 / 32, Y0 / 32, g.sc[5], gplane(5), S);
         }
+        __syncthreads();  // the tile is reused by the next image
     }
 }
 
@@ -818,12 +750,24 @@ __global__ void __launch_bounds__(128) k_finalize(const __grid_constant__ Geo g,
     }
 }
 
-// Test hook: the device build of exact_math.cuh over an array (op 0 = cbrtf, 1 = powf(x, y)).
+// Test hook: the device build of exact_math.cuh over an array.
+//   op 0: out[i] = cbrtf(in[i])            op 1: out[i] = powf(in[i], y)
+//   op 2: out[i] = fdiv_normal(in[i], y)   op 3: in = n pairs of doubles (num, den), out = n doubles ddiv_normal
+//   op 4: out[i] = div_rn_normal(in[2i], in[2i+1]) (the V-pass quotient)
 __global__ void k_debug_math(int op, const float* __restrict__ in, float y, float* __restrict__ out, size_t n)
 {
+    __shared__ exact_math::CbrtScale S;
+    S.tab[threadIdx.x] = exact_math::cbrt_scale_entry(threadIdx.x);
+    __syncthreads();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    out[i] = op == 0 ? exact_math::cbrtf_glibc(in[i]) : exact_math::powf_glibc(in[i], y, kPowfTablesInit);
+    if (op == 0) out[i] = exact_math::cbrtf_glibc(in[i], &S);
+    else if (op == 1) out[i] = exact_math::powf_glibc(in[i], y, kPowfTablesInit);
+    else if (op == 2) out[i] = exact_math::fdiv_normal(in[i], y);
+    else if (op == 3) {
+        const double* din = reinterpret_cast<const double*>(in);
+        reinterpret_cast<double*>(out)[i] = exact_math::ddiv_normal(din[2 * i], din[2 * i + 1]);
+    } else out[i] = div_rn_normal(in[2 * i], in[2 * i + 1]);
 }
 
 }  // namespace ssimu2

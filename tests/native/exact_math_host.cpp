@@ -5,15 +5,16 @@
 #include <cstddef>
 
 static const exact_math::PowfTables kTables = {{EM_POWF_LOG2_TAB}, {EM_EXP2F_TAB}};
+static const exact_math::Consts kK = EM_CONSTS_INIT;
 
 extern "C" {
 void em_cbrtf_array(const float* in, float* out, size_t n)
 {
-    for (size_t i = 0; i < n; i++) out[i] = exact_math::cbrtf_glibc(in[i]);
+    for (size_t i = 0; i < n; i++) out[i] = exact_math::cbrtf_glibc(in[i], kK);
 }
 void em_powf_array(const float* in, float y, float* out, size_t n)
 {
-    for (size_t i = 0; i < n; i++) out[i] = exact_math::powf_glibc(in[i], y, kTables);
+    for (size_t i = 0; i < n; i++) out[i] = exact_math::powf_glibc(in[i], y, kK, kTables);
 }
 void libm_cbrtf_array(const float* in, float* out, size_t n)
 {

@@ -56,6 +56,21 @@ struct PowfTables {
     0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,        \
     0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull
 
+// Every double constant of the two routines.  On the device this lives in __constant__ memory so the
+// FP64 instructions read their operand straight from the constant bank (as immediates each one costs
+// two moves per use).
+struct Consts {
+    double cb2, cb1, cb0;          // cbrtf seed polynomial
+    double A0, A1, A2, A3, A4;     // powf log2 polynomial
+    double C0, C1, C2;             // powf exp2 polynomial
+    double shift, minus_one, one;
+};
+#define EM_CONSTS_INIT                                                                                        \
+    {0x1.8832490c2feddp-3, 0x1.6527f4927f555p-1, 0x1.f87bc378ed415p-2,                                        \
+     0x1.27616c9496e0bp-2, -0x1.71969a075c67ap-2, 0x1.ec70a6ca7baddp-2, -0x1.7154748bef6c8p-1,                \
+     0x1.71547652ab82bp+0, 0x1.c6af84b912394p-5, 0x1.ebfce50fac4f3p-3, 0x1.62e42ff0c52d6p-1, 0x1.8p+47, -1.0, \
+     1.0}
+
 EM_HD uint32_t f2u(float f)
 {
 #if defined(__CUDA_ARCH__)
@@ -151,7 +166,7 @@ struct CbrtScale {
 // glibc 2.39 cbrtf.  Bit-exact for every finite x; zero / inf / nan return x + x like glibc;
 // subnormals take the platform cbrtf (never produced by the pipeline: the opsin bias keeps the
 // argument >= 0.0037).  `S` may be null (host / cold paths): the scale is then computed in place.
-EM_HD float cbrtf_glibc(float x, const CbrtScale* S = nullptr)
+EM_HD float cbrtf_glibc(float x, const Consts& K, const CbrtScale* S = nullptr)
 {
     const uint32_t ix = f2u(x) & 0x7fffffffu;
     if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
@@ -162,10 +177,10 @@ EM_HD float cbrtf_glibc(float x, const CbrtScale* S = nullptr)
     const uint32_t m = ix & 0x007fffffu;
     const double xm = u2d(((uint64_t)(0x3fe00000u | (m >> 3)) << 32) | (uint64_t)(m << 29));
     // u = 0.4926... + (0.6975... - 0.1915... * xm) * xm   (mulsd, subsd, mulsd, addsd; then cvtsd2ss)
-    double t = 0x1.8832490c2feddp-3 * xm;
-    t = 0x1.6527f4927f555p-1 - t;
+    double t = K.cb2 * xm;
+    t = K.cb1 - t;
     t = t * xm;
-    t = t + 0x1.f87bc378ed415p-2;
+    t = t + K.cb0;
     const float u = (float)t;
     const float t2 = (u * u) * u;
     const double t2d = (double)t2, ud = (double)u;
@@ -182,7 +197,7 @@ EM_HD float cbrtf_glibc(float x, const CbrtScale* S = nullptr)
 
 // glibc 2.39 powf (FMA variant) for x > 0 normal and finite nonzero y; anything else, and results
 // that would leave the normal float range, go to the platform powf.
-EM_HD float powf_glibc(float x, float y, const PowfTables& T)
+EM_HD float powf_glibc(float x, float y, const Consts& K, const PowfTables& T)
 {
     const uint32_t ix = f2u(x), iy = f2u(y);
     const bool x_special = ix - 0x00800000u >= 0x7f800000u - 0x00800000u;
@@ -196,32 +211,28 @@ EM_HD float powf_glibc(float x, float y, const PowfTables& T)
     const int k = (int32_t)top >> 23;
     const double invc = T.log2_tab[i][0], logc = T.log2_tab[i][1];
     const double z = (double)u2f(iz);
-    const double r = fma(z, invc, -1.0);
+    const double r = fma(z, invc, K.minus_one);
     const double y0 = logc + (double)k;
-    const double A0 = 0x1.27616c9496e0bp-2, A1 = -0x1.71969a075c67ap-2, A2 = 0x1.ec70a6ca7baddp-2,
-                 A3 = -0x1.7154748bef6c8p-1, A4 = 0x1.71547652ab82bp+0;
     const double r2 = r * r;
-    double yy = fma(A0, r, A1);
-    const double p = fma(A2, r, A3);
+    double yy = fma(K.A0, r, K.A1);
+    const double p = fma(K.A2, r, K.A3);
     const double r4 = r2 * r2;
-    double q = fma(A4, r, y0);
+    double q = fma(K.A4, r, y0);
     q = fma(p, r2, q);
     yy = fma(yy, r4, q);
     const double ylogx = (double)y * yy;
     if (((d2u(ylogx) >> 47) & 0xffffu) >= (0x405F800000000000ull >> 47)) return ::powf(x, y);  // |y log2 x| >= 126
     // exp2_inline (sign_bias = 0)
-    const double SHIFT = 0x1.8p+47;
-    double kd = ylogx + SHIFT;
+    double kd = ylogx + K.shift;
     const uint64_t ki = d2u(kd);
-    kd = kd - SHIFT;
+    kd = kd - K.shift;
     const double rr = ylogx - kd;
     uint64_t tt = T.exp2_tab[ki & 31u];
     tt += ki << 47;
     const double s = u2d(tt);
-    const double C0 = 0x1.c6af84b912394p-5, C1 = 0x1.ebfce50fac4f3p-3, C2 = 0x1.62e42ff0c52d6p-1;
-    const double zz = fma(C0, rr, C1);
+    const double zz = fma(K.C0, rr, K.C1);
     const double rr2 = rr * rr;
-    double w = fma(C2, rr, 1.0);
+    double w = fma(K.C2, rr, K.one);
     w = fma(zz, rr2, w);
     w = w * s;
     return (float)w;

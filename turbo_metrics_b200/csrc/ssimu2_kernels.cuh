@@ -82,6 +82,7 @@ __device__ const float kSrgb8Lut[256] = {
 // colour front-end
 // ------------------------------------------------------------------------------------------
 __device__ const exact_math::PowfTables kPowfTablesInit = {{EM_POWF_LOG2_TAB}, {EM_EXP2F_TAB}};
+__constant__ exact_math::Consts kEM = EM_CONSTS_INIT;
 
 // BT709::eotf, cuda-colorspace-kernel/src/lib.rs:220-236 (same body for the BT601 variants).
 // The reference uses __nv_fast_powf (not reproducible on a CPU); the oracle and this kernel both use
@@ -92,7 +93,7 @@ __device__ __forceinline__ float bt709_eotf(float v, const exact_math::PowfTable
     const float ALPHA = 1.0f + 5.5f * BETA;
     const float THRESHOLD = 0.08124285829863521110029445797874f;
     if (v >= THRESHOLD)
-        return exact_math::powf_glibc(exact_math::fdiv_normal(v + (ALPHA - 1.0f), ALPHA), 1.0f / 0.45f, T);
+        return exact_math::powf_glibc(exact_math::fdiv_normal(v + (ALPHA - 1.0f), ALPHA), 1.0f / 0.45f, kEM, T);
     return v / 4.5f;
 }
 
@@ -103,7 +104,7 @@ __device__ __forceinline__ float srgb_inverse_oetf(float x, const exact_math::Po
     const float SRGB_BETA = 0.0030412825f;
     if (x < 12.92f * SRGB_BETA)
         return x / 12.92f;
-    return exact_math::powf_glibc(exact_math::fdiv_normal(x + (SRGB_ALPHA - 1.0f), SRGB_ALPHA), 2.4f, T);
+    return exact_math::powf_glibc(exact_math::fdiv_normal(x + (SRGB_ALPHA - 1.0f), SRGB_ALPHA), 2.4f, kEM, T);
 }
 
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
@@ -169,9 +170,9 @@ __device__ __forceinline__ void linear_to_xyb(float r, float g, float b, const e
     float rg = fmaf(K_M00, r, fmaf(K_M01, g, fmaf(K_M02, b, K_B0)));
     float gr = fmaf(K_M10, r, fmaf(K_M11, g, fmaf(K_M12, b, K_B0)));
     float bb = fmaf(K_M20, r, fmaf(K_M21, g, fmaf(K_M22, b, K_B0)));
-    rg = exact_math::cbrtf_glibc(fmaxf(rg, 0.0f), &S) - K_B0_ROOT;
-    gr = exact_math::cbrtf_glibc(fmaxf(gr, 0.0f), &S) - K_B0_ROOT;
-    bb = exact_math::cbrtf_glibc(fmaxf(bb, 0.0f), &S) - K_B0_ROOT;
+    rg = exact_math::cbrtf_glibc(fmaxf(rg, 0.0f), kEM, &S) - K_B0_ROOT;
+    gr = exact_math::cbrtf_glibc(fmaxf(gr, 0.0f), kEM, &S) - K_B0_ROOT;
+    bb = exact_math::cbrtf_glibc(fmaxf(bb, 0.0f), kEM, &S) - K_B0_ROOT;
     float x = 0.5f * (rg - gr);
     float y = 0.5f * (rg + gr);
     X = fmaf(x, 14.0f, 0.42f);
@@ -416,25 +417,26 @@ __global__ void __launch_bounds__(kHThreads, 2) k_hpass(const __grid_constant__ 
     const int nchunks = (W + kHCols - 1) / kHCols + 1;
     float4 pre[kHLoadsPerThread];
 
-    auto load_chunk = [&](int k) {  // global -> registers
+    int pre_col = 0;
+    auto load_chunk = [&](int k) {  // global -> registers (nothing here may touch the loaded values)
         const int col = kHCols * k + 4 + 4 * g4;
+        pre_col = col;
         const bool ok = row_ok && col >= 0 && col < W;
 #pragma unroll
         for (int i = 0; i < kHLoadsPerThread; i++) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) {
-                v = __ldg(reinterpret_cast<const float4*>(gin + (size_t)(2 * i) * plane + (kHCols * k + 4)));
-                if (col + 1 >= W) v.y = 0.f;
-                if (col + 2 >= W) v.z = 0.f;
-                if (col + 3 >= W) v.w = 0.f;
-            }
-            pre[i] = v;
+            pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) pre[i] = __ldg(reinterpret_cast<const float4*>(gin + (size_t)(2 * i) * plane + (kHCols * k + 4)));
         }
     };
-    auto park_chunk = [&]() {  // registers -> shared
+    auto park_chunk = [&]() {  // registers -> shared; columns >= W are the filter's zero padding
 #pragma unroll
-        for (int i = 0; i < kHLoadsPerThread; i++)
-            *reinterpret_cast<float4*>(s_in + s_off + 2 * i * kHRows * kHPitch) = pre[i];
+        for (int i = 0; i < kHLoadsPerThread; i++) {
+            float4 v = pre[i];
+            if (pre_col + 1 >= W) v.y = 0.f;
+            if (pre_col + 2 >= W) v.z = 0.f;
+            if (pre_col + 3 >= W) v.w = 0.f;
+            *reinterpret_cast<float4*>(s_in + s_off + 2 * i * kHRows * kHPitch) = v;
+        }
     };
 
     load_chunk(-1);
@@ -482,6 +484,9 @@ __global__ void __launch_bounds__(kHThreads, 2) k_hpass(const __grid_constant__ 
 // iteration so that 7*kVUnroll independent loads are in flight per thread; the 10-row delay line
 // of each filter is a per-thread ring in shared memory (no barriers in the main loop).
 // ------------------------------------------------------------------------------------------
+#ifndef KV_MINB
+#define KV_MINB 3
+#endif
 constexpr int kVCols = 64;
 constexpr int kVThreads = 3 * kVCols;
 constexpr int kVRing = 10;
@@ -555,7 +560,7 @@ __device__ __forceinline__ void error_maps(const float (&o)[5], float ref, float
     part[5] += pos ? 0.0f : e4;
 }
 
-__global__ void __launch_bounds__(kVThreads, 2) k_vpass(const __grid_constant__ Geo g, const float* __restrict__ xyb_base,
+__global__ void __launch_bounds__(kVThreads, KV_MINB) k_vpass(const __grid_constant__ Geo g, const float* __restrict__ xyb_base,
                                                         const float* __restrict__ hb_base, double* __restrict__ partials)
 {
     __shared__ float ring[kVRing * 5 * kVThreads];
@@ -761,8 +766,8 @@ __global__ void k_debug_math(int op, const float* __restrict__ in, float y, floa
     __syncthreads();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (op == 0) out[i] = exact_math::cbrtf_glibc(in[i], &S);
-    else if (op == 1) out[i] = exact_math::powf_glibc(in[i], y, kPowfTablesInit);
+    if (op == 0) out[i] = exact_math::cbrtf_glibc(in[i], kEM, &S);
+    else if (op == 1) out[i] = exact_math::powf_glibc(in[i], y, kEM, kPowfTablesInit);
     else if (op == 2) out[i] = exact_math::fdiv_normal(in[i], y);
     else if (op == 3) {
         const double* din = reinterpret_cast<const double*>(in);

@@ -145,7 +145,8 @@ int ssimu2_debug_read(ssimu2_t *h, uint64_t ticket, int what, int scale, float *
 /* Run the device arithmetic helpers over an array (host pointers) so the tests can compare them bit for
  * bit with libm / IEEE division:  op 0: out[i] = cbrtf(in[i]);  op 1: powf(in[i], y);  op 2: in[i] / y (f32);
  * op 3: `in` holds n (num, den) pairs of DOUBLES, `out` n doubles: num / den;
- * op 4: `in` holds n (num, den) pairs of floats: the V-pass quotient. */
+ * op 4: `in` holds n (num, den) pairs of floats: the V-pass quotient;
+ * op 5 / 6: the unchecked hot-path forms of op 0 / 1 (positive normal arguments only). */
 int ssimu2_debug_math(int op, const float *in, float y, float *out, size_t n);
 /* Average device time (ms) of the last completed batch per kernel: pyramid, hpass, vpass, finalize. */
 int ssimu2_last_batch_ms(ssimu2_t *h, float ms[4]);

@@ -51,9 +51,13 @@ def test_device_libm_restatements_match_host_libm(exact_math_host):
     out = np.empty_like(x)
     ref = np.empty_like(x)
     fp = C.POINTER(C.c_float)
-    assert lib.ssimu2_debug_math(0, x.ctypes.data_as(fp), 0.0, out.ctypes.data_as(fp), x.size) == 0
     exact_math_host.libm_cbrtf_array(x.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p), C.c_size_t(x.size))
+    assert lib.ssimu2_debug_math(0, x.ctypes.data_as(fp), 0.0, out.ctypes.data_as(fp), x.size) == 0
     assert np.array_equal(_bits(out), _bits(ref)), f"{(_bits(out) != _bits(ref)).sum()} cbrtf mismatches"
+    pos = x > 0  # the unchecked hot-path form
+    xp, out = np.ascontiguousarray(x[pos]), np.empty(int(pos.sum()), np.float32)
+    assert lib.ssimu2_debug_math(5, xp.ctypes.data_as(fp), 0.0, out.ctypes.data_as(fp), xp.size) == 0
+    assert np.array_equal(_bits(out), _bits(ref[pos]))
     for y in [float(np.float32(1.0) / np.float32(0.45)), 2.4]:
         xb = rng.uniform(0.07, 1.3, 3_000_000).astype(np.float32)
         out = np.empty_like(xb)
@@ -62,6 +66,8 @@ def test_device_libm_restatements_match_host_libm(exact_math_host):
         exact_math_host.libm_powf_array(xb.ctypes.data_as(C.c_void_p), C.c_float(y), ref.ctypes.data_as(C.c_void_p),
                                         C.c_size_t(xb.size))
         assert np.array_equal(_bits(out), _bits(ref)), f"{(_bits(out) != _bits(ref)).sum()} powf mismatches (y={y})"
+        assert lib.ssimu2_debug_math(6, xb.ctypes.data_as(fp), y, out.ctypes.data_as(fp), xb.size) == 0
+        assert np.array_equal(_bits(out), _bits(ref)), "unchecked powf"
 
 
 def test_device_divisions_are_ieee():

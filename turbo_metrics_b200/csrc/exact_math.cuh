@@ -31,8 +31,11 @@
 
 namespace exact_math {
 
-struct PowfTables {
-    double log2_tab[16][2];  // {invc, logc}
+struct alignas(16) Log2Entry {
+    double invc, logc;
+};
+struct alignas(16) PowfTables {
+    Log2Entry log2_tab[16];
     uint64_t exp2_tab[32];
 };
 
@@ -166,12 +169,16 @@ struct CbrtScale {
 // glibc 2.39 cbrtf.  Bit-exact for every finite x; zero / inf / nan return x + x like glibc;
 // subnormals take the platform cbrtf (never produced by the pipeline: the opsin bias keeps the
 // argument >= 0.0037).  `S` may be null (host / cold paths): the scale is then computed in place.
+// CHECKED = false is the hot-path form: the caller guarantees a positive normal argument.
+template <bool CHECKED = true>
 EM_HD float cbrtf_glibc(float x, const Consts& K, const CbrtScale* S = nullptr)
 {
-    const uint32_t ix = f2u(x) & 0x7fffffffu;
-    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
-        if (ix == 0 || ix >= 0x7f800000u) return x + x;
-        return ::cbrtf(x);
+    const uint32_t ix = CHECKED ? (f2u(x) & 0x7fffffffu) : f2u(x);
+    if (CHECKED) {
+        if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+            if (ix == 0 || ix >= 0x7f800000u) return x + x;
+            return ::cbrtf(x);
+        }
     }
     // frexpf: |x| = xm * 2^e, xm in [0.5, 1); the double of xm is built directly from the mantissa bits
     const uint32_t m = ix & 0x007fffffu;
@@ -192,24 +199,31 @@ EM_HD float cbrtf_glibc(float x, const Consts& K, const CbrtScale* S = nullptr)
     const int eb = (int)(ix >> 23);
     const double f = S ? S->tab[eb] : cbrt_scale_entry(eb);
     const float r = (float)(ddiv_normal(num, den) * f);
+    if (!CHECKED) return r;
     return (f2u(x) >> 31) ? -r : r;
 }
 
 // glibc 2.39 powf (FMA variant) for x > 0 normal and finite nonzero y; anything else, and results
 // that would leave the normal float range, go to the platform powf.
+// CHECKED = false is the hot-path form: the caller guarantees x normal and positive, y finite and
+// |y log2 x| < 126 (true for the EOTF arguments of the integer pixel formats).
+template <bool CHECKED = true>
 EM_HD float powf_glibc(float x, float y, const Consts& K, const PowfTables& T)
 {
     const uint32_t ix = f2u(x), iy = f2u(y);
-    const bool x_special = ix - 0x00800000u >= 0x7f800000u - 0x00800000u;
-    const bool y_special = 2u * iy - 1u >= 2u * 0x7f800000u - 1u;
-    if (x_special || y_special) return ::powf(x, y);
+    if (CHECKED) {
+        const bool x_special = ix - 0x00800000u >= 0x7f800000u - 0x00800000u;
+        const bool y_special = 2u * iy - 1u >= 2u * 0x7f800000u - 1u;
+        if (x_special || y_special) return ::powf(x, y);
+    }
     // log2_inline
     const uint32_t tmp = ix - 0x3f330000u;
     const int i = (int)((tmp >> 19) & 15u);
     const uint32_t top = tmp & 0xff800000u;
     const uint32_t iz = ix - top;
     const int k = (int32_t)top >> 23;
-    const double invc = T.log2_tab[i][0], logc = T.log2_tab[i][1];
+    const Log2Entry le = T.log2_tab[i];
+    const double invc = le.invc, logc = le.logc;
     const double z = (double)u2f(iz);
     const double r = fma(z, invc, K.minus_one);
     const double y0 = logc + (double)k;
@@ -221,7 +235,7 @@ EM_HD float powf_glibc(float x, float y, const Consts& K, const PowfTables& T)
     q = fma(p, r2, q);
     yy = fma(yy, r4, q);
     const double ylogx = (double)y * yy;
-    if (((d2u(ylogx) >> 47) & 0xffffu) >= (0x405F800000000000ull >> 47)) return ::powf(x, y);  // |y log2 x| >= 126
+    if (CHECKED && ((d2u(ylogx) >> 47) & 0xffffu) >= (0x405F800000000000ull >> 47)) return ::powf(x, y);  // |y log2 x| >= 126
     // exp2_inline (sign_bias = 0)
     double kd = ylogx + K.shift;
     const uint64_t ki = d2u(kd);

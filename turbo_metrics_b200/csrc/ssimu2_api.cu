@@ -628,7 +628,7 @@ int ssimu2_debug_read(ssimu2_t* h, uint64_t ticket, int what, int scale, float* 
 
 int ssimu2_debug_math(int op, const float* in, float y, float* out, size_t n)
 {
-    if (!in || !out || op < 0 || op > 4) return SSIMU2_E_INVALID;
+    if (!in || !out || op < 0 || op > 6) return SSIMU2_E_INVALID;
     if (n == 0) return SSIMU2_OK;
     const size_t in_b = op == 3 ? n * 16 : (op == 4 ? n * 8 : n * 4), out_b = op == 3 ? n * 8 : n * 4;
     float *din = nullptr, *dout = nullptr;

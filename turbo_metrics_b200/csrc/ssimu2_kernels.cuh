@@ -87,24 +87,29 @@ __constant__ exact_math::Consts kEM = EM_CONSTS_INIT;
 // BT709::eotf, cuda-colorspace-kernel/src/lib.rs:220-236 (same body for the BT601 variants).
 // The reference uses __nv_fast_powf (not reproducible on a CPU); the oracle and this kernel both use
 // glibc's powf, bit for bit (exact_math.cuh).
+// The argument comes from integer samples and f32 coefficients: finite, and > 0.16 on the power branch,
+// so the unchecked powf applies.
 __device__ __forceinline__ float bt709_eotf(float v, const exact_math::PowfTables& T)
 {
     const float BETA = 0.018053968510807f;
     const float ALPHA = 1.0f + 5.5f * BETA;
     const float THRESHOLD = 0.08124285829863521110029445797874f;
     if (v >= THRESHOLD)
-        return exact_math::powf_glibc(exact_math::fdiv_normal(v + (ALPHA - 1.0f), ALPHA), 1.0f / 0.45f, kEM, T);
+        return exact_math::powf_glibc<false>(exact_math::fdiv_normal(v + (ALPHA - 1.0f), ALPHA), 1.0f / 0.45f, kEM, T);
     return v / 4.5f;
 }
 
 // srgb_inverse_oetf, cuda-colorspace-kernel/src/srgb.rs:40-48.
+// CHECKED: the f32 pixel format can carry anything (nan, inf, huge); u16 cannot.
+template <bool CHECKED>
 __device__ __forceinline__ float srgb_inverse_oetf(float x, const exact_math::PowfTables& T)
 {
     const float SRGB_ALPHA = 1.0550107f;
     const float SRGB_BETA = 0.0030412825f;
     if (x < 12.92f * SRGB_BETA)
         return x / 12.92f;
-    return exact_math::powf_glibc(exact_math::fdiv_normal(x + (SRGB_ALPHA - 1.0f), SRGB_ALPHA), 2.4f, kEM, T);
+    if (CHECKED) return exact_math::powf_glibc<true>((x + (SRGB_ALPHA - 1.0f)) / SRGB_ALPHA, 2.4f, kEM, T);
+    return exact_math::powf_glibc<false>(exact_math::fdiv_normal(x + (SRGB_ALPHA - 1.0f), SRGB_ALPHA), 2.4f, kEM, T);
 }
 
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
@@ -145,14 +150,14 @@ __device__ __forceinline__ void load_px(const FrameIn& f, int x, int y, const Yu
         b = kSrgb8Lut[__ldg(p + 2)];
     } else if constexpr (FMT == kSRGB16) {
         const uint16_t* p = reinterpret_cast<const uint16_t*>(f.p0 + (size_t)y * f.pitch) + 3 * x;
-        r = srgb_inverse_oetf((float)__ldg(p) / 65535.0f, T);
-        g = srgb_inverse_oetf((float)__ldg(p + 1) / 65535.0f, T);
-        b = srgb_inverse_oetf((float)__ldg(p + 2) / 65535.0f, T);
+        r = srgb_inverse_oetf<false>((float)__ldg(p) / 65535.0f, T);
+        g = srgb_inverse_oetf<false>((float)__ldg(p + 1) / 65535.0f, T);
+        b = srgb_inverse_oetf<false>((float)__ldg(p + 2) / 65535.0f, T);
     } else {
         const float* p = reinterpret_cast<const float*>(f.p0 + (size_t)y * f.pitch) + 3 * x;
         r = __ldg(p); g = __ldg(p + 1); b = __ldg(p + 2);
         if constexpr (FMT == kSRGBF32) {
-            r = srgb_inverse_oetf(r, T); g = srgb_inverse_oetf(g, T); b = srgb_inverse_oetf(b, T);
+            r = srgb_inverse_oetf<true>(r, T); g = srgb_inverse_oetf<true>(g, T); b = srgb_inverse_oetf<true>(b, T);
         }
     }
 }
@@ -170,9 +175,20 @@ __device__ __forceinline__ void linear_to_xyb(float r, float g, float b, const e
     float rg = fmaf(K_M00, r, fmaf(K_M01, g, fmaf(K_M02, b, K_B0)));
     float gr = fmaf(K_M10, r, fmaf(K_M11, g, fmaf(K_M12, b, K_B0)));
     float bb = fmaf(K_M20, r, fmaf(K_M21, g, fmaf(K_M22, b, K_B0)));
-    rg = exact_math::cbrtf_glibc(fmaxf(rg, 0.0f), kEM, &S) - K_B0_ROOT;
-    gr = exact_math::cbrtf_glibc(fmaxf(gr, 0.0f), kEM, &S) - K_B0_ROOT;
-    bb = exact_math::cbrtf_glibc(fmaxf(bb, 0.0f), kEM, &S) - K_B0_ROOT;
+    rg = fmaxf(rg, 0.0f); gr = fmaxf(gr, 0.0f); bb = fmaxf(bb, 0.0f);
+    // in-range frames give arguments in [0.0037, 1.01]; anything else (only possible with the f32 pixel
+    // formats) takes the fully checked routine
+    const float lo = fminf(fminf(rg, gr), bb), hi = fmaxf(fmaxf(rg, gr), bb);
+    if (lo >= 1.17549435e-38f && hi <= 3.0e38f) {
+        rg = exact_math::cbrtf_glibc<false>(rg, kEM, &S);
+        gr = exact_math::cbrtf_glibc<false>(gr, kEM, &S);
+        bb = exact_math::cbrtf_glibc<false>(bb, kEM, &S);
+    } else {
+        rg = exact_math::cbrtf_glibc<true>(rg, kEM, &S);
+        gr = exact_math::cbrtf_glibc<true>(gr, kEM, &S);
+        bb = exact_math::cbrtf_glibc<true>(bb, kEM, &S);
+    }
+    rg -= K_B0_ROOT; gr -= K_B0_ROOT; bb -= K_B0_ROOT;
     float x = 0.5f * (rg - gr);
     float y = 0.5f * (rg + gr);
     X = fmaf(x, 14.0f, 0.42f);
@@ -485,7 +501,7 @@ __global__ void __launch_bounds__(kHThreads, 2) k_hpass(const __grid_constant__ 
 // of each filter is a per-thread ring in shared memory (no barriers in the main loop).
 // ------------------------------------------------------------------------------------------
 #ifndef KV_MINB
-#define KV_MINB 3
+#define KV_MINB 2
 #endif
 constexpr int kVCols = 64;
 constexpr int kVThreads = 3 * kVCols;
@@ -759,6 +775,7 @@ __global__ void __launch_bounds__(128) k_finalize(const __grid_constant__ Geo g,
 //   op 0: out[i] = cbrtf(in[i])            op 1: out[i] = powf(in[i], y)
 //   op 2: out[i] = fdiv_normal(in[i], y)   op 3: in = n pairs of doubles (num, den), out = n doubles ddiv_normal
 //   op 4: out[i] = div_rn_normal(in[2i], in[2i+1]) (the V-pass quotient)
+//   op 5 / 6: the unchecked hot-path forms of op 0 / 1 (positive normal arguments only)
 __global__ void k_debug_math(int op, const float* __restrict__ in, float y, float* __restrict__ out, size_t n)
 {
     __shared__ exact_math::CbrtScale S;
@@ -766,8 +783,10 @@ __global__ void k_debug_math(int op, const float* __restrict__ in, float y, floa
     __syncthreads();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (op == 0) out[i] = exact_math::cbrtf_glibc(in[i], kEM, &S);
-    else if (op == 1) out[i] = exact_math::powf_glibc(in[i], y, kEM, kPowfTablesInit);
+    if (op == 0) out[i] = exact_math::cbrtf_glibc<true>(in[i], kEM, &S);
+    else if (op == 1) out[i] = exact_math::powf_glibc<true>(in[i], y, kEM, kPowfTablesInit);
+    else if (op == 5) out[i] = exact_math::cbrtf_glibc<false>(in[i], kEM, &S);
+    else if (op == 6) out[i] = exact_math::powf_glibc<false>(in[i], y, kEM, kPowfTablesInit);
     else if (op == 2) out[i] = exact_math::fdiv_normal(in[i], y);
     else if (op == 3) {
         const double* din = reinterpret_cast<const double*>(in);

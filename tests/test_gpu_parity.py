@@ -315,3 +315,22 @@ def test_property_checks_at_full_size():
     assert s[0] == s[3] and s[2] == s[4]
     assert 0 < s[0] < 100 and 0 < s[2] < 100
     assert s[5] < min(s[0], s[2])  # unrelated frame is far worse than its own distorted version
+
+
+def test_engine_compute_one_and_compute_all(oracle):
+    """TurboMetrics mirror (turbo-metrics/src/lib.rs:268-433): per-pair call and the submit-ahead frame loop give
+    the same ordered score stream."""
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    w, h, n = 320, 192, 11
+    pairs = [synth.make_pair_yuv420(w, h, 8, frame=i, seed=33) for i in range(n)]
+    pitch, ch = pairs[0][2], pairs[0][3]
+    dev = [(r.cuda(), d.cuda()) for r, d, _, _ in pairs]
+    F = lambda t: tm.DeviceFrame.yuv420(t, pitch, ch)
+    eng = tm.TurboMetrics(w, h, tm.PixelFormat.NV12, batch=4, ring=2)
+    one = [eng.compute_one(F(r), F(d)).ssimulacra2 for r, d in dev]
+    allp = eng.compute_all((F(r), F(d)) for r, d in dev)
+    eng.close()
+    assert one == allp
+    expect = [oracle.ssimu2_yuv420(r.numpy(), d.numpy(), pitch, ch, w, h, 8)[0] for r, d, _, _ in pairs[:3]]
+    assert max(abs(a - b) for a, b in zip(one, expect)) <= SCORE_ATOL

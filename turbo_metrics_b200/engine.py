@@ -1,0 +1,112 @@
+"""Host-side mirror of the reference's per-pair driver `TurboMetrics`
+(/root/reference/crates/turbo-metrics/src/lib.rs:188-433) for the SSIMULACRA2 metric, plus the frame
+sharding the reference does not have (it is single-GPU: device 0 is hard-coded, lib.rs:442).
+
+* `TurboMetrics.compute_one(fref, fdis)`  -- same contract as lib.rs:268-360: one pair in, `FrameScores` out,
+  host-synchronous (the score is fetched before returning).
+* `TurboMetrics.compute_all(pairs)`       -- the frame loop of lib.rs:362-433 re-done for throughput: pairs are
+  submitted ahead (batch x ring in flight) and scores are collected in submission order.
+* `shard_range / gather_scores`           -- frame pairs are independent, so N GPUs = N processes, each scoring a
+  contiguous shard; only scalar scores are exchanged (ordered gather to rank 0).  No data-path collective.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+from .ssimulacra2 import ColorMatrix, DeviceFrame, PixelFormat, Ssimulacra2
+
+
+@dataclass
+class FrameScores:
+    """turbo-metrics/src/lib.rs:114-123 (only the metric of this path is ever populated)."""
+    psnr: Optional[float] = None
+    ssim: Optional[float] = None
+    msssim: Optional[float] = None
+    ssimulacra2: Optional[float] = None
+
+
+@dataclass
+class Options:
+    """turbo-metrics/src/lib.rs:40-54: frame selection of `compute_all`."""
+    every: int = 1
+    skip: int = 0
+    skip_ref: int = 0
+    skip_dis: int = 0
+    frames: int = 0  # 0 = all
+
+
+def select_frames(n_ref: int, n_dis: int, opt: Options) -> List[Tuple[int, int]]:
+    """Index pairs (ref_idx, dis_idx) the reference loop scores (lib.rs:385-400): skip `skip + skip_ref` reference
+    frames and `skip + skip_dis` distorted frames; with k counting the frames decoded after that, score k when
+    `k % every == 0`, and stop at the first scored candidate with `k >= frames` (`frames` bounds the DECODE count)."""
+    r0, d0 = opt.skip + opt.skip_ref, opt.skip + opt.skip_dis
+    out = []
+    k = 0
+    while r0 + k < n_ref and d0 + k < n_dis:
+        if opt.every > 1 and k != 0 and k % opt.every != 0:
+            k += 1
+            continue
+        if opt.frames > 0 and k >= opt.frames:
+            break
+        out.append((r0 + k, d0 + k))
+        k += 1
+    return out
+
+
+def shard_range(n: int, rank: int, world: int) -> range:
+    """Contiguous shard of `n` frame pairs for `rank` of `world` (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return range(start, start + base + (1 if rank < rem else 0))
+
+
+def gather_scores(local: Sequence[float], n_total: int, rank: int, world: int, group=None) -> Optional[List[float]]:
+    """Ordered per-frame score stream on rank 0 (None elsewhere).  Only 8 bytes per frame cross the process
+    boundary; works on any torch.distributed backend (nccl on GPUs, gloo in the CPU tests)."""
+    if world == 1:
+        return list(local)
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    sizes = [len(shard_range(n_total, r, world)) for r in range(world)]
+    mx = max(sizes)
+    buf = torch.full((mx,), float("nan"), dtype=torch.float64, device=dev)
+    buf[: len(local)] = torch.tensor(list(local), dtype=torch.float64, device=dev)
+    out = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, out, dst=0, group=group)
+    if rank != 0:
+        return None
+    res: List[float] = []
+    for r in range(world):
+        res.extend(out[r][: sizes[r]].cpu().tolist())
+    return res
+
+
+class TurboMetrics:
+    """`TurboMetrics::new(width, height, &Metrics)` (lib.rs:201-251) for metrics = {ssimulacra2}."""
+
+    def __init__(self, width: int, height: int, fmt: PixelFormat, matrix: ColorMatrix = ColorMatrix.BT709,
+                 full_range: bool = False, device: int = 0, batch: int = 0, ring: int = 0):
+        self.ssimulacra2 = Ssimulacra2(width, height, fmt, matrix, full_range, device, batch, ring)
+        info = self.ssimulacra2.info()
+        self.window = info.batch * info.ring
+
+    def close(self):
+        self.ssimulacra2.close()
+
+    def compute_one(self, fref: DeviceFrame, fdis: DeviceFrame, stream=None) -> FrameScores:
+        """lib.rs:268-360."""
+        return FrameScores(ssimulacra2=self.ssimulacra2.compute_sync(fref, fdis, stream))
+
+    def compute_all(self, pairs: Iterable[Tuple[DeviceFrame, DeviceFrame]], stream=None) -> List[float]:
+        """lib.rs:362-433 with submit-ahead: at most batch x ring pairs in flight; scores in submission order."""
+        scores: List[float] = []
+        pending: List[int] = []
+        for fref, fdis in pairs:
+            pending.append(self.ssimulacra2.compute(fref, fdis, stream))
+            if len(pending) >= self.window:
+                scores.append(self.ssimulacra2.get_score(pending.pop(0)))
+        self.ssimulacra2.flush()
+        scores.extend(self.ssimulacra2.get_score(t) for t in pending)
+        return scores

@@ -45,6 +45,7 @@ struct Slot {
     double* scores_h = nullptr;       // pinned
     uint8_t* staging = nullptr;       // device staging for host frames: [batch][2][staging_frame_bytes]
     BatchIn in{};
+    TmaMaps maps{};                   // tensor maps of this slot's H-pass / XYB buffers, per scale
     uint32_t count = 0;               // pairs recorded
     uint64_t first_ticket = 0;
     bool inflight = false;            // launched, results not harvested yet
@@ -170,6 +171,44 @@ static void build_geo(ssimu2_handle* h)
     h->alg_bytes = 120ULL * sum_px + 2ULL * in_bytes_per_px(h->cfg.format) * h->cfg.width * h->cfg.height + 72ULL * sum_px_ge1;
 }
 
+// ---- TMA tensor maps (driver entry point fetched through the runtime; libcuda is not linked) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_plane_map(EncodeTiledFn enc, CUtensorMap* out, float* base, const ScaleDesc& d, int planes, long long slot_stride,
+                          uint32_t batch, uint32_t box_rows)
+{
+    // 4-D view {x, y, plane, frame} of a [frame][plane][h][pitch] f32 buffer; out-of-range elements read as 0
+    cuuint64_t dims[4] = {(cuuint64_t)d.w, (cuuint64_t)d.h, (cuuint64_t)planes, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {(cuuint64_t)d.pitch * 4, (cuuint64_t)d.h * d.pitch * 4, (cuuint64_t)slot_stride * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kVCols, box_rows, (cuuint32_t)planes, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : SSIMU2_E_INTERNAL;
+}
+
+static int build_tma_maps(ssimu2_handle* h, Slot& sl)
+{
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return SSIMU2_E_INTERNAL;
+    }
+    EncodeTiledFn enc = (EncodeTiledFn)fn;
+    const Geo& g = h->geo;
+    for (int s = 0; s < g.nscales; s++) {
+        int r = make_plane_map(enc, &sl.maps.hb[s], sl.hb + g.sc[s].hb_off, g.sc[s], 15, g.hb_stride, h->batch, kVRowsPerStage);
+        if (r) return r;
+        r = make_plane_map(enc, &sl.maps.xyb[s], sl.xyb + g.sc[s].xyb_off, g.sc[s], 6, g.xyb_stride, h->batch, kVRowsPerStage);
+        if (r) return r;
+    }
+    return 0;
+}
+
 template <int FMT>
 static int launch_batch_fmt(ssimu2_handle* h, Slot& sl)
 {
@@ -184,7 +223,7 @@ static int launch_batch_fmt(ssimu2_handle* h, Slot& sl)
     if (sl.timed) cudaEventRecord(sl.ev_k[1], st);
     k_hpass<<<dim3(g.items_h, n), kHThreads, kHSmemBytes, st>>>(g, sl.xyb, sl.hb);
     if (sl.timed) cudaEventRecord(sl.ev_k[2], st);
-    k_vpass<<<dim3(g.items_v, n), kVThreads, 0, st>>>(g, sl.xyb, sl.hb, sl.partials);
+    k_vpass<<<dim3(g.items_v, n), kVTmaThreads, kVSmemBytes, st>>>(g, sl.maps, sl.partials);
     if (sl.timed) cudaEventRecord(sl.ev_k[3], st);
     k_finalize<<<n, 128, 0, st>>>(g, sl.partials, sl.norms_d, h->scores_ring_d, sl.first_ticket, kResultCap, sl.scores_d);
     if (sl.timed) cudaEventRecord(sl.ev_k[4], st);
@@ -241,8 +280,6 @@ static int harvest(ssimu2_handle* h, uint32_t si)
     sl.count = 0;
     return 0;
 }
-
-static int set_device(const ssimu2_handle* h) { return (int)cudaSetDevice(h->cfg.device); }
 
 // make slot `cur` ready to record a pair
 static int prepare_cur(ssimu2_handle* h)
@@ -365,6 +402,7 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
     CR(cudaMemset(h->scores_ring_d, 0, kResultCap * sizeof(double)));
     h->device_bytes += kResultCap * sizeof(double);
     CR(cudaFuncSetAttribute((const void*)k_hpass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBytes));
+    CR(cudaFuncSetAttribute((const void*)k_vpass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVSmemBytes));
     {
         static const void* ffn[6] = {(const void*)k_frontend<kNV12>,    (const void*)k_frontend<kP016>,
                                      (const void*)k_frontend<kSRGB8>,   (const void*)k_frontend<kSRGB16>,
@@ -389,6 +427,8 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
         CR(cudaMallocHost(&sl.norms_h, (size_t)h->batch * 108 * sizeof(double)));
         CR(cudaMallocHost(&sl.scores_h, (size_t)h->batch * sizeof(double)));
         h->device_bytes += xyb_b + hb_b + part_b + (size_t)h->batch * 109 * sizeof(double);
+        rc = build_tma_maps(h, sl);
+        if (rc) goto fail;
         sl.timed = getenv("SSIMU2_NO_TIMING") == nullptr;
     }
     *out = h;

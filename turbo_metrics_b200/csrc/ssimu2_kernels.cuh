@@ -14,6 +14,7 @@
 // CPU path; compile with -fmad=false, fused ops are explicit fmaf()/fma().  The GPU reference
 // kernels each function replaces are cited at the function.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -500,9 +501,6 @@ __global__ void __launch_bounds__(kHThreads, 2) k_hpass(const __grid_constant__ 
 // iteration so that 7*kVUnroll independent loads are in flight per thread; the 10-row delay line
 // of each filter is a per-thread ring in shared memory (no barriers in the main loop).
 // ------------------------------------------------------------------------------------------
-#ifndef KV_MINB
-#define KV_MINB 2
-#endif
 constexpr int kVCols = 64;
 constexpr int kVThreads = 3 * kVCols;
 constexpr int kVRing = 10;
@@ -576,118 +574,165 @@ __device__ __forceinline__ void error_maps(const float (&o)[5], float ref, float
     part[5] += pos ? 0.0f : e4;
 }
 
-__global__ void __launch_bounds__(kVThreads, KV_MINB) k_vpass(const __grid_constant__ Geo g, const float* __restrict__ xyb_base,
-                                                        const float* __restrict__ hb_base, double* __restrict__ partials)
+// ---- TMA / mbarrier plumbing (PTX; sm_90+ instructions, SASS: UTMALDG / SYNCS) -------------------
+struct alignas(64) TmaMaps {
+    CUtensorMap hb[kMaxScales];   // 4-D {x, y, plane(15), frame}, box {64, kVRowsPerStage, 15, 1}
+    CUtensorMap xyb[kMaxScales];  // 4-D {x, y, plane(6),  frame}, box {64, kVRowsPerStage, 6, 1}
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
-    __shared__ float ring[kVRing * 5 * kVThreads];
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+// k_vpass, TMA-fed.  CTA = one 64-column strip of one scale of one frame; 6 consumer warps = (channel c, column x)
+// + 1 producer warp.  The producer streams {hb rows t, t+1 ; xyb rows t-4, t-3} boxes into a 5-stage shared-memory
+// ring with cp.async.bulk.tensor (out-of-range rows / columns arrive as zeros = the filter's zero padding, so the loop
+// has no edge cases); full/empty mbarriers per stage.  Each consumer thread runs its 5 filters down the column: the
+// 10-row delay line lives in REGISTERS (the row loop is unrolled by 10 = one turn of the ring), shared memory is read
+// once per value, there are no block-wide barriers and no global-memory instructions in the loop.
+constexpr int kVRowsPerStage = 2;
+constexpr int kVStages = kVRing / kVRowsPerStage;                  // 5 stages = one 10-row group
+constexpr int kVBoxHb = 15 * kVRowsPerStage * kVCols;              // floats
+constexpr int kVBoxXyb = 6 * kVRowsPerStage * kVCols;
+constexpr int kVStageFloats = kVBoxHb + kVBoxXyb;                  // 2688 floats = 10752 B
+constexpr uint32_t kVStageBytes = kVStageFloats * sizeof(float);
+constexpr int kVTmaThreads = kVThreads + 32;                       // + producer warp
+constexpr size_t kVSmemBytes = (size_t)kVStages * kVStageBytes + 128;
+
+__global__ void __launch_bounds__(kVTmaThreads, 2) k_vpass(const __grid_constant__ Geo g, const __grid_constant__ TmaMaps maps,
+                                                           double* __restrict__ partials)
+{
+    extern __shared__ __align__(128) float vs[];
+    __shared__ uint64_t full_bar[kVStages], empty_bar[kVStages];
     __shared__ double red[kVThreads / 32][6];
 
     const int frame = blockIdx.y;
     int item = blockIdx.x, s = 0;
     while (item >= g.sc[s].n_strips) { item -= g.sc[s].n_strips; s++; }
     const ScaleDesc sd = g.sc[s];
-    const size_t plane = (size_t)sd.h * sd.pitch;
-    const float* xyb = xyb_base + (size_t)frame * g.xyb_stride + sd.xyb_off;
-    const float* hb = hb_base + (size_t)frame * g.hb_stride + sd.hb_off;
+    const int H = sd.h;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ngroups = (H + 4 + kVRing - 1) / kVRing;
 
-    const int tid = threadIdx.x, tx = tid % kVCols, c = tid / kVCols;
-    const int xq = item * kVCols + tx;
-    const bool active = xq < sd.w;
-    const int x = active ? xq : sd.w - 1;  // idle lanes shadow the last column; their sums are dropped
-    const int H = sd.h, pitch = sd.pitch;
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kVStages; i++) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], kVThreads / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
-    VState st[5];
+    if (warp == kVThreads / 32) {
+        // ===== producer warp: one elected lane issues the TMA loads =====
+        if (lane == 0) {
+            const CUtensorMap* mhb = &maps.hb[s];
+            const CUtensorMap* mxyb = &maps.xyb[s];
+            const int x0 = item * kVCols;
+            for (int gi = 0; gi < ngroups; gi++) {
+#pragma unroll 1
+                for (int st = 0; st < kVStages; st++) {
+                    if (gi > 0) mbar_wait(&empty_bar[st], (uint32_t)((gi - 1) & 1));
+                    float* dst = vs + st * kVStageFloats;
+                    const int row = gi * kVRing + st * kVRowsPerStage;
+                    mbar_expect_tx(&full_bar[st], kVStageBytes);
+                    tma_load_4d(dst, mhb, &full_bar[st], x0, row, 0, frame);
+                    tma_load_4d(dst + kVBoxHb, mxyb, &full_bar[st], x0, row - 4, 0, frame);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const int tx = tid % kVCols, c = tid / kVCols;
+    VState stq[5];
 #pragma unroll
-    for (int qi = 0; qi < 5; qi++) st[qi] = VState{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float* rp = ring + tid;  // element (slot, q) at rp[(slot * 5 + q) * kVThreads]
+    for (int qi = 0; qi < 5; qi++) stq[qi] = VState{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float dl[kVRing][5];  // delay line: the input of 10 rows ago, per quantity
 #pragma unroll
-    for (int i = 0; i < kVRing * 5; i++) rp[i * kVThreads] = 0.f;
+    for (int i = 0; i < kVRing; i++)
+#pragma unroll
+        for (int qi = 0; qi < 5; qi++) dl[i][qi] = 0.f;
     double acc[6] = {0, 0, 0, 0, 0, 0};
 
-    // row pointers: p[q] walks plane (q*3 + c) of the H-pass output at row t, pr / pd walk the XYB planes of
-    // channel c at row n = t - 4
-    const float* p[5];
+    for (int gi = 0; gi < ngroups; gi++) {
+        const uint32_t parity = (uint32_t)(gi & 1);
+        float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int qi = 0; qi < 5; qi++) p[qi] = hb + (size_t)(qi * 3 + c) * plane + x;
-    const float* pr = xyb + (size_t)c * plane + x;
-    const float* pd = xyb + (size_t)(3 + c) * plane + x;
-
-    // generic step (any t): used for the first 4 rows (no output yet), the tail, and tiny images
-    int t = 0, slot = 0;
-    auto slow_step = [&]() {
-        float v[5], part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, o[5];
-        const bool ld = t < H;
+        for (int st = 0; st < kVStages; st++) {
+            mbar_wait(&full_bar[st], parity);
+            const float* sb = vs + st * kVStageFloats;
 #pragma unroll
-        for (int qi = 0; qi < 5; qi++) {
-            v[qi] = ld ? __ldg(p[qi]) : 0.f;
-            p[qi] += pitch;
-        }
-        float* rs = rp + slot * 5 * kVThreads;
-#pragma unroll
-        for (int qi = 0; qi < 5; qi++) {
-            const float old = rs[qi * kVThreads];
-            rs[qi * kVThreads] = v[qi];
-            o[qi] = vstep(st[qi], old, v[qi]);
-        }
-        if (t >= 4) {
-            const float fr = __ldg(pr), fd = __ldg(pd);
-            pr += pitch; pd += pitch;
-            error_maps(o, fr, fd, part);
-#pragma unroll
-            for (int k = 0; k < 6; k++) acc[k] += (double)part[k];
-        }
-        slot = (slot == kVRing - 1) ? 0 : slot + 1;
-        t++;
-    };
-
-    const int nsteps = H + 4;
-    while (t < 4 && t < nsteps) slow_step();
-    // main loop: t = 4 (mod 10) at the top, rows t .. t+9 all inside the image, ring slots static
-    while (t + kVRing <= H) {
-#pragma unroll
-        for (int half = 0; half < kVRing / kVSub; half++) {
-            float v[kVSub][5], fr[kVSub], fd[kVSub];
-#pragma unroll
-            for (int r = 0; r < kVSub; r++) {
-#pragma unroll
-                for (int qi = 0; qi < 5; qi++) {
-                    v[r][qi] = __ldg(p[qi]);
-                    p[qi] += pitch;
-                }
-                fr[r] = __ldg(pr); fd[r] = __ldg(pd);
-                pr += pitch; pd += pitch;
-            }
-            float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int r = 0; r < kVSub; r++) {
-                constexpr int kBase = 4;  // slot of the first row of a group
-                const int sl = (kBase + half * kVSub + r) % kVRing;
-                float* rs = rp + sl * 5 * kVThreads;
+            for (int r = 0; r < kVRowsPerStage; r++) {
+                constexpr int dummy = 0; (void)dummy;
+                const int slot = st * kVRowsPerStage + r;
+                const int t = gi * kVRing + slot;
                 float o[5];
 #pragma unroll
                 for (int qi = 0; qi < 5; qi++) {
-                    const float old = rs[qi * kVThreads];
-                    rs[qi * kVThreads] = v[r][qi];
-                    o[qi] = vstep(st[qi], old, v[r][qi]);
+                    const float v = sb[((qi * 3 + c) * kVRowsPerStage + r) * kVCols + tx];
+                    o[qi] = vstep(stq[qi], dl[slot][qi], v);
+                    dl[slot][qi] = v;
                 }
-                error_maps(o, fr[r], fd[r], part);
+                const float fr = sb[kVBoxHb + ((0 + c) * kVRowsPerStage + r) * kVCols + tx];
+                const float fd = sb[kVBoxHb + ((3 + c) * kVRowsPerStage + r) * kVCols + tx];
+                if (t >= 4 && t < H + 4) error_maps(o, fr, fd, part);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[st]);
+            if (st == kVStages / 2) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) acc[k] += (double)part[k];
+                for (int k = 0; k < 6; k++) { acc[k] += (double)part[k]; part[k] = 0.f; }
+            }
         }
-        t += kVRing;  // slot is unchanged: a whole turn of the ring
+#pragma unroll
+        for (int k = 0; k < 6; k++) acc[k] += (double)part[k];
     }
-    while (t < nsteps) slow_step();
 
-    // block reduction: warps are channel-uniform (64 columns = 2 warps per channel)
+    // reduction over the 6 consumer warps (channel-uniform: 64 columns = 2 warps per channel); the producer warp
+    // has exited, so a named barrier over the consumer threads only
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-        double vsum = active ? acc[k] : 0.0;
+        double vsum = acc[k];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) vsum += __shfl_down_sync(0xffffffffu, vsum, off);
-        if ((tid & 31) == 0) red[tid >> 5][k] = vsum;
+        if (lane == 0) red[warp][k] = vsum;
     }
-    __syncthreads();
+    asm volatile("bar.sync 1, %0;" ::"n"(kVThreads) : "memory");
     if (tid < 18) {
         int cc = tid / 6, k = tid % 6;
         double vsum = red[2 * cc][k] + red[2 * cc + 1][k];

@@ -45,7 +45,8 @@ struct Slot {
     double* scores_h = nullptr;       // pinned
     uint8_t* staging = nullptr;       // device staging for host frames: [batch][2][staging_frame_bytes]
     BatchIn in{};
-    TmaMaps maps{};                   // tensor maps of this slot's H-pass / XYB buffers, per scale
+    TmaMaps maps{};                   // tensor maps of this slot's H-pass / XYB buffers, per scale (V pass)
+    TmaMapsH maps_h{};                // (H pass)
     uint32_t count = 0;               // pairs recorded
     uint64_t first_ticket = 0;
     bool inflight = false;            // launched, results not harvested yet
@@ -177,15 +178,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static int make_plane_map(EncodeTiledFn enc, CUtensorMap* out, float* base, const ScaleDesc& d, int planes, long long slot_stride,
-                          uint32_t batch, uint32_t box_rows)
+                          uint32_t batch, uint32_t box_cols, uint32_t box_rows, bool swizzle128)
 {
     // 4-D view {x, y, plane, frame} of a [frame][plane][h][pitch] f32 buffer; out-of-range elements read as 0
     cuuint64_t dims[4] = {(cuuint64_t)d.w, (cuuint64_t)d.h, (cuuint64_t)planes, (cuuint64_t)batch};
     cuuint64_t strides[3] = {(cuuint64_t)d.pitch * 4, (cuuint64_t)d.h * d.pitch * 4, (cuuint64_t)slot_stride * 4};
-    cuuint32_t box[4] = {(cuuint32_t)kVCols, box_rows, (cuuint32_t)planes, 1};
+    cuuint32_t box[4] = {box_cols, box_rows, (cuuint32_t)planes, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : SSIMU2_E_INTERNAL;
 }
 
@@ -201,9 +203,15 @@ static int build_tma_maps(ssimu2_handle* h, Slot& sl)
     EncodeTiledFn enc = (EncodeTiledFn)fn;
     const Geo& g = h->geo;
     for (int s = 0; s < g.nscales; s++) {
-        int r = make_plane_map(enc, &sl.maps.hb[s], sl.hb + g.sc[s].hb_off, g.sc[s], 15, g.hb_stride, h->batch, kVRowsPerStage);
+        float* hb = sl.hb + g.sc[s].hb_off;
+        float* xyb = sl.xyb + g.sc[s].xyb_off;
+        int r = make_plane_map(enc, &sl.maps.hb[s], hb, g.sc[s], 15, g.hb_stride, h->batch, kVCols, kVRowsPerStage, false);
         if (r) return r;
-        r = make_plane_map(enc, &sl.maps.xyb[s], sl.xyb + g.sc[s].xyb_off, g.sc[s], 6, g.xyb_stride, h->batch, kVRowsPerStage);
+        r = make_plane_map(enc, &sl.maps.xyb[s], xyb, g.sc[s], 6, g.xyb_stride, h->batch, kVCols, kVRowsPerStage, false);
+        if (r) return r;
+        r = make_plane_map(enc, &sl.maps_h.xyb_in[s], xyb, g.sc[s], 6, g.xyb_stride, h->batch, kHCols, kHRows, true);
+        if (r) return r;
+        r = make_plane_map(enc, &sl.maps_h.hb_out[s], hb, g.sc[s], 15, g.hb_stride, h->batch, kHCols, kHRows, true);
         if (r) return r;
     }
     return 0;
@@ -221,7 +229,7 @@ static int launch_batch_fmt(ssimu2_handle* h, Slot& sl)
         k_frontend<FMT><<<grid, kFThreads, kFSmemBytes, st>>>(g, sl.in, sl.xyb);
     }
     if (sl.timed) cudaEventRecord(sl.ev_k[1], st);
-    k_hpass<<<dim3(g.items_h, n), kHThreads, kHSmemBytes, st>>>(g, sl.xyb, sl.hb);
+    k_hpass<<<dim3(g.items_h, n), kHThreads, kHSmemBytes, st>>>(g, sl.maps_h);
     if (sl.timed) cudaEventRecord(sl.ev_k[2], st);
     k_vpass<<<dim3(g.items_v, n), kVTmaThreads, kVSmemBytes, st>>>(g, sl.maps, sl.partials);
     if (sl.timed) cudaEventRecord(sl.ev_k[3], st);

@@ -324,31 +324,89 @@ __global__ void __launch_bounds__(kFThreads) k_frontend(const __grid_constant__ 
     }
 }
 
+// ---- TMA / mbarrier plumbing (PTX; sm_90+ instructions, SASS: UTMALDG / SYNCS) -------------------
+// Tensor maps of one batch slot, per scale.  All are 4-D {x, y, plane, frame} views of [frame][plane][h][pitch] f32.
+struct alignas(64) TmaMaps {
+    CUtensorMap hb[kMaxScales];      // V pass load : 15 planes, box {64, 2, 15, 1}, no swizzle
+    CUtensorMap xyb[kMaxScales];     // V pass load :  6 planes, box {64, 2, 6, 1},  no swizzle
+};
+struct alignas(64) TmaMapsH {
+    CUtensorMap xyb_in[kMaxScales];  // H pass load :  6 planes, box {32, 32, 6, 1},  128B swizzle
+    CUtensorMap hb_out[kMaxScales];  // H pass store: 15 planes, box {32, 32, 15, 1}, 128B swizzle
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------
-// k_hpass: products + horizontal recursive Gaussian.
+// k_hpass: products + horizontal recursive Gaussian, TMA in / TMA out.
 // Replaces nppiMul x3 (ssimulacra2-cuda/src/lib.rs:300-317) and one of the two
 // blur_plane_pass_fused launches + its nppiTranspose x5 (lib.rs:328-361).
 // Follows image_multiply cpu.rs:537-543 and RecursiveGaussian::horizontal_row cpu.rs:967-1022.
 //
-// CTA = one 32-row band of one scale of one frame; 512 threads.
-//   load  : all threads, 128-bit coalesced loads of the next 6 x 32 x 32 XYB chunk into registers
-//           (zero outside the row = the filter's zero padding), parked in shared memory after the scan
-//   scan  : warp p (0..14) = plane (quantity q = p/3, channel c = p%3), lane = row; walks the chunk
-//           4 columns per 128-bit smem access, filter state in registers across chunks
-//   store : all threads, 128-bit coalesced stores of the 15 x 32 x 32 output tile
+// CTA = one 32-row band of one scale of one frame; 15 scan warps + 1 control warp, 2 CTAs per SM.
+//   control : one lane streams 6 x 32 x 32 XYB chunks into a 2-stage shared-memory ring with
+//             cp.async.bulk.tensor (128B swizzle; columns < 0 or >= W arrive as zeros = the filter's zero
+//             padding) and writes each finished 15 x 32 x 32 output tile back with a TMA store (clipped at the
+//             image edge by the hardware)
+//   scan    : warp p (0..14) = plane (quantity q = p/3, channel c = p%3), lane = row; walks the chunk 4 columns
+//             per 128-bit shared-memory access (swizzle => conflict-free), filter state in registers across chunks
 // Step t consumes x[t] (right tap, index n+4) and x[t-10] (left tap, n-6) and emits y[t-4]
 // (n = t-4, cpu.rs:976-984).  Chunk k (k = -1, 0, ...) covers steps 32k+4 .. 32k+35, i.e. outputs
 // 32k .. 32k+31; chunk -1 only warms the state with x[0..3] (its other inputs are the zero padding).
 // ------------------------------------------------------------------------------------------
 constexpr int kHRows = 32;
 constexpr int kHCols = 32;
-constexpr int kHPitch = 36;  // floats; 144 B = 9 x 16 B -> conflict-free 128-bit row-per-lane access
-constexpr int kHThreads = 512;
-constexpr int kHSmemIn = 6 * kHRows * kHPitch;   // [img*3+ch][row][col]
-constexpr int kHSmemOut = 15 * kHRows * kHPitch;  // [plane][row][col]
-constexpr size_t kHSmemBytes = (size_t)(kHSmemIn + kHSmemOut) * sizeof(float);  // 96.8 KB -> 2 CTAs per SM
-constexpr int kHLoadsPerThread = 6 * kHRows * (kHCols / 4) / kHThreads;    // 3
-constexpr int kHStoresPerThread = (15 * kHRows * (kHCols / 4) + kHThreads - 1) / kHThreads;  // 8 (last one half-populated)
+constexpr int kHScanWarps = 15;
+constexpr int kHThreads = (kHScanWarps + 1) * 32;
+constexpr int kHInStages = 2;
+constexpr uint32_t kHInBytes = 6 * kHRows * kHCols * sizeof(float);    // 24576
+constexpr uint32_t kHOutBytes = 15 * kHRows * kHCols * sizeof(float);  // 61440
+constexpr size_t kHSmemBytes = (size_t)kHInStages * kHInBytes + kHOutBytes + 1024;  // + alignment slack
 
 struct HState {
     float p1, p3, p5, pp1, pp3, pp5;
@@ -369,18 +427,20 @@ __device__ __forceinline__ float hstep(HState& s, float left, float right)
     return (o1 + o3) + o5;
 }
 
+// s_ref / s_dis / s_out point at this lane's 128-byte row; xs = (lane & 7) << 4 is the swizzle term
 template <int Q>
-__device__ __forceinline__ void hscan_chunk(const float* __restrict__ s_ref, const float* __restrict__ s_dis,
-                                            float* __restrict__ s_out, HState& st, float (&hist)[12])
+__device__ __forceinline__ void hscan_chunk(const char* __restrict__ s_ref, const char* __restrict__ s_dis,
+                                            char* __restrict__ s_out, uint32_t xs, HState& st, float (&hist)[12])
 {
     float win[12 + kHCols];
 #pragma unroll
     for (int i = 0; i < 12; i++) win[i] = hist[i];
 #pragma unroll
     for (int gI = 0; gI < kHCols / 4; gI++) {
+        const uint32_t off = ((uint32_t)gI << 4) ^ xs;
         float4 a, d;
-        if (Q == 0 || Q == 2 || Q == 3) a = *reinterpret_cast<const float4*>(s_ref + 4 * gI);
-        if (Q == 1 || Q == 2 || Q == 4) d = *reinterpret_cast<const float4*>(s_dis + 4 * gI);
+        if (Q == 0 || Q == 2 || Q == 3) a = *reinterpret_cast<const float4*>(s_ref + off);
+        if (Q == 1 || Q == 2 || Q == 4) d = *reinterpret_cast<const float4*>(s_dis + off);
         float pr[4];
         if (Q == 0) { pr[0] = a.x * a.x; pr[1] = a.y * a.y; pr[2] = a.z * a.z; pr[3] = a.w * a.w; }
         if (Q == 1) { pr[0] = d.x * d.x; pr[1] = d.y * d.y; pr[2] = d.z * d.z; pr[3] = d.w * d.w; }
@@ -393,98 +453,96 @@ __device__ __forceinline__ void hscan_chunk(const float* __restrict__ s_ref, con
             win[12 + 4 * gI + j] = pr[j];
             o[j] = hstep(st, win[4 * gI + j + 2], pr[j]);  // left tap = 10 columns back
         }
-        *reinterpret_cast<float4*>(s_out + 4 * gI) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(s_out + off) = make_float4(o[0], o[1], o[2], o[3]);
     }
 #pragma unroll
     for (int i = 0; i < 12; i++) hist[i] = win[kHCols + i];
 }
 
-__global__ void __launch_bounds__(kHThreads, 2) k_hpass(const __grid_constant__ Geo g, const float* __restrict__ xyb_base,
-                                                        float* __restrict__ hb_base)
+__global__ void __launch_bounds__(kHThreads, 2) k_hpass(const __grid_constant__ Geo g, const __grid_constant__ TmaMapsH maps)
 {
-    extern __shared__ __align__(16) float smem[];
-    float* s_in = smem;
-    float* s_out = smem + kHSmemIn;
+    extern __shared__ char hs_raw[];
+    __shared__ uint64_t full_in[kHInStages], empty_in[kHInStages], scan_done, out_free;
+    // 128B swizzle wants the tiles 1024-byte aligned
+    char* hs = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(hs_raw) + 1023) & ~(uintptr_t)1023);
+    char* s_in = hs;                             // [stage][6][32 rows][128 B]
+    char* s_out = hs + kHInStages * kHInBytes;   // [15][32 rows][128 B]
 
     const int frame = blockIdx.y;
     int item = blockIdx.x, s = 0;
     while (item >= g.sc[s].n_bands) { item -= g.sc[s].n_bands; s++; }
-    const ScaleDesc sd = g.sc[s];
+    const int W = g.sc[s].w;
     const int row0 = item * kHRows;
-    const size_t plane = (size_t)sd.h * sd.pitch;
-    const float* xyb = xyb_base + (size_t)frame * g.xyb_stride + sd.xyb_off;
-    float* hb = hb_base + (size_t)frame * g.hb_stride + sd.hb_off;
-    const int W = sd.w;
-
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp / 3, ch = warp - 3 * q;  // scan role
+    const int nchunks = (W + kHCols - 1) / kHCols + 1;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kHInStages; i++) {
+            mbar_init(&full_in[i], 1);
+            mbar_init(&empty_in[i], kHScanWarps);
+        }
+        mbar_init(&scan_done, kHScanWarps);
+        mbar_init(&out_free, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kHScanWarps) {
+        // ===== control warp =====
+        if (lane == 0) {
+            const CUtensorMap* min = &maps.xyb_in[s];
+            const CUtensorMap* mout = &maps.hb_out[s];
+            auto issue_load = [&](int kk) {  // chunk k = kk - 1 into stage kk % 2
+                const int st = kk % kHInStages;
+                if (kk >= kHInStages) mbar_wait(&empty_in[st], (uint32_t)(((kk / kHInStages) - 1) & 1));
+                mbar_expect_tx(&full_in[st], kHInBytes);
+                tma_load_4d(s_in + st * kHInBytes, min, &full_in[st], kHCols * (kk - 1) + 4, row0, 0, frame);
+            };
+            issue_load(0);
+            for (int kk = 0; kk < nchunks; kk++) {
+                if (kk + 1 < nchunks) issue_load(kk + 1);
+                mbar_wait(&scan_done, (uint32_t)(kk & 1));  // the scan warps have written tile kk (generic proxy, fenced)
+                if (kk >= 1) {
+                    tma_store_4d(mout, s_out, kHCols * (kk - 1), row0, 0, frame);
+                    tma_store_commit();
+                    tma_store_wait_read();                  // shared memory may be overwritten again
+                }
+                mbar_arrive(&out_free);
+            }
+            tma_store_wait_all();
+        }
+        return;
+    }
+
+    // ===== scan warps =====
+    const int q = warp / 3, ch = warp - 3 * q;
+    const uint32_t xs = (uint32_t)(lane & 7) << 4;
     HState st = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float hist[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) hist[i] = 0.f;
+    char* so = s_out + (warp * kHRows + lane) * 128;
 
-    // copy roles: every index below is loop-invariant; only the column offset of the chunk changes.
-    // tile element idx = tid + i*512 -> (plane idx>>8, row (idx>>3)&31, 4-column group idx&7)
-    const int g4 = tid & 7, r0 = (tid >> 3) & 31, pl0 = tid >> 8;  // idx = tid: plane 0/1; +512 per i: plane += 2
-    const bool row_ok = row0 + r0 < sd.h;
-    const float* gin = xyb + (size_t)pl0 * plane + (size_t)(row0 + r0) * sd.pitch + 4 * g4;  // + 2*i*plane + c0
-    float* gout = hb + (size_t)pl0 * plane + (size_t)(row0 + r0) * sd.pitch + 4 * g4;        // + 2*i*plane + 32k
-    const int s_off = (pl0 * kHRows + r0) * kHPitch + 4 * g4;                                // + 2*i*kHRows*kHPitch
-
-    const int nchunks = (W + kHCols - 1) / kHCols + 1;
-    float4 pre[kHLoadsPerThread];
-
-    int pre_col = 0;
-    auto load_chunk = [&](int k) {  // global -> registers (nothing here may touch the loaded values)
-        const int col = kHCols * k + 4 + 4 * g4;
-        pre_col = col;
-        const bool ok = row_ok && col >= 0 && col < W;
-#pragma unroll
-        for (int i = 0; i < kHLoadsPerThread; i++) {
-            pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) pre[i] = __ldg(reinterpret_cast<const float4*>(gin + (size_t)(2 * i) * plane + (kHCols * k + 4)));
-        }
-    };
-    auto park_chunk = [&]() {  // registers -> shared; columns >= W are the filter's zero padding
-#pragma unroll
-        for (int i = 0; i < kHLoadsPerThread; i++) {
-            float4 v = pre[i];
-            if (pre_col + 1 >= W) v.y = 0.f;
-            if (pre_col + 2 >= W) v.z = 0.f;
-            if (pre_col + 3 >= W) v.w = 0.f;
-            *reinterpret_cast<float4*>(s_in + s_off + 2 * i * kHRows * kHPitch) = v;
-        }
-    };
-
-    load_chunk(-1);
-    park_chunk();
-    __syncthreads();
     for (int kk = 0; kk < nchunks; kk++) {
-        const int k = kk - 1;
-        if (kk + 1 < nchunks) load_chunk(k + 1);
-        if (warp < 15) {
-            const float* s_ref = s_in + (ch * kHRows + lane) * kHPitch;
-            const float* s_dis = s_in + ((3 + ch) * kHRows + lane) * kHPitch;
-            float* so = s_out + (warp * kHRows + lane) * kHPitch;
-            switch (q) {
-            case 0: hscan_chunk<0>(s_ref, s_dis, so, st, hist); break;
-            case 1: hscan_chunk<1>(s_ref, s_dis, so, st, hist); break;
-            case 2: hscan_chunk<2>(s_ref, s_dis, so, st, hist); break;
-            case 3: hscan_chunk<3>(s_ref, s_dis, so, st, hist); break;
-            default: hscan_chunk<4>(s_ref, s_dis, so, st, hist); break;
-            }
+        const int stg = kk % kHInStages;
+        mbar_wait(&full_in[stg], (uint32_t)((kk / kHInStages) & 1));
+        if (kk >= 1) mbar_wait(&out_free, (uint32_t)((kk - 1) & 1));  // tile kk-1 has left shared memory
+        const char* sref = s_in + stg * kHInBytes + ((ch * kHRows + lane) * 128);
+        const char* sdis = s_in + stg * kHInBytes + (((3 + ch) * kHRows + lane) * 128);
+        switch (q) {
+        case 0: hscan_chunk<0>(sref, sdis, so, xs, st, hist); break;
+        case 1: hscan_chunk<1>(sref, sdis, so, xs, st, hist); break;
+        case 2: hscan_chunk<2>(sref, sdis, so, xs, st, hist); break;
+        case 3: hscan_chunk<3>(sref, sdis, so, xs, st, hist); break;
+        default: hscan_chunk<4>(sref, sdis, so, xs, st, hist); break;
         }
-        __syncthreads();
-        if (kk + 1 < nchunks) park_chunk();
-        if (k >= 0 && row_ok && kHCols * k + 4 * g4 < W) {
-#pragma unroll
-            for (int i = 0; i < kHStoresPerThread; i++) {
-                if (2 * i + pl0 < 15)
-                    *reinterpret_cast<float4*>(gout + (size_t)(2 * i) * plane + kHCols * k) =
-                        *reinterpret_cast<const float4*>(s_out + s_off + 2 * i * kHRows * kHPitch);
-            }
+        fence_proxy_async();  // make this lane's tile writes visible to the TMA store
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&scan_done);
+            mbar_arrive(&empty_in[stg]);
         }
-        __syncthreads();
     }
 }
 
@@ -572,48 +630,6 @@ __device__ __forceinline__ void error_maps(const float (&o)[5], float ref, float
     part[3] += pos ? e4 : 0.0f;
     part[4] += pos ? 0.0f : -d1;     // detail lost
     part[5] += pos ? 0.0f : e4;
-}
-
-// ---- TMA / mbarrier plumbing (PTX; sm_90+ instructions, SASS: UTMALDG / SYNCS) -------------------
-struct alignas(64) TmaMaps {
-    CUtensorMap hb[kMaxScales];   // 4-D {x, y, plane(15), frame}, box {64, kVRowsPerStage, 15, 1}
-    CUtensorMap xyb[kMaxScales];  // 4-D {x, y, plane(6),  frame}, box {64, kVRowsPerStage, 6, 1}
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
 }
 
 // k_vpass, TMA-fed.  CTA = one 64-column strip of one scale of one frame; 6 consumer warps = (channel c, column x)

@@ -348,18 +348,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait suspends the thread in hardware for up to the hinted time before it reports failure, so a waiting
+// warp does not burn issue slots of the warps that have work.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra WAIT_DONE;\n"
         "bra WAIT_LOOP;\n"
         "WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(20000u)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3)
@@ -406,7 +408,7 @@ constexpr int kHThreads = (kHScanWarps + 1) * 32;
 constexpr int kHInStages = 2;
 constexpr uint32_t kHInBytes = 6 * kHRows * kHCols * sizeof(float);    // 24576
 constexpr uint32_t kHOutBytes = 15 * kHRows * kHCols * sizeof(float);  // 61440
-constexpr size_t kHSmemBytes = (size_t)kHInStages * kHInBytes + kHOutBytes + 1024;  // + alignment slack
+constexpr size_t kHSmemBytes = (size_t)kHInStages * kHInBytes + kHOutBytes + 128 + 64;  // tiles + ones row + mbarriers
 
 struct HState {
     float p1, p3, p5, pp1, pp3, pp5;
@@ -427,10 +429,24 @@ __device__ __forceinline__ float hstep(HState& s, float left, float right)
     return (o1 + o3) + o5;
 }
 
-// s_ref / s_dis / s_out point at this lane's 128-byte row; xs = (lane & 7) << 4 is the swizzle term
-template <int Q>
-__device__ __forceinline__ void hscan_chunk(const char* __restrict__ s_ref, const char* __restrict__ s_dis,
-                                            char* __restrict__ s_out, uint32_t xs, HState& st, float (&hist)[12])
+// One code path for all five quantities (keeps the kernel inside the instruction cache): the filter input is
+// x[j] * y[j] with (x, y) = (ref, ref), (dis, dis), (ref, dis), (ref, 1), (dis, 1); multiplying by 1.0f is exact, so
+// the mu planes are filtered on exactly the values the reference filters (cpu.rs:396-399).
+// s_x / s_y / s_out are shared-space byte addresses of this lane's 128-byte row; xs = (lane & 7) << 4 is the
+// 128B-swizzle term.
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ void hscan_chunk(uint32_t s_x, uint32_t s_y, uint32_t s_out, uint32_t xs, HState& st,
+                                            float (&hist)[12])
 {
     float win[12 + kHCols];
 #pragma unroll
@@ -438,35 +454,35 @@ __device__ __forceinline__ void hscan_chunk(const char* __restrict__ s_ref, cons
 #pragma unroll
     for (int gI = 0; gI < kHCols / 4; gI++) {
         const uint32_t off = ((uint32_t)gI << 4) ^ xs;
-        float4 a, d;
-        if (Q == 0 || Q == 2 || Q == 3) a = *reinterpret_cast<const float4*>(s_ref + off);
-        if (Q == 1 || Q == 2 || Q == 4) d = *reinterpret_cast<const float4*>(s_dis + off);
-        float pr[4];
-        if (Q == 0) { pr[0] = a.x * a.x; pr[1] = a.y * a.y; pr[2] = a.z * a.z; pr[3] = a.w * a.w; }
-        if (Q == 1) { pr[0] = d.x * d.x; pr[1] = d.y * d.y; pr[2] = d.z * d.z; pr[3] = d.w * d.w; }
-        if (Q == 2) { pr[0] = a.x * d.x; pr[1] = a.y * d.y; pr[2] = a.z * d.z; pr[3] = a.w * d.w; }
-        if (Q == 3) { pr[0] = a.x; pr[1] = a.y; pr[2] = a.z; pr[3] = a.w; }
-        if (Q == 4) { pr[0] = d.x; pr[1] = d.y; pr[2] = d.z; pr[3] = d.w; }
+        const float4 a = lds128(s_x + off), d = lds128(s_y + off);
+        const float pr[4] = {a.x * d.x, a.y * d.y, a.z * d.z, a.w * d.w};
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             win[12 + 4 * gI + j] = pr[j];
             o[j] = hstep(st, win[4 * gI + j + 2], pr[j]);  // left tap = 10 columns back
         }
-        *reinterpret_cast<float4*>(s_out + off) = make_float4(o[0], o[1], o[2], o[3]);
+        sts128(s_out + off, make_float4(o[0], o[1], o[2], o[3]));
     }
 #pragma unroll
     for (int i = 0; i < 12; i++) hist[i] = win[kHCols + i];
 }
 
+// dynamic shared memory: [2 in stages][out tile][ones row 128 B][mbarriers]
+constexpr uint32_t kHOffOut = kHInStages * kHInBytes;
+constexpr uint32_t kHOffOnes = kHOffOut + kHOutBytes;
+constexpr uint32_t kHOffBars = kHOffOnes + 128;
+
 __global__ void __launch_bounds__(kHThreads, 2) k_hpass(const __grid_constant__ Geo g, const __grid_constant__ TmaMapsH maps)
 {
-    extern __shared__ char hs_raw[];
-    __shared__ uint64_t full_in[kHInStages], empty_in[kHInStages], scan_done, out_free;
-    // 128B swizzle wants the tiles 1024-byte aligned
-    char* hs = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(hs_raw) + 1023) & ~(uintptr_t)1023);
-    char* s_in = hs;                             // [stage][6][32 rows][128 B]
-    char* s_out = hs + kHInStages * kHInBytes;   // [15][32 rows][128 B]
+    extern __shared__ __align__(1024) char hs[];
+    const uint32_t sbase = smem_u32(hs);
+    if ((sbase & 1023u) != 0) __trap();  // the 128B swizzle pattern is anchored at 1024-byte boundaries
+    uint64_t* bars = reinterpret_cast<uint64_t*>(hs + kHOffBars);
+    uint64_t* full_in = bars;            // [2]
+    uint64_t* empty_in = bars + 2;       // [2]
+    uint64_t* scan_done = bars + 4;
+    uint64_t* out_free = bars + 5;
 
     const int frame = blockIdx.y;
     int item = blockIdx.x, s = 0;
@@ -482,10 +498,11 @@ __global__ void __launch_bounds__(kHThreads, 2) k_hpass(const __grid_constant__ 
             mbar_init(&full_in[i], 1);
             mbar_init(&empty_in[i], kHScanWarps);
         }
-        mbar_init(&scan_done, kHScanWarps);
-        mbar_init(&out_free, 1);
+        mbar_init(scan_done, kHScanWarps);
+        mbar_init(out_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (tid < 32) reinterpret_cast<float*>(hs + kHOffOnes)[tid] = 1.0f;
     __syncthreads();
 
     if (warp == kHScanWarps) {
@@ -497,18 +514,18 @@ __global__ void __launch_bounds__(kHThreads, 2) k_hpass(const __grid_constant__ 
                 const int st = kk % kHInStages;
                 if (kk >= kHInStages) mbar_wait(&empty_in[st], (uint32_t)(((kk / kHInStages) - 1) & 1));
                 mbar_expect_tx(&full_in[st], kHInBytes);
-                tma_load_4d(s_in + st * kHInBytes, min, &full_in[st], kHCols * (kk - 1) + 4, row0, 0, frame);
+                tma_load_4d(hs + st * kHInBytes, min, &full_in[st], kHCols * (kk - 1) + 4, row0, 0, frame);
             };
             issue_load(0);
             for (int kk = 0; kk < nchunks; kk++) {
                 if (kk + 1 < nchunks) issue_load(kk + 1);
-                mbar_wait(&scan_done, (uint32_t)(kk & 1));  // the scan warps have written tile kk (generic proxy, fenced)
+                mbar_wait(scan_done, (uint32_t)(kk & 1));  // the scan warps have written tile kk (generic proxy, fenced)
                 if (kk >= 1) {
-                    tma_store_4d(mout, s_out, kHCols * (kk - 1), row0, 0, frame);
+                    tma_store_4d(mout, hs + kHOffOut, kHCols * (kk - 1), row0, 0, frame);
                     tma_store_commit();
-                    tma_store_wait_read();                  // shared memory may be overwritten again
+                    tma_store_wait_read();                 // shared memory may be overwritten again
                 }
-                mbar_arrive(&out_free);
+                mbar_arrive(out_free);
             }
             tma_store_wait_all();
         }
@@ -522,25 +539,24 @@ __global__ void __launch_bounds__(kHThreads, 2) k_hpass(const __grid_constant__ 
     float hist[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) hist[i] = 0.f;
-    char* so = s_out + (warp * kHRows + lane) * 128;
+    // plane of the first / second factor inside an input stage (0..2 = ref X,Y,B; 3..5 = dis X,Y,B); second < 0: ones
+    const int px = (q == 1 || q == 4) ? 3 + ch : ch;
+    const int py = (q == 0) ? ch : ((q == 1 || q == 2) ? 3 + ch : -1);
+    const uint32_t row_x = (uint32_t)((px * kHRows + lane) * 128);
+    const uint32_t row_y = (uint32_t)(((py < 0 ? 0 : py) * kHRows + lane) * 128);
+    const uint32_t so = sbase + kHOffOut + (uint32_t)((warp * kHRows + lane) * 128);
 
     for (int kk = 0; kk < nchunks; kk++) {
         const int stg = kk % kHInStages;
         mbar_wait(&full_in[stg], (uint32_t)((kk / kHInStages) & 1));
-        if (kk >= 1) mbar_wait(&out_free, (uint32_t)((kk - 1) & 1));  // tile kk-1 has left shared memory
-        const char* sref = s_in + stg * kHInBytes + ((ch * kHRows + lane) * 128);
-        const char* sdis = s_in + stg * kHInBytes + (((3 + ch) * kHRows + lane) * 128);
-        switch (q) {
-        case 0: hscan_chunk<0>(sref, sdis, so, xs, st, hist); break;
-        case 1: hscan_chunk<1>(sref, sdis, so, xs, st, hist); break;
-        case 2: hscan_chunk<2>(sref, sdis, so, xs, st, hist); break;
-        case 3: hscan_chunk<3>(sref, sdis, so, xs, st, hist); break;
-        default: hscan_chunk<4>(sref, sdis, so, xs, st, hist); break;
-        }
+        if (kk >= 1) mbar_wait(out_free, (uint32_t)((kk - 1) & 1));  // tile kk-1 has left shared memory
+        const uint32_t sin = sbase + stg * kHInBytes;
+        // the ones row is not swizzled data, any 16-byte chunk of it will do: cancel the swizzle term
+        hscan_chunk(sin + row_x, py < 0 ? (sbase + kHOffOnes) : (sin + row_y), so, xs, st, hist);
         fence_proxy_async();  // make this lane's tile writes visible to the TMA store
         __syncwarp();
         if (lane == 0) {
-            mbar_arrive(&scan_done);
+            mbar_arrive(scan_done);
             mbar_arrive(&empty_in[stg]);
         }
     }

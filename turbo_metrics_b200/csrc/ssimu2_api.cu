@@ -49,7 +49,11 @@ struct Slot {
     TmaMapsH maps_h{};                // (H pass)
     uint32_t count = 0;               // pairs recorded
     uint64_t first_ticket = 0;
-    bool inflight = false;            // launched, results not harvested yet
+    bool inflight = false;            // fully launched, results not harvested yet
+    bool awaiting = false;            // front-end launched, H pass waiting for the next batch (fused mode)
+    bool staged = false;              // holds host frames copied on the slot stream
+    bool was_timed = false;
+    cudaEvent_t ev_mid = nullptr;     // main stream -> slot stream hand-off
     bool timed = false;
     void* last_stream = nullptr;
     bool have_dep = false;
@@ -63,6 +67,9 @@ struct ssimu2_handle {
     uint32_t batch = 0, ring = 0;
     std::vector<Slot> slots;
     uint32_t cur = 0;
+    int awaiting = -1;                // slot index in the `awaiting` state, or -1
+    bool fuse = false;                // cross-batch fusion of front-end and H pass (ring >= 2)
+    cudaStream_t main_stream = nullptr;
     uint64_t next_ticket = 0;
     double* scores_ring_d = nullptr;  // [kResultCap] device score stream
     std::vector<double> res_scores;   // host result ring
@@ -217,8 +224,15 @@ static int build_tma_maps(ssimu2_handle* h, Slot& sl)
     return 0;
 }
 
+// ---- launch logic -------------------------------------------------------------------------------
+// ring == 1 (or SSIMU2_NO_FUSE): the four kernels of a batch run back to back on the slot's stream, with
+//   CUDA events between them (this is the mode bench.py uses to time each kernel alone).
+// ring >= 2: software pipeline across batches.  The front-end of batch k is launched in the SAME kernel as the
+//   H pass of batch k-1 (k_fused_fh: compute-bound and memory-bound CTAs share the SMs) on the handle's main
+//   stream; the V pass + finalize + result copy of k-1 follow on that slot's own stream.  The last batch of a
+//   burst is completed by flush / get_score with an H-only launch.
 template <int FMT>
-static int launch_batch_fmt(ssimu2_handle* h, Slot& sl)
+static int launch_unfused(ssimu2_handle* h, Slot& sl)
 {
     const Geo& g = h->geo;
     const uint32_t n = sl.count;
@@ -226,7 +240,7 @@ static int launch_batch_fmt(ssimu2_handle* h, Slot& sl)
     if (sl.timed) cudaEventRecord(sl.ev_k[0], st);
     {
         dim3 grid((g.sc[0].w + 63) / 64, (g.sc[0].h + 63) / 64, n);
-        k_frontend<FMT><<<grid, kFThreads, kFSmemBytes, st>>>(g, sl.in, sl.xyb);
+        k_frontend<FMT><<<grid, kFThreads, kFSmemTotal, st>>>(g, sl.in, sl.xyb);
     }
     if (sl.timed) cudaEventRecord(sl.ev_k[1], st);
     k_hpass<<<dim3(g.items_h, n), kHThreads, kHSmemBytes, st>>>(g, sl.maps_h);
@@ -241,26 +255,125 @@ static int launch_batch_fmt(ssimu2_handle* h, Slot& sl)
     CU_TRY(cudaMemcpyAsync(sl.norms_h, sl.norms_d, (size_t)n * 108 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaEventRecord(sl.ev_done, st));
     sl.inflight = true;
+    sl.was_timed = sl.timed;
     return 0;
 }
 
-static int launch_batch(ssimu2_handle* h, Slot& sl)
+// [H pass of slot hp] + [front-end of slot fk] in one launch on the main stream; either may be null
+template <int FMT>
+static int launch_fused(ssimu2_handle* h, Slot* hp, Slot* fk)
 {
-    if (sl.count == 0) return 0;
-    if (sl.have_dep && sl.last_stream != (void*)sl.stream) {
+    const Geo& g = h->geo;
+    FuseArgs fa{};
+    fa.frames_h = hp ? (int)hp->count : 1;
+    fa.n_h_blocks = hp ? g.items_h * (int)hp->count : 0;
+    fa.tiles_x = (g.sc[0].w + 63) / 64;
+    fa.tiles_y = (g.sc[0].h + 63) / 64;
+    fa.n_f_blocks = fk ? fa.tiles_x * fa.tiles_y * (int)fk->count : 0;
+    const unsigned total = (unsigned)(fa.n_h_blocks + fa.n_f_blocks);
+    if (total == 0) return 0;
+    Slot& any = hp ? *hp : *fk;
+    k_fused_fh<FMT><<<total, kHThreads, kHSmemBytes, h->main_stream>>>(g, hp ? hp->maps_h : any.maps_h, fk ? fk->in : any.in,
+                                                                    fk ? fk->xyb : any.xyb, fa);
+    h->launches += 1;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+// V pass + finalize + result copy of a slot whose H pass has been enqueued on the main stream
+static int launch_tail(ssimu2_handle* h, Slot& sl)
+{
+    const Geo& g = h->geo;
+    const uint32_t n = sl.count;
+    CU_TRY(cudaEventRecord(sl.ev_mid, h->main_stream));
+    CU_TRY(cudaStreamWaitEvent(sl.stream, sl.ev_mid, 0));
+    cudaStream_t st = sl.stream;
+    k_vpass<<<dim3(g.items_v, n), kVTmaThreads, kVSmemBytes, st>>>(g, sl.maps, sl.partials);
+    k_finalize<<<n, 128, 0, st>>>(g, sl.partials, sl.norms_d, h->scores_ring_d, sl.first_ticket, kResultCap, sl.scores_d);
+    h->launches += 2;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(sl.scores_h, sl.scores_d, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(sl.norms_h, sl.norms_d, (size_t)n * 108 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventRecord(sl.ev_done, st));
+    sl.inflight = true;
+    sl.was_timed = false;
+    return 0;
+}
+
+template <int FMT>
+static int launch_batch_fmt(ssimu2_handle* h, Slot& sl, int si)
+{
+    if (!h->fuse) return launch_unfused<FMT>(h, sl);
+    Slot* prev = h->awaiting >= 0 ? &h->slots[h->awaiting] : nullptr;
+    int r = launch_fused<FMT>(h, prev, &sl);
+    if (r) return r;
+    if (prev) {
+        r = launch_tail(h, *prev);
+        if (r) return r;
+    }
+    sl.awaiting = true;
+    h->awaiting = si;
+    return 0;
+}
+
+// the slot whose front-end ran but whose H pass is still waiting for a partner: finish it alone
+template <int FMT>
+static int complete_awaiting_fmt(ssimu2_handle* h)
+{
+    if (h->awaiting < 0) return 0;
+    Slot& sl = h->slots[h->awaiting];
+    int r = launch_fused<FMT>(h, &sl, nullptr);
+    if (r) return r;
+    r = launch_tail(h, sl);
+    if (r) return r;
+    sl.awaiting = false;
+    h->awaiting = -1;
+    return 0;
+}
+
+static int complete_awaiting(ssimu2_handle* h)
+{
+#define CALL_(F) complete_awaiting_fmt<F>(h)
+    switch (h->cfg.format) {
+    case kNV12: return CALL_(kNV12);
+    case kP016: return CALL_(kP016);
+    case kSRGB8: return CALL_(kSRGB8);
+    case kSRGB16: return CALL_(kSRGB16);
+    case kSRGBF32: return CALL_(kSRGBF32);
+    case kLINEARF32: return CALL_(kLINEARF32);
+    }
+#undef CALL_
+    return SSIMU2_E_UNSUPPORTED;
+}
+
+// launch the batch recorded in slot si (it must hold at least one pair and not be launched yet)
+static int launch_batch(ssimu2_handle* h, int si)
+{
+    Slot& sl = h->slots[si];
+    if (sl.count == 0 || sl.inflight || sl.awaiting) return 0;
+    cudaStream_t first = h->fuse ? h->main_stream : sl.stream;
+    if (sl.have_dep && sl.last_stream != (void*)first) {
         // order the batch after everything the submitter enqueued so far on its stream
         CU_TRY(cudaEventRecord(sl.ev_in, (cudaStream_t)sl.last_stream));
-        CU_TRY(cudaStreamWaitEvent(sl.stream, sl.ev_in, 0));
+        CU_TRY(cudaStreamWaitEvent(first, sl.ev_in, 0));
+    }
+    if (h->fuse && sl.staged) {
+        // host frames were copied on the slot's stream: the front-end on the main stream must see them
+        CU_TRY(cudaEventRecord(sl.ev_in, sl.stream));
+        CU_TRY(cudaStreamWaitEvent(h->main_stream, sl.ev_in, 0));
     }
     sl.have_dep = false;
+    sl.staged = false;
+#define CALL_(F) launch_batch_fmt<F>(h, sl, si)
     switch (h->cfg.format) {
-    case kNV12: return launch_batch_fmt<kNV12>(h, sl);
-    case kP016: return launch_batch_fmt<kP016>(h, sl);
-    case kSRGB8: return launch_batch_fmt<kSRGB8>(h, sl);
-    case kSRGB16: return launch_batch_fmt<kSRGB16>(h, sl);
-    case kSRGBF32: return launch_batch_fmt<kSRGBF32>(h, sl);
-    case kLINEARF32: return launch_batch_fmt<kLINEARF32>(h, sl);
+    case kNV12: return CALL_(kNV12);
+    case kP016: return CALL_(kP016);
+    case kSRGB8: return CALL_(kSRGB8);
+    case kSRGB16: return CALL_(kSRGB16);
+    case kSRGBF32: return CALL_(kSRGBF32);
+    case kLINEARF32: return CALL_(kLINEARF32);
     }
+#undef CALL_
     return SSIMU2_E_UNSUPPORTED;
 }
 
@@ -276,7 +389,7 @@ static int harvest(ssimu2_handle* h, uint32_t si)
         memcpy(&h->res_norms[r * 108], &sl.norms_h[(size_t)i * 108], 108 * sizeof(double));
         h->res_slot[r] = (int32_t)si;
     }
-    if (sl.timed) {
+    if (sl.was_timed) {
         for (int k = 0; k < 4; k++) {
             cudaEventElapsedTime(&h->last_ms[k], sl.ev_k[k], sl.ev_k[k + 1]);
             h->total_ms[k] += h->last_ms[k];
@@ -293,6 +406,10 @@ static int harvest(ssimu2_handle* h, uint32_t si)
 static int prepare_cur(ssimu2_handle* h)
 {
     Slot& sl = h->slots[h->cur];
+    if (sl.awaiting) {  // the ring wrapped onto the batch whose H pass is still parked: finish it first
+        int r = complete_awaiting(h);
+        if (r) return r;
+    }
     if (sl.inflight) {
         int r = harvest(h, h->cur);
         if (r) return r;
@@ -312,7 +429,7 @@ static int finish_pair(ssimu2_handle* h)
     sl.count++;
     h->next_ticket++;
     if (sl.count == h->batch) {
-        int r = launch_batch(h, sl);
+        int r = launch_batch(h, (int)h->cur);
         if (r) return r;
         h->cur = (h->cur + 1) % h->ring;
     }
@@ -411,11 +528,18 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
     h->device_bytes += kResultCap * sizeof(double);
     CR(cudaFuncSetAttribute((const void*)k_hpass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBytes));
     CR(cudaFuncSetAttribute((const void*)k_vpass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVSmemBytes));
+    static_assert(kHSmemBytes >= kFSmemTotal, "the fused kernel runs front-end tiles inside the H pass allocation");
+    h->fuse = h->ring >= 2 && getenv("SSIMU2_NO_FUSE") == nullptr;
+    CR(cudaStreamCreateWithFlags(&h->main_stream, cudaStreamNonBlocking));
     {
         static const void* ffn[6] = {(const void*)k_frontend<kNV12>,    (const void*)k_frontend<kP016>,
                                      (const void*)k_frontend<kSRGB8>,   (const void*)k_frontend<kSRGB16>,
                                      (const void*)k_frontend<kSRGBF32>, (const void*)k_frontend<kLINEARF32>};
-        CR(cudaFuncSetAttribute(ffn[cfg->format], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmemBytes));
+        CR(cudaFuncSetAttribute(ffn[cfg->format], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmemTotal));
+        static const void* gfn[6] = {(const void*)k_fused_fh<kNV12>,    (const void*)k_fused_fh<kP016>,
+                                     (const void*)k_fused_fh<kSRGB8>,   (const void*)k_fused_fh<kSRGB16>,
+                                     (const void*)k_fused_fh<kSRGBF32>, (const void*)k_fused_fh<kLINEARF32>};
+        CR(cudaFuncSetAttribute(gfn[cfg->format], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBytes));
     }
     for (uint32_t i = 0; i < h->ring; i++) {
         Slot& sl = h->slots[i];
@@ -426,6 +550,7 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
         CR(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         CR(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
         CR(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+        CR(cudaEventCreateWithFlags(&sl.ev_mid, cudaEventDisableTiming));
         for (int k = 0; k < 5; k++) CR(cudaEventCreate(&sl.ev_k[k]));
         CR(cudaMalloc(&sl.xyb, xyb_b));
         CR(cudaMalloc(&sl.hb, hb_b));
@@ -437,7 +562,7 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
         h->device_bytes += xyb_b + hb_b + part_b + (size_t)h->batch * 109 * sizeof(double);
         rc = build_tma_maps(h, sl);
         if (rc) goto fail;
-        sl.timed = getenv("SSIMU2_NO_TIMING") == nullptr;
+        sl.timed = !h->fuse && getenv("SSIMU2_NO_TIMING") == nullptr;
     }
     *out = h;
     return SSIMU2_OK;
@@ -451,8 +576,10 @@ int ssimu2_destroy(ssimu2_t* h)
 {
     if (!h) return SSIMU2_OK;
     cudaSetDevice(h->cfg.device);
+    if (h->main_stream) cudaStreamSynchronize(h->main_stream);
     for (auto& sl : h->slots) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
+        if (sl.ev_mid) cudaEventDestroy(sl.ev_mid);
         if (sl.ev_in) cudaEventDestroy(sl.ev_in);
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
         for (int k = 0; k < 5; k++)
@@ -464,6 +591,7 @@ int ssimu2_destroy(ssimu2_t* h)
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     cudaFree(h->scores_ring_d);
+    if (h->main_stream) cudaStreamDestroy(h->main_stream);
     delete h;
     return SSIMU2_OK;
 }
@@ -519,9 +647,9 @@ int ssimu2_submit_host(ssimu2_t* h, const ssimu2_frame* ref, const ssimu2_frame*
     CU_TRY(cudaSetDevice(h->cfg.device));
     if (frame_bytes > h->staging_frame_bytes) {
         // (re)allocate the staging rings; rare (first call), so a full drain is acceptable
+        int fr = ssimu2_flush(h);
+        if (fr) return fr;
         for (uint32_t i = 0; i < h->ring; i++) {
-            Slot& sl = h->slots[i];
-            if (sl.count && !sl.inflight) { int r = launch_batch(h, sl); if (r) return r; }
             int r = harvest(h, i);
             if (r) return r;
         }
@@ -545,6 +673,7 @@ int ssimu2_submit_host(ssimu2_t* h, const ssimu2_frame* ref, const ssimu2_frame*
     FrameIn& b = sl.in.dis[sl.count];
     a.p0 = da; a.p1 = yuv ? da + (ref->plane[1] - ref->plane[0]) : nullptr; a.pitch = ref->pitch; a.pad = 0;
     b.p0 = db; b.p1 = yuv ? db + (dis->plane[1] - dis->plane[0]) : nullptr; b.pitch = dis->pitch; b.pad = 0;
+    sl.staged = true;
     if (ticket) *ticket = h->next_ticket;
     return finish_pair(h);
 }
@@ -554,12 +683,13 @@ int ssimu2_flush(ssimu2_t* h)
     if (!h) return SSIMU2_E_INVALID;
     CU_TRY(cudaSetDevice(h->cfg.device));
     Slot& sl = h->slots[h->cur];
-    if (sl.count && !sl.inflight) {
-        int r = launch_batch(h, sl);
+    if (sl.count && !sl.inflight && !sl.awaiting) {
+        int r = launch_batch(h, (int)h->cur);
         if (r) return r;
         h->cur = (h->cur + 1) % h->ring;
     }
-    return SSIMU2_OK;
+    // nothing may stay parked after a flush: the last batch gets its H pass without a partner
+    return h->fuse ? complete_awaiting(h) : SSIMU2_OK;
 }
 
 int ssimu2_wait(ssimu2_t* h, uint64_t ticket)
@@ -570,8 +700,18 @@ int ssimu2_wait(ssimu2_t* h, uint64_t ticket)
     int where = locate(h, ticket, &si);
     if (where < 0) return SSIMU2_E_TICKET;
     if (where == 2) {
-        int r = ssimu2_flush(h);
-        if (r) return r;
+        // not fully launched yet: a partial batch still being filled, or a batch parked between its front-end and
+        // its H pass.  Launch what is missing for THIS ticket only.
+        Slot& sl = h->slots[si];
+        if (!sl.awaiting) {
+            int r = launch_batch(h, (int)si);
+            if (r) return r;
+            if (si == h->cur) h->cur = (h->cur + 1) % h->ring;
+        }
+        if (sl.awaiting) {
+            int r = complete_awaiting(h);
+            if (r) return r;
+        }
         where = 1;
     }
     if (where == 1) return harvest(h, si);
@@ -612,8 +752,16 @@ int ssimu2_stream_wait(ssimu2_t* h, uint64_t ticket, void* stream)
     int where = locate(h, ticket, &si);
     if (where < 0) return SSIMU2_E_TICKET;
     if (where == 2) {
-        int r = ssimu2_flush(h);
-        if (r) return r;
+        Slot& sl = h->slots[si];
+        if (!sl.awaiting) {
+            int r = launch_batch(h, (int)si);
+            if (r) return r;
+            if (si == h->cur) h->cur = (h->cur + 1) % h->ring;
+        }
+        if (sl.awaiting) {
+            int r = complete_awaiting(h);
+            if (r) return r;
+        }
         where = 1;
     }
     if (where == 1) CU_TRY(cudaStreamWaitEvent((cudaStream_t)stream, h->slots[si].ev_done, 0));

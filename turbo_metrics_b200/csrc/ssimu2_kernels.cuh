@@ -210,6 +210,13 @@ __device__ __forceinline__ void linear_to_xyb(float r, float g, float b, const e
 // inside the instruction cache.
 __device__ __forceinline__ float box4(float a, float b, float c, float d) { return ((((0.0f + a) + b) + c) + d) * 0.25f; }
 
+#ifndef KF_UNROLL
+#define KF_UNROLL 1
+#endif
+#ifndef KF_MINB
+#define KF_MINB 3
+#endif
+constexpr int kFUnroll = KF_UNROLL;
 constexpr int kFTile = 64;
 constexpr int kFThreads = 256;
 // shared linear-RGB levels: [3][side][side + 1]
@@ -223,7 +230,7 @@ constexpr size_t kFSmemBytes = (size_t)kFSmemFloats * sizeof(float);  // 65.4 KB
 
 // One 2x downscale step inside the tile: src level (side 2n, global size srcW x srcH) -> dst level (side n),
 // XYB of the dst level written to global.  cpu.rs:545-579 (sum order (0,0),(1,0),(0,1),(1,1); clamp; x0.25).
-template <int N, bool KEEP>
+template <int N, bool KEEP, int NT>
 __device__ __forceinline__ void down_level(const float* __restrict__ src, float* __restrict__ dst, int srcW, int srcH,
                                            int ox0, int oy0, const ScaleDesc& sd, float* __restrict__ gdst,
                                            const exact_math::CbrtScale& S)
@@ -231,7 +238,7 @@ __device__ __forceinline__ void down_level(const float* __restrict__ src, float*
     constexpr int SP = 2 * N + 1, DP = N + 1;
     const size_t plane = (size_t)sd.h * sd.pitch;
 #pragma unroll 1
-    for (int idx = threadIdx.x; idx < N * N; idx += kFThreads) {
+    for (int idx = threadIdx.x; idx < N * N; idx += NT) {
         const int lx = idx % N, ly = idx / N;
         const int ox = ox0 + lx, oy = oy0 + ly;
         const bool valid = ox < sd.w && oy < sd.h;
@@ -252,37 +259,43 @@ __device__ __forceinline__ void down_level(const float* __restrict__ src, float*
     }
 }
 
-template <int FMT>
-__global__ void __launch_bounds__(kFThreads) k_frontend(const __grid_constant__ Geo g, const __grid_constant__ BatchIn in,
-                                                        float* __restrict__ xyb_base)
+// shared-memory carve-up of one frontend tile: linear levels, then the two tables
+constexpr size_t kFOffT = (kFSmemBytes + 15) / 16 * 16;
+constexpr size_t kFOffS = kFOffT + sizeof(exact_math::PowfTables);
+constexpr size_t kFSmemTotal = kFOffS + sizeof(exact_math::CbrtScale);  // 68.2 KB
+
+// One 64x64 source tile of one frame, both images; NT threads (256 standalone, 512 inside the fused kernel).
+template <int FMT, int NT>
+__device__ __forceinline__ void frontend_tile(const Geo& g, const BatchIn& in, float* __restrict__ xyb_base, int tbx, int tby,
+                                              int frame, char* smem)
 {
-    extern __shared__ __align__(16) float fs[];
-    __shared__ exact_math::PowfTables T;
-    __shared__ exact_math::CbrtScale S;
+    float* fs = reinterpret_cast<float*>(smem);
+    exact_math::PowfTables& T = *reinterpret_cast<exact_math::PowfTables*>(smem + kFOffT);
+    exact_math::CbrtScale& S = *reinterpret_cast<exact_math::CbrtScale*>(smem + kFOffS);
     {
         const uint64_t* src = reinterpret_cast<const uint64_t*>(&kPowfTablesInit);
         uint64_t* dst = reinterpret_cast<uint64_t*>(&T);
-        for (int i = threadIdx.x; i < (int)(sizeof(exact_math::PowfTables) / 8); i += kFThreads) dst[i] = src[i];
-        S.tab[threadIdx.x] = exact_math::cbrt_scale_entry(threadIdx.x);
+        for (int i = threadIdx.x; i < (int)(sizeof(exact_math::PowfTables) / 8); i += NT) dst[i] = src[i];
+        if (threadIdx.x < 256) S.tab[threadIdx.x] = exact_math::cbrt_scale_entry(threadIdx.x);
     }
     __syncthreads();
-    const int frame = blockIdx.z;
     float* xyb_slot = xyb_base + (size_t)frame * g.xyb_stride;
     const int W0 = g.sc[0].w, H0 = g.sc[0].h;
-    const int X0 = blockIdx.x * kFTile, Y0 = blockIdx.y * kFTile;
+    const int X0 = tbx * kFTile, Y0 = tby * kFTile;
     const int ns = g.nscales;
+    constexpr int kRowsPerIter = NT / 64;
 
     for (int img = 0; img < 2; img++) {
         const FrameIn& f = img ? in.dis[frame] : in.ref[frame];
-        // ---- scale 0: source -> linear RGB (shared) -> XYB (global); thread = column lx, rows ly0 + 4k
+        // ---- scale 0: source -> linear RGB (shared) -> XYB (global); thread = column lx, rows ly0 + kRowsPerIter*k
         {
             const ScaleDesc& sd = g.sc[0];
             const size_t plane = (size_t)sd.h * sd.pitch;
             float* gdst = xyb_slot + sd.xyb_off + (size_t)img * 3 * plane;
             const int lx = threadIdx.x & 63, x = X0 + lx;
-#pragma unroll 1
-            for (int k = 0; k < kFTile / 4; k++) {
-                const int ly = (threadIdx.x >> 6) + 4 * k, y = Y0 + ly;
+#pragma unroll kFUnroll
+            for (int k = 0; k < kFTile / kRowsPerIter; k++) {
+                const int ly = (threadIdx.x >> 6) + kRowsPerIter * k, y = Y0 + ly;
                 float r = 0.f, gg = 0.f, b = 0.f;
                 if (x < W0 && y < H0) {
                     load_px<FMT>(f, x, y, g.coef, T, r, gg, b);
@@ -302,26 +315,34 @@ __global__ void __launch_bounds__(kFThreads) k_frontend(const __grid_constant__ 
         };
         if (ns > 1) {
             __syncthreads();
-            down_level<32, true>(fs + kFOff0, fs + kFOff1, W0, H0, X0 / 2, Y0 / 2, g.sc[1], gplane(1), S);
+            down_level<32, true, NT>(fs + kFOff0, fs + kFOff1, W0, H0, X0 / 2, Y0 / 2, g.sc[1], gplane(1), S);
         }
         if (ns > 2) {
             __syncthreads();
-            down_level<16, true>(fs + kFOff1, fs + kFOff2, g.sc[1].w, g.sc[1].h, X0 / 4, Y0 / 4, g.sc[2], gplane(2), S);
+            down_level<16, true, NT>(fs + kFOff1, fs + kFOff2, g.sc[1].w, g.sc[1].h, X0 / 4, Y0 / 4, g.sc[2], gplane(2), S);
         }
         if (ns > 3) {
             __syncthreads();
-            down_level<8, true>(fs + kFOff2, fs + kFOff3, g.sc[2].w, g.sc[2].h, X0 / 8, Y0 / 8, g.sc[3], gplane(3), S);
+            down_level<8, true, NT>(fs + kFOff2, fs + kFOff3, g.sc[2].w, g.sc[2].h, X0 / 8, Y0 / 8, g.sc[3], gplane(3), S);
         }
         if (ns > 4) {
             __syncthreads();
-            down_level<4, true>(fs + kFOff3, fs + kFOff4, g.sc[3].w, g.sc[3].h, X0 / 16, Y0 / 16, g.sc[4], gplane(4), S);
+            down_level<4, true, NT>(fs + kFOff3, fs + kFOff4, g.sc[3].w, g.sc[3].h, X0 / 16, Y0 / 16, g.sc[4], gplane(4), S);
         }
         if (ns > 5) {
             __syncthreads();
-            down_level<2, false>(fs + kFOff4, nullptr, g.sc[4].w, g.sc[4].h, X0 / 32, Y0 / 32, g.sc[5], gplane(5), S);
+            down_level<2, false, NT>(fs + kFOff4, nullptr, g.sc[4].w, g.sc[4].h, X0 / 32, Y0 / 32, g.sc[5], gplane(5), S);
         }
         __syncthreads();  // the tile is reused by the next image
     }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kFThreads, KF_MINB) k_frontend(const __grid_constant__ Geo g, const __grid_constant__ BatchIn in,
+                                                                 float* __restrict__ xyb_base)
+{
+    extern __shared__ __align__(16) char fsm[];
+    frontend_tile<FMT, kFThreads>(g, in, xyb_base, blockIdx.x, blockIdx.y, blockIdx.z, fsm);
 }
 
 // ---- TMA / mbarrier plumbing (PTX; sm_90+ instructions, SASS: UTMALDG / SYNCS) -------------------
@@ -473,9 +494,9 @@ constexpr uint32_t kHOffOut = kHInStages * kHInBytes;
 constexpr uint32_t kHOffOnes = kHOffOut + kHOutBytes;
 constexpr uint32_t kHOffBars = kHOffOnes + 128;
 
-__global__ void __launch_bounds__(kHThreads, 2) k_hpass(const __grid_constant__ Geo g, const __grid_constant__ TmaMapsH maps)
+// One 32-row band (work item `item` of the scale-ordered list) of frame `frame`; 512 threads; hs = 1024-aligned smem.
+__device__ __forceinline__ void hpass_band(const Geo& g, const TmaMapsH& maps, int item, int frame, char* hs)
 {
-    extern __shared__ __align__(1024) char hs[];
     const uint32_t sbase = smem_u32(hs);
     if ((sbase & 1023u) != 0) __trap();  // the 128B swizzle pattern is anchored at 1024-byte boundaries
     uint64_t* bars = reinterpret_cast<uint64_t*>(hs + kHOffBars);
@@ -484,8 +505,7 @@ __global__ void __launch_bounds__(kHThreads, 2) k_hpass(const __grid_constant__ 
     uint64_t* scan_done = bars + 4;
     uint64_t* out_free = bars + 5;
 
-    const int frame = blockIdx.y;
-    int item = blockIdx.x, s = 0;
+    int s = 0;
     while (item >= g.sc[s].n_bands) { item -= g.sc[s].n_bands; s++; }
     const int W = g.sc[s].w;
     const int row0 = item * kHRows;
@@ -559,6 +579,45 @@ __global__ void __launch_bounds__(kHThreads, 2) k_hpass(const __grid_constant__ 
             mbar_arrive(scan_done);
             mbar_arrive(&empty_in[stg]);
         }
+    }
+}
+
+__global__ void __launch_bounds__(kHThreads, 2) k_hpass(const __grid_constant__ Geo g, const __grid_constant__ TmaMapsH maps)
+{
+    extern __shared__ __align__(1024) char hsm[];
+    hpass_band(g, maps, blockIdx.x, blockIdx.y, hsm);
+}
+
+// Horizontal fusion of two INDEPENDENT pieces of work in one launch so that they share the SMs: the H pass of
+// batch p (streams 0.93 GB per pair through HBM, leaves ~60 % of the issue slots idle) and the front-end of
+// the NEXT batch k (FP64 / integer bound, almost no HBM traffic).  Roles are interleaved over blockIdx with a
+// Bresenham split, so every SM holds a mix of the two and the memory-bound CTAs hide behind the compute-bound
+// ones.  Either side may be empty (n_h_blocks == 0 or n_f_blocks == 0).
+struct FuseArgs {
+    int n_h_blocks;   // items_h * frames_h
+    int frames_h;
+    int n_f_blocks;   // tiles_x * tiles_y * frames_f
+    int tiles_x, tiles_y;
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(kHThreads, 2) k_fused_fh(const __grid_constant__ Geo g, const __grid_constant__ TmaMapsH maps_h,
+                                                           const __grid_constant__ BatchIn in_f, float* __restrict__ xyb_f,
+                                                           const FuseArgs fa)
+{
+    extern __shared__ __align__(1024) char sm[];
+    const long long total = (long long)fa.n_h_blocks + fa.n_f_blocks;
+    const long long b = blockIdx.x;
+    const int ih = (int)((b * fa.n_h_blocks) / total);
+    const bool is_h = (int)(((b + 1) * fa.n_h_blocks) / total) > ih;
+    if (is_h) {
+        // item-major order: all frames' largest bands first
+        hpass_band(g, maps_h, ih / fa.frames_h, ih % fa.frames_h, sm);
+    } else {
+        const int jf = (int)(b - ih);
+        const int per_frame = fa.tiles_x * fa.tiles_y;
+        const int frame = jf / per_frame, t = jf - frame * per_frame;
+        frontend_tile<FMT, kHThreads>(g, in_f, xyb_f, t % fa.tiles_x, t / fa.tiles_x, frame, sm);
     }
 }
 

@@ -310,6 +310,7 @@ static int launch_batch_fmt(ssimu2_handle* h, Slot& sl, int si)
     if (prev) {
         r = launch_tail(h, *prev);
         if (r) return r;
+        prev->awaiting = false;
     }
     sl.awaiting = true;
     h->awaiting = si;

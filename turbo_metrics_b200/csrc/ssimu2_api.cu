@@ -72,6 +72,7 @@ struct ssimu2_handle {
     cudaStream_t main_stream = nullptr;
     uint64_t next_ticket = 0;
     double* scores_ring_d = nullptr;  // [kResultCap] device score stream
+    float* eotf_lut = nullptr;        // exact R / B transfer memo for YUV sources (see Geo)
     std::vector<double> res_scores;   // host result ring
     std::vector<double> res_norms;    // [kResultCap][108]
     std::vector<int32_t> res_slot;    // slot that served the ticket (for debug_read)
@@ -542,6 +543,18 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
                                      (const void*)k_fused_fh<kSRGBF32>, (const void*)k_fused_fh<kLINEARF32>};
         CR(cudaFuncSetAttribute(gfn[cfg->format], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBytes));
     }
+    if ((cfg->format == kNV12 || cfg->format == kP016) && getenv("SSIMU2_NO_LUT") == nullptr) {
+        const int n = cfg->format == kNV12 ? 256 : 1024, shift = cfg->format == kNV12 ? 0 : 6;
+        const size_t bytes = (size_t)2 * n * n * sizeof(float);
+        CR(cudaMalloc(&h->eotf_lut, bytes));
+        k_build_eotf_lut<<<(n * n + 255) / 256, 256, 0, h->main_stream>>>(h->geo.coef, n, shift, h->eotf_lut);
+        CR(cudaGetLastError());
+        CR(cudaStreamSynchronize(h->main_stream));
+        h->geo.eotf_lut = h->eotf_lut;
+        h->geo.lut_n = n;
+        h->geo.lut_shift = shift;
+        h->device_bytes += bytes;
+    }
     for (uint32_t i = 0; i < h->ring; i++) {
         Slot& sl = h->slots[i];
         const Geo& g = h->geo;
@@ -592,6 +605,7 @@ int ssimu2_destroy(ssimu2_t* h)
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     cudaFree(h->scores_ring_d);
+    cudaFree(h->eotf_lut);
     if (h->main_stream) cudaStreamDestroy(h->main_stream);
     delete h;
     return SSIMU2_OK;

@@ -49,6 +49,13 @@ struct Geo {
     long long xyb_stride;        // floats per slot
     long long hb_stride;         // floats per slot
     YuvCoef coef;
+    // Exact memo of the R and B transfer for YUV sources: R' = luma(Y) + r*Cr and B' = luma(Y) + b*Cb depend on two
+    // integer codes only, so linear R / B are looked up in two N x N tables ([0]: R by (Cr, Y), [1]: B by (Cb, Y),
+    // index c * N + y) built at create time BY THE SAME device code (bit-identical by construction).  G' depends on
+    // three codes and keeps the arithmetic path.  Codes are sample >> lut_shift (P016: the 10 significant bits);
+    // samples with non-zero low bits take the arithmetic path.
+    const float* eotf_lut;
+    int lut_n, lut_shift;
 };
 
 struct FrameIn {
@@ -120,7 +127,7 @@ __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f),
 // srgb_to_linear_f32 (srgb.rs:50-127).  x, y must be inside the frame.
 template <int FMT>
 __device__ __forceinline__ void load_px(const FrameIn& f, int x, int y, const YuvCoef& k, const exact_math::PowfTables& T,
-                                        float& r, float& g, float& b)
+                                        const float* __restrict__ lut, int lut_n, int lut_shift, float& r, float& g, float& b)
 {
     if constexpr (FMT == kNV12 || FMT == kP016) {
         int Y, cbi, cri;
@@ -137,13 +144,19 @@ __device__ __forceinline__ void load_px(const FrameIn& f, int x, int y, const Yu
         }
         float cb = (float)(cbi - k.neutral);
         float cr = (float)(cri - k.neutral);
-        float r_ = k.r * cr;
         float g_ = fmaf(k.g1, cb, k.g2 * cr);
-        float b_ = k.b * cb;
         float luma = (float)(max(Y, k.luma_min) - k.luma_min) * k.y;
-        r = clamp01(bt709_eotf(luma + r_, T));
         g = clamp01(bt709_eotf(luma + g_, T));
-        b = clamp01(bt709_eotf(luma + b_, T));
+        if (lut != nullptr && ((Y | cbi | cri) & ((1 << lut_shift) - 1)) == 0) {
+            const int yc = Y >> lut_shift;
+            r = __ldg(lut + (size_t)(cri >> lut_shift) * lut_n + yc);
+            b = __ldg(lut + (size_t)lut_n * lut_n + (size_t)(cbi >> lut_shift) * lut_n + yc);
+        } else {
+            float r_ = k.r * cr;
+            float b_ = k.b * cb;
+            r = clamp01(bt709_eotf(luma + r_, T));
+            b = clamp01(bt709_eotf(luma + b_, T));
+        }
     } else if constexpr (FMT == kSRGB8) {
         const uint8_t* p = f.p0 + (size_t)y * f.pitch + 3 * x;
         r = kSrgb8Lut[__ldg(p)];
@@ -298,7 +311,7 @@ __device__ __forceinline__ void frontend_tile(const Geo& g, const BatchIn& in, f
                 const int ly = (threadIdx.x >> 6) + kRowsPerIter * k, y = Y0 + ly;
                 float r = 0.f, gg = 0.f, b = 0.f;
                 if (x < W0 && y < H0) {
-                    load_px<FMT>(f, x, y, g.coef, T, r, gg, b);
+                    load_px<FMT>(f, x, y, g.coef, T, g.eotf_lut, g.lut_n, g.lut_shift, r, gg, b);
                     float X, Y, B;
                     linear_to_xyb(r, gg, b, S, X, Y, B);
                     const size_t off = (size_t)y * sd.pitch + x;
@@ -905,6 +918,27 @@ __global__ void __launch_bounds__(128) k_finalize(const __grid_constant__ Geo g,
         scores_out[frame] = ssim;
         scores_ring[(first_ticket + frame) % ring_cap] = ssim;
     }
+}
+
+// Builds Geo::eotf_lut with the arithmetic path of load_px (same expressions, same device routines).
+__global__ void k_build_eotf_lut(const YuvCoef k, int n, int shift, float* __restrict__ out)
+{
+    __shared__ exact_math::PowfTables T;
+    {
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(&kPowfTablesInit);
+        uint64_t* dst = reinterpret_cast<uint64_t*>(&T);
+        for (int i = threadIdx.x; i < (int)(sizeof(exact_math::PowfTables) / 8); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    const int c = idx / n, y = idx - c * n;
+    const int Y = y << shift, C = c << shift;
+    const float cc = (float)(C - k.neutral);
+    const float luma = (float)(max(Y, k.luma_min) - k.luma_min) * k.y;
+    const float r_ = k.r * cc, b_ = k.b * cc;
+    out[idx] = clamp01(bt709_eotf(luma + r_, T));
+    out[(size_t)n * n + idx] = clamp01(bt709_eotf(luma + b_, T));
 }
 
 // Test hook: the device build of exact_math.cuh over an array.

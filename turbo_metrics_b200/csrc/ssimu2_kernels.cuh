@@ -720,19 +720,166 @@ __device__ __forceinline__ void error_maps(const float (&o)[5], float ref, float
     part[5] += pos ? 0.0f : e4;
 }
 
-// k_vpass, TMA-fed.  CTA = one 64-column strip of one scale of one frame; 6 consumer warps = (channel c, column x)
-// + 1 producer warp.  The producer streams {hb rows t, t+1 ; xyb rows t-4, t-3} boxes into a 5-stage shared-memory
-// ring with cp.async.bulk.tensor (out-of-range rows / columns arrive as zeros = the filter's zero padding, so the loop
-// has no edge cases); full/empty mbarriers per stage.  Each consumer thread runs its 5 filters down the column: the
-// 10-row delay line lives in REGISTERS (the row loop is unrolled by 10 = one turn of the ring), shared memory is read
-// once per value, there are no block-wide barriers and no global-memory instructions in the loop.
+// ---- packed f32x2 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2) ----------------------------------------
+// One instruction = two independent IEEE round-to-nearest f32 operations on a 64-bit register pair, so the
+// results are bit-identical to the scalar forms while the filter costs half the issue slots.  Negations are
+// written as unpack / negate / pack: ptxas folds them into the source modifiers of the consuming instruction.
+struct f2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ f2 f2_pack(float lo, float hi)
+{
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(f2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ f2 f2_splat(float c) { return f2_pack(c, c); }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b)
+{
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 f2_sub(f2 a, f2 b)
+{
+    f2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b)
+{
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c)
+{
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+// a - m and a + m where m is the result of f2_mul: ptxas contracts mul.rn.f32x2 + add/sub.rn.f32x2 into one FFMA2
+// (even with --fmad=false), which would change the rounding; fma(m, -+1, a) is the same single-rounded a -+ m and
+// cannot be contracted.
+__device__ __forceinline__ f2 f2_sub_prod(f2 a, f2 m) { return f2_fma(m, f2_pack(-1.0f, -1.0f), a); }
+__device__ __forceinline__ f2 f2_add_prod(f2 a, f2 m) { return f2_fma(m, f2_pack(1.0f, 1.0f), a); }
+__device__ __forceinline__ f2 f2_neg(f2 a)
+{
+    float lo, hi;
+    f2_unpack(a, lo, hi);
+    return f2_pack(-lo, -hi);
+}
+__device__ __forceinline__ f2 f2_abs(f2 a)
+{
+    float lo, hi;
+    f2_unpack(a, lo, hi);
+    return f2_pack(fabsf(lo), fabsf(hi));
+}
+__device__ __forceinline__ f2 f2_max0(f2 a)
+{
+    float lo, hi;
+    f2_unpack(a, lo, hi);
+    return f2_pack(fmaxf(lo, 0.0f), fmaxf(hi, 0.0f));
+}
+__device__ __forceinline__ f2 f2_rcp_approx(f2 a)
+{
+    float lo, hi, rl, rh;
+    f2_unpack(a, lo, hi);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rl) : "f"(lo));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rh) : "f"(hi));
+    return f2_pack(rl, rh);
+}
+__device__ __forceinline__ float f2_hsum(f2 a)
+{
+    float lo, hi;
+    f2_unpack(a, lo, hi);
+    return lo + hi;
+}
+__device__ __forceinline__ f2 lds64(uint32_t addr)
+{
+    f2 r;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r.v) : "r"(addr));
+    return r;
+}
+
+// vstep / div_rn_normal / error_maps on two adjacent columns at once (same operations, same order).
+struct VState2 {
+    f2 p1, p3, p5, pp1, pp3, pp5;
+};
+
+__device__ __forceinline__ f2 vstep2(VState2& s, f2 top, f2 bottom)
+{
+    const f2 sum = f2_add(top, bottom);
+    const f2 a1 = f2_fma(s.p1, f2_splat(-RG_PREV_1), s.pp1);
+    const f2 a3 = f2_fma(s.p3, f2_splat(-RG_PREV_3), s.pp3);
+    const f2 a5 = f2_fma(s.p5, f2_splat(-RG_PREV_5), s.pp5);
+    const f2 o1 = f2_fma(sum, f2_splat(RG_IN_1), f2_neg(a1));
+    const f2 o3 = f2_fma(sum, f2_splat(RG_IN_3), f2_neg(a3));
+    const f2 o5 = f2_fma(sum, f2_splat(RG_IN_5), f2_neg(a5));
+    s.pp1 = s.p1; s.pp3 = s.p3; s.pp5 = s.p5;
+    s.p1 = o1; s.p3 = o3; s.p5 = o5;
+    return f2_add(f2_add(o1, o3), o5);
+}
+
+__device__ __forceinline__ f2 div_rn_normal2(f2 n, f2 d)
+{
+    const f2 one = f2_splat(1.0f);
+    f2 r = f2_rcp_approx(d);
+    const f2 nd = f2_neg(d);
+    const f2 e = f2_fma(nd, r, one);
+    r = f2_fma(r, e, r);
+    const f2 q = f2_mul(n, r);
+    const f2 rem = f2_fma(nd, q, n);
+    return f2_fma(rem, r, q);
+}
+
+// art = max(d1, 0), detail = max(-d1, 0); their 4th powers are formed from the clamped values (identical to
+// selecting d1^4 by the sign of d1: one of the two is exactly zero).
+__device__ __forceinline__ void error_maps2(const f2 (&o)[5], f2 ref, f2 dis, f2 (&part)[6])
+{
+    const f2 C2 = f2_splat(0.0009f), one = f2_splat(1.0f);
+    const f2 s11 = o[0], s22 = o[1], s12 = o[2], mu1 = o[3], mu2 = o[4];
+    const f2 mu11 = f2_mul(mu1, mu1), mu22 = f2_mul(mu2, mu2), mu12 = f2_mul(mu1, mu2);
+    const f2 mu_diff = f2_sub(mu1, mu2);
+    const f2 num_m = f2_fma(mu_diff, f2_neg(mu_diff), one);
+    const f2 num_s = f2_fma(f2_splat(2.0f), f2_sub_prod(s12, mu12), C2);
+    const f2 denom_s = f2_add(f2_add(f2_sub_prod(s11, mu11), f2_sub_prod(s22, mu22)), C2);
+    const f2 q = div_rn_normal2(f2_mul(num_m, num_s), denom_s);
+    const f2 d = f2_max0(f2_sub(one, q));
+    part[0] = f2_add(part[0], d);
+    const f2 d2 = f2_mul(d, d);
+    part[1] = f2_fma(d2, d2, part[1]);
+
+    const f2 a = f2_abs(f2_sub(dis, mu2)), b = f2_abs(f2_sub(ref, mu1));
+    const f2 den = f2_add(one, b);
+    f2 r = f2_rcp_approx(den);
+    r = f2_fma(r, f2_fma(f2_neg(den), r, one), r);
+    const f2 d1 = f2_mul(f2_sub(a, b), r);
+    const f2 art = f2_max0(d1), det = f2_max0(f2_neg(d1));
+    const f2 art2 = f2_mul(art, art), det2 = f2_mul(det, det);
+    part[2] = f2_add(part[2], art);
+    part[3] = f2_fma(art2, art2, part[3]);
+    part[4] = f2_add(part[4], det);
+    part[5] = f2_fma(det2, det2, part[5]);
+}
+
+// k_vpass, TMA-fed.  CTA = one 64-column strip of one scale of one frame; 3 consumer warps (warp = channel, lane =
+// a PAIR of adjacent columns, all arithmetic packed f32x2) + 1 producer warp.  The producer streams
+// {hb rows t, t+1 ; xyb rows t-4, t-3} boxes into a 5-stage shared-memory ring with cp.async.bulk.tensor (out-of-range
+// rows / columns arrive as zeros = the filter's zero padding, so the loop has no edge cases; an all-zero column
+// contributes exactly 0 to every sum); full/empty mbarriers per stage.  Each consumer thread runs its 5 filters down
+// its two columns: the 10-row delay line lives in REGISTERS (the row loop is unrolled by 10 = one turn of the ring),
+// shared memory is read once per value with 64-bit loads, there are no block-wide barriers and no global-memory
+// instructions in the loop.
 constexpr int kVRowsPerStage = 2;
 constexpr int kVStages = kVRing / kVRowsPerStage;                  // 5 stages = one 10-row group
 constexpr int kVBoxHb = 15 * kVRowsPerStage * kVCols;              // floats
 constexpr int kVBoxXyb = 6 * kVRowsPerStage * kVCols;
 constexpr int kVStageFloats = kVBoxHb + kVBoxXyb;                  // 2688 floats = 10752 B
 constexpr uint32_t kVStageBytes = kVStageFloats * sizeof(float);
-constexpr int kVTmaThreads = kVThreads + 32;                       // + producer warp
+constexpr int kVConsumers = 3 * (kVCols / 2);                      // 96
+constexpr int kVTmaThreads = kVConsumers + 32;                     // + producer warp
 constexpr size_t kVSmemBytes = (size_t)kVStages * kVStageBytes + 128;
 
 __global__ void __launch_bounds__(kVTmaThreads, 2) k_vpass(const __grid_constant__ Geo g, const __grid_constant__ TmaMaps maps,
@@ -740,7 +887,6 @@ __global__ void __launch_bounds__(kVTmaThreads, 2) k_vpass(const __grid_constant
 {
     extern __shared__ __align__(128) float vs[];
     __shared__ uint64_t full_bar[kVStages], empty_bar[kVStages];
-    __shared__ double red[kVThreads / 32][6];
 
     const int frame = blockIdx.y;
     int item = blockIdx.x, s = 0;
@@ -754,13 +900,13 @@ __global__ void __launch_bounds__(kVTmaThreads, 2) k_vpass(const __grid_constant
 #pragma unroll
         for (int i = 0; i < kVStages; i++) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], kVThreads / 32);
+            mbar_init(&empty_bar[i], kVConsumers / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == kVThreads / 32) {
+    if (warp == kVConsumers / 32) {
         // ===== producer warp: one elected lane issues the TMA loads =====
         if (lane == 0) {
             const CUtensorMap* mhb = &maps.hb[s];
@@ -781,66 +927,60 @@ __global__ void __launch_bounds__(kVTmaThreads, 2) k_vpass(const __grid_constant
         return;
     }
 
-    // ===== consumers =====
-    const int tx = tid % kVCols, c = tid / kVCols;
-    VState stq[5];
+    // ===== consumers: warp = channel, lane = column pair =====
+    const int c = warp;
+    const uint32_t sbase = smem_u32(vs) + (uint32_t)lane * 8u;
+    VState2 stq[5];
+    f2 dl[kVRing][5];  // delay line: the input of 10 rows ago, per quantity
+    f2 zero2 = f2_splat(0.0f);
 #pragma unroll
-    for (int qi = 0; qi < 5; qi++) stq[qi] = VState{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float dl[kVRing][5];  // delay line: the input of 10 rows ago, per quantity
+    for (int qi = 0; qi < 5; qi++) stq[qi] = VState2{zero2, zero2, zero2, zero2, zero2, zero2};
 #pragma unroll
     for (int i = 0; i < kVRing; i++)
 #pragma unroll
-        for (int qi = 0; qi < 5; qi++) dl[i][qi] = 0.f;
+        for (int qi = 0; qi < 5; qi++) dl[i][qi] = zero2;
     double acc[6] = {0, 0, 0, 0, 0, 0};
 
     for (int gi = 0; gi < ngroups; gi++) {
         const uint32_t parity = (uint32_t)(gi & 1);
-        float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        f2 part[6] = {zero2, zero2, zero2, zero2, zero2, zero2};
 #pragma unroll
         for (int st = 0; st < kVStages; st++) {
             mbar_wait(&full_bar[st], parity);
-            const float* sb = vs + st * kVStageFloats;
+            const uint32_t sb = sbase + (uint32_t)st * kVStageBytes;
 #pragma unroll
             for (int r = 0; r < kVRowsPerStage; r++) {
-                constexpr int dummy = 0; (void)dummy;
                 const int slot = st * kVRowsPerStage + r;
                 const int t = gi * kVRing + slot;
-                float o[5];
+                f2 o[5];
 #pragma unroll
                 for (int qi = 0; qi < 5; qi++) {
-                    const float v = sb[((qi * 3 + c) * kVRowsPerStage + r) * kVCols + tx];
-                    o[qi] = vstep(stq[qi], dl[slot][qi], v);
+                    const f2 v = lds64(sb + (uint32_t)(((qi * 3 + c) * kVRowsPerStage + r) * kVCols) * 4u);
+                    o[qi] = vstep2(stq[qi], dl[slot][qi], v);
                     dl[slot][qi] = v;
                 }
-                const float fr = sb[kVBoxHb + ((0 + c) * kVRowsPerStage + r) * kVCols + tx];
-                const float fd = sb[kVBoxHb + ((3 + c) * kVRowsPerStage + r) * kVCols + tx];
-                if (t >= 4 && t < H + 4) error_maps(o, fr, fd, part);
+                const f2 fr = lds64(sb + (uint32_t)(kVBoxHb + ((0 + c) * kVRowsPerStage + r) * kVCols) * 4u);
+                const f2 fd = lds64(sb + (uint32_t)(kVBoxHb + ((3 + c) * kVRowsPerStage + r) * kVCols) * 4u);
+                if (t >= 4 && t < H + 4) error_maps2(o, fr, fd, part);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[st]);
             if (st == kVStages / 2) {
 #pragma unroll
-                for (int k = 0; k < 6; k++) { acc[k] += (double)part[k]; part[k] = 0.f; }
+                for (int k = 0; k < 6; k++) { acc[k] += (double)f2_hsum(part[k]); part[k] = zero2; }
             }
         }
 #pragma unroll
-        for (int k = 0; k < 6; k++) acc[k] += (double)part[k];
+        for (int k = 0; k < 6; k++) acc[k] += (double)f2_hsum(part[k]);
     }
 
-    // reduction over the 6 consumer warps (channel-uniform: 64 columns = 2 warps per channel); the producer warp
-    // has exited, so a named barrier over the consumer threads only
+    // one warp = one channel: reduce over the 32 column pairs and write the strip's partial sums
 #pragma unroll
     for (int k = 0; k < 6; k++) {
         double vsum = acc[k];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) vsum += __shfl_down_sync(0xffffffffu, vsum, off);
-        if (lane == 0) red[warp][k] = vsum;
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kVThreads) : "memory");
-    if (tid < 18) {
-        int cc = tid / 6, k = tid % 6;
-        double vsum = red[2 * cc][k] + red[2 * cc + 1][k];
-        partials[((size_t)frame * g.total_strips + sd.strip0 + item) * 18 + cc * 6 + k] = vsum;
+        if (lane == 0) partials[((size_t)frame * g.total_strips + sd.strip0 + item) * 18 + c * 6 + k] = vsum;
     }
 }
 

@@ -127,7 +127,7 @@ def test_intermediate_planes_are_bit_identical_srgb8(oracle, w, h):
     tm = _tm()
     from turbo_metrics_b200 import synth
     r, d = synth.make_pair_srgb8(w, h, frame=3, seed=5)
-    with tm.Ssimulacra2(w, h, tm.PixelFormat.SRGB8, batch=1, ring=1) as m:
+    with tm.Ssimulacra2(w, h, tm.PixelFormat.SRGB8, batch=1, ring=1, pipeline="split") as m:
         rg, dg = r.cuda(), d.cuda()
         t = m.compute(tm.DeviceFrame.packed(rg), tm.DeviceFrame.packed(dg))
         score = m.get_score(t)
@@ -149,7 +149,7 @@ def test_intermediate_planes_are_bit_identical_yuv(oracle, bits):
     w, h = 192, 108
     rb, db, pitch, ch = synth.make_pair_yuv420(w, h, bits, frame=2, seed=9)
     fmt = tm.PixelFormat.NV12 if bits == 8 else tm.PixelFormat.P016
-    with tm.Ssimulacra2(w, h, fmt, batch=1, ring=1) as m:
+    with tm.Ssimulacra2(w, h, fmt, batch=1, ring=1, pipeline="split") as m:
         rg, dg = rb.cuda(), db.cuda()
         t = m.compute(tm.DeviceFrame.yuv420(rg, pitch, ch), tm.DeviceFrame.yuv420(dg, pitch, ch))
         score, norms, ns = m.get_score(t), m.get_norms(t), m.info().nscales
@@ -211,6 +211,30 @@ def test_score_and_norms_match_oracle(oracle, kind, w, h):
         norms = m.get_norms(t)
         assert m.info().nscales == nso
     _assert_norms(norms, no, score, so)
+
+
+@pytest.mark.parametrize("w,h", [(203, 131), (640, 360), (1000, 77)])
+def test_pipelines_agree(oracle, w, h):
+    """The three launch pipelines ("hv": fused H+V kernel with the systolic strip hand-off, "fh", "split") run
+    the same arithmetic: norms agree to accumulation-order noise, and all of them match the oracle."""
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    n = 5
+    pairs = [synth.make_pair_srgb8(w, h, frame=i, seed=17) for i in range(n)]
+    dev = [(r.cuda(), d.cuda()) for r, d in pairs]
+    out = {}
+    for pl in ("hv", "fh", "split"):
+        with tm.Ssimulacra2(w, h, tm.PixelFormat.SRGB8, batch=3, ring=2, pipeline=pl) as m:
+            ts = [m.compute(tm.DeviceFrame.packed(r), tm.DeviceFrame.packed(d)) for r, d in dev]
+            out[pl] = [(m.get_score(t), m.get_norms(t)) for t in ts]
+    for i, (r, d) in enumerate(pairs[:2]):
+        so, no, _ = oracle.ssimu2_srgb8(r.numpy(), d.numpy())
+        for pl in out:
+            _assert_norms(out[pl][i][1], no, out[pl][i][0], so)
+    for i in range(n):
+        for pl in ("fh", "split"):
+            assert abs(out["hv"][i][0] - out[pl][i][0]) < 1e-6
+            np.testing.assert_allclose(out["hv"][i][1], out[pl][i][1], rtol=1e-7, atol=1e-12)
 
 
 def test_identical_frames_score_100():

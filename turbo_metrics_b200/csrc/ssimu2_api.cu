@@ -47,6 +47,10 @@ struct Slot {
     BatchIn in{};
     TmaMaps maps{};                   // tensor maps of this slot's H-pass / XYB buffers, per scale (V pass)
     TmaMapsH maps_h{};                // (H pass)
+    TmaMapsX maps_x{};                // (fused H+V kernel)
+    f2* hstate = nullptr;             // k_hv hand-off records: [batch][total_recs][6][96]
+    uint32_t* hvflags = nullptr;      // [batch][total_recs] + 1 ticket counter at the end
+    uint32_t epoch = 0;               // launch counter of k_hv on this slot (flag value)
     uint32_t count = 0;               // pairs recorded
     uint64_t first_ticket = 0;
     bool inflight = false;            // fully launched, results not harvested yet
@@ -68,7 +72,9 @@ struct ssimu2_handle {
     std::vector<Slot> slots;
     uint32_t cur = 0;
     int awaiting = -1;                // slot index in the `awaiting` state, or -1
-    bool fuse = false;                // cross-batch fusion of front-end and H pass (ring >= 2)
+    bool fuse = false;                // cross-batch fusion of front-end and H pass (pipeline "fh", ring >= 2)
+    int pipeline = 0;                 // 0 = "hv": front-end, fused H+V kernel, finalize (default)
+                                      // 1 = "fh": k_fused_fh + k_vpass (ring >= 2) / 2 = "split": four kernels
     cudaStream_t main_stream = nullptr;
     uint64_t next_ticket = 0;
     double* scores_ring_d = nullptr;  // [kResultCap] device score stream
@@ -149,7 +155,7 @@ static void build_geo(ssimu2_handle* h)
     Geo& g = h->geo;
     int w = (int)h->cfg.width, hh = (int)h->cfg.height;
     long long xyb_off = 0, hb_off = 0;
-    int strips = 0, ns = 0;
+    int strips = 0, ns = 0, recs = 0;
     unsigned long long sum_px = 0, sum_px_ge1 = 0;
     for (int s = 0; s < kMaxScales; s++) {
         if (w < 8 || hh < 8) break;  // cpu.rs:359: tested on the size BEFORE this scale's downscale
@@ -165,12 +171,17 @@ static void build_geo(ssimu2_handle* h)
         xyb_off += 6LL * hh * d.pitch;
         d.hb_off = hb_off;
         hb_off += 15LL * hh * d.pitch;
+        d.nb = (hh + 4 + kXR - 1) / kXR;
+        d.rec0 = recs;
+        d.item0 = strips - d.n_strips;
+        recs += d.n_strips * d.nb;
         sum_px += (unsigned long long)w * hh;
         if (s >= 1) sum_px_ge1 += (unsigned long long)w * hh;
         ns++;
     }
     g.nscales = ns;
     g.total_strips = strips;
+    g.total_recs = recs;
     g.xyb_stride = xyb_off;
     g.hb_stride = hb_off;
     g.items_h = 0; g.items_v = 0;
@@ -211,9 +222,15 @@ static int build_tma_maps(ssimu2_handle* h, Slot& sl)
     EncodeTiledFn enc = (EncodeTiledFn)fn;
     const Geo& g = h->geo;
     for (int s = 0; s < g.nscales; s++) {
-        float* hb = sl.hb + g.sc[s].hb_off;
         float* xyb = sl.xyb + g.sc[s].xyb_off;
-        int r = make_plane_map(enc, &sl.maps.hb[s], hb, g.sc[s], 15, g.hb_stride, h->batch, kVCols, kVRowsPerStage, false);
+        int r;
+        if (h->pipeline == 0) {
+            r = make_plane_map(enc, &sl.maps_x.xyb_in[s], xyb, g.sc[s], 6, g.xyb_stride, h->batch, kXInW, kXR, false);
+            if (r) return r;
+            continue;
+        }
+        float* hb = sl.hb + g.sc[s].hb_off;
+        r = make_plane_map(enc, &sl.maps.hb[s], hb, g.sc[s], 15, g.hb_stride, h->batch, kVCols, kVRowsPerStage, false);
         if (r) return r;
         r = make_plane_map(enc, &sl.maps.xyb[s], xyb, g.sc[s], 6, g.xyb_stride, h->batch, kVCols, kVRowsPerStage, false);
         if (r) return r;
@@ -248,9 +265,44 @@ static int launch_unfused(ssimu2_handle* h, Slot& sl)
     if (sl.timed) cudaEventRecord(sl.ev_k[2], st);
     k_vpass<<<dim3(g.items_v, n), kVTmaThreads, kVSmemBytes, st>>>(g, sl.maps, sl.partials);
     if (sl.timed) cudaEventRecord(sl.ev_k[3], st);
-    k_finalize<<<n, 128, 0, st>>>(g, sl.partials, sl.norms_d, h->scores_ring_d, sl.first_ticket, kResultCap, sl.scores_d);
+    k_finalize<<<n, 128, 0, st>>>(g, sl.partials, sl.norms_d, h->scores_ring_d, sl.first_ticket, kResultCap, sl.scores_d, nullptr);
     if (sl.timed) cudaEventRecord(sl.ev_k[4], st);
     h->launches += 4;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(sl.scores_h, sl.scores_d, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(sl.norms_h, sl.norms_d, (size_t)n * 108 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventRecord(sl.ev_done, st));
+    sl.inflight = true;
+    sl.was_timed = sl.timed;
+    return 0;
+}
+
+// pipeline "hv": front-end, fused H+V kernel, finalize, back to back on the slot's stream
+template <int FMT>
+static int launch_hv(ssimu2_handle* h, Slot& sl)
+{
+    const Geo& g = h->geo;
+    const uint32_t n = sl.count;
+    cudaStream_t st = sl.stream;
+    if (sl.timed) cudaEventRecord(sl.ev_k[0], st);
+    {
+        dim3 grid((g.sc[0].w + 63) / 64, (g.sc[0].h + 63) / 64, n);
+        k_frontend<FMT><<<grid, kFThreads, kFSmemTotal, st>>>(g, sl.in, sl.xyb);
+    }
+    if (sl.timed) cudaEventRecord(sl.ev_k[1], st);
+    HvArgs a{};
+    a.hstate = sl.hstate;
+    a.flags = sl.hvflags;
+    a.ticket = sl.hvflags + (size_t)h->batch * g.total_recs;
+    a.partials = sl.partials;
+    a.epoch = ++sl.epoch;
+    a.nframes = (int)n;
+    k_hv<<<(unsigned)(g.items_v * n), kXThreads, kXSmemBytes, st>>>(g, sl.maps_x, a);
+    if (sl.timed) cudaEventRecord(sl.ev_k[2], st);
+    if (sl.timed) cudaEventRecord(sl.ev_k[3], st);
+    k_finalize<<<n, 128, 0, st>>>(g, sl.partials, sl.norms_d, h->scores_ring_d, sl.first_ticket, kResultCap, sl.scores_d, a.ticket);
+    if (sl.timed) cudaEventRecord(sl.ev_k[4], st);
+    h->launches += 3;
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(sl.scores_h, sl.scores_d, n * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(sl.norms_h, sl.norms_d, (size_t)n * 108 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -290,7 +342,7 @@ static int launch_tail(ssimu2_handle* h, Slot& sl)
     CU_TRY(cudaStreamWaitEvent(sl.stream, sl.ev_mid, 0));
     cudaStream_t st = sl.stream;
     k_vpass<<<dim3(g.items_v, n), kVTmaThreads, kVSmemBytes, st>>>(g, sl.maps, sl.partials);
-    k_finalize<<<n, 128, 0, st>>>(g, sl.partials, sl.norms_d, h->scores_ring_d, sl.first_ticket, kResultCap, sl.scores_d);
+    k_finalize<<<n, 128, 0, st>>>(g, sl.partials, sl.norms_d, h->scores_ring_d, sl.first_ticket, kResultCap, sl.scores_d, nullptr);
     h->launches += 2;
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(sl.scores_h, sl.scores_d, n * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -304,6 +356,7 @@ static int launch_tail(ssimu2_handle* h, Slot& sl)
 template <int FMT>
 static int launch_batch_fmt(ssimu2_handle* h, Slot& sl, int si)
 {
+    if (h->pipeline == 0) return launch_hv<FMT>(h, sl);
     if (!h->fuse) return launch_unfused<FMT>(h, sl);
     Slot* prev = h->awaiting >= 0 ? &h->slots[h->awaiting] : nullptr;
     int r = launch_fused<FMT>(h, prev, &sl);
@@ -531,7 +584,13 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
     CR(cudaFuncSetAttribute((const void*)k_hpass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBytes));
     CR(cudaFuncSetAttribute((const void*)k_vpass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVSmemBytes));
     static_assert(kHSmemBytes >= kFSmemTotal, "the fused kernel runs front-end tiles inside the H pass allocation");
-    h->fuse = h->ring >= 2 && getenv("SSIMU2_NO_FUSE") == nullptr;
+    {
+        // SSIMU2_PIPELINE = hv (default) | fh | split; "split" keeps the H-pass planes in HBM (ssimu2_debug_read what = 1)
+        const char* pm = getenv("SSIMU2_PIPELINE");
+        h->pipeline = (pm && !strcmp(pm, "fh")) ? 1 : ((pm && !strcmp(pm, "split")) ? 2 : 0);
+    }
+    CR(cudaFuncSetAttribute((const void*)k_hv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXSmemBytes));
+    h->fuse = h->pipeline == 1 && h->ring >= 2 && getenv("SSIMU2_NO_FUSE") == nullptr;
     CR(cudaStreamCreateWithFlags(&h->main_stream, cudaStreamNonBlocking));
     {
         static const void* ffn[6] = {(const void*)k_frontend<kNV12>,    (const void*)k_frontend<kP016>,
@@ -559,7 +618,9 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
         Slot& sl = h->slots[i];
         const Geo& g = h->geo;
         size_t xyb_b = (size_t)g.xyb_stride * h->batch * sizeof(float);
-        size_t hb_b = (size_t)g.hb_stride * h->batch * sizeof(float);
+        size_t hb_b = h->pipeline == 0 ? 0 : (size_t)g.hb_stride * h->batch * sizeof(float);
+        size_t hs_b = h->pipeline == 0 ? (size_t)g.total_recs * h->batch * kXHsBytes : 0;
+        size_t fl_b = h->pipeline == 0 ? ((size_t)g.total_recs * h->batch + 1) * sizeof(uint32_t) : 0;
         size_t part_b = (size_t)g.total_strips * 18 * h->batch * sizeof(double);
         CR(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         CR(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
@@ -567,13 +628,18 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
         CR(cudaEventCreateWithFlags(&sl.ev_mid, cudaEventDisableTiming));
         for (int k = 0; k < 5; k++) CR(cudaEventCreate(&sl.ev_k[k]));
         CR(cudaMalloc(&sl.xyb, xyb_b));
-        CR(cudaMalloc(&sl.hb, hb_b));
+        if (hb_b) CR(cudaMalloc(&sl.hb, hb_b));
+        if (hs_b) {
+            CR(cudaMalloc(&sl.hstate, hs_b));
+            CR(cudaMalloc(&sl.hvflags, fl_b));
+            CR(cudaMemset(sl.hvflags, 0, fl_b));
+        }
         CR(cudaMalloc(&sl.partials, part_b));
         CR(cudaMalloc(&sl.norms_d, (size_t)h->batch * 108 * sizeof(double)));
         CR(cudaMalloc(&sl.scores_d, (size_t)h->batch * sizeof(double)));
         CR(cudaMallocHost(&sl.norms_h, (size_t)h->batch * 108 * sizeof(double)));
         CR(cudaMallocHost(&sl.scores_h, (size_t)h->batch * sizeof(double)));
-        h->device_bytes += xyb_b + hb_b + part_b + (size_t)h->batch * 109 * sizeof(double);
+        h->device_bytes += xyb_b + hb_b + hs_b + fl_b + part_b + (size_t)h->batch * 109 * sizeof(double);
         rc = build_tma_maps(h, sl);
         if (rc) goto fail;
         sl.timed = !h->fuse && getenv("SSIMU2_NO_TIMING") == nullptr;
@@ -598,7 +664,7 @@ int ssimu2_destroy(ssimu2_t* h)
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
         for (int k = 0; k < 5; k++)
             if (sl.ev_k[k]) cudaEventDestroy(sl.ev_k[k]);
-        cudaFree(sl.xyb); cudaFree(sl.hb); cudaFree(sl.partials); cudaFree(sl.norms_d); cudaFree(sl.scores_d);
+        cudaFree(sl.xyb); cudaFree(sl.hb); cudaFree(sl.hstate); cudaFree(sl.hvflags); cudaFree(sl.partials); cudaFree(sl.norms_d); cudaFree(sl.scores_d);
         cudaFree(sl.staging);
         if (sl.norms_h) cudaFreeHost(sl.norms_h);
         if (sl.scores_h) cudaFreeHost(sl.scores_h);
@@ -826,6 +892,7 @@ int ssimu2_debug_read(ssimu2_t* h, uint64_t ticket, int what, int scale, float* 
         planes = 6;
         src = sl.xyb + idx * h->geo.xyb_stride + sd.xyb_off;
     } else if (what == 1) {
+        if (!sl.hb) return SSIMU2_E_UNSUPPORTED;  // the fused H+V pipeline never materialises these planes
         planes = 15;
         src = sl.hb + idx * h->geo.hb_stride + sd.hb_off;
     } else {

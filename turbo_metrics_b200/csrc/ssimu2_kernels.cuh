@@ -34,6 +34,9 @@ struct ScaleDesc {
     int strip0;            // index of this scale's first strip in the partial-sum table
     long long xyb_off;     // float offset of scale s inside a slot's XYB buffer: [2 img][3 ch][h][pitch]
     long long hb_off;      // float offset of scale s inside a slot's H-pass buffer: [15][h][pitch]
+    int nb;                // k_hv: 12-row bands, ceil((h + 4) / 12)
+    int rec0;              // k_hv: index of this scale's first hand-off record (records: [strip][band])
+    int item0;             // k_hv: strips of the larger scales before this one
 };
 
 struct YuvCoef {           // MatrixCoefficients::coefficients, cuda-colorspace-kernel/src/lib.rs:183-201
@@ -46,6 +49,7 @@ struct Geo {
     int nscales;
     int items_h, items_v;        // work items per frame (all scales)
     int total_strips;            // partial-sum rows per frame
+    int total_recs;              // k_hv hand-off records per frame
     long long xyb_stride;        // floats per slot
     long long hb_stride;         // floats per slot
     YuvCoef coef;
@@ -363,6 +367,9 @@ __global__ void __launch_bounds__(kFThreads, KF_MINB) k_frontend(const __grid_co
 struct alignas(64) TmaMaps {
     CUtensorMap hb[kMaxScales];      // V pass load : 15 planes, box {64, 2, 15, 1}, no swizzle
     CUtensorMap xyb[kMaxScales];     // V pass load :  6 planes, box {64, 2, 6, 1},  no swizzle
+};
+struct alignas(64) TmaMapsX {
+    CUtensorMap xyb_in[kMaxScales];  // k_hv load   :  6 planes, box {76, 12, 6, 1},  no swizzle
 };
 struct alignas(64) TmaMapsH {
     CUtensorMap xyb_in[kMaxScales];  // H pass load :  6 planes, box {32, 32, 6, 1},  128B swizzle
@@ -985,6 +992,336 @@ __global__ void __launch_bounds__(kVTmaThreads, 2) k_vpass(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------
+// k_hv: horizontal pass, vertical pass, error maps and partial sums in ONE kernel -- the 15 H-pass planes
+// (60 B per pyramid pixel, written and read back by k_hpass / k_vpass) never leave the SM.
+// Same arithmetic, operation for operation, as k_hpass + k_vpass (cpu.rs:967-1022, :1054-1115, :581-683).
+//
+// CTA = one 64-column strip of one scale of one frame, walked top to bottom in 12-row bands; 7 warps:
+//   P  (1 warp) : TMA-loads the XYB tile of band j (6 planes x 12 rows x 76 columns: 8 columns of left halo for the
+//                 10-tap history, 4 of right halo for the look-ahead tap) into a 3-deep ring, and fetches the
+//                 horizontal filter state the strip to the LEFT left behind for band j (see below)
+//   H  (3 warps): warp = channel, lane = (quantity, row pair): 5 x 6 = 30 lanes, two rows per lane in packed f32x2;
+//                 scans the 64 columns of the band, writes the 15-plane tile of the band into a 3-deep ring
+//   V  (3 warps): warp = channel, lane = column pair: the five vertical filters + error maps + sums of k_vpass;
+//                 the 10-row delay line is read back from the tile ring (this band's tile and the previous one)
+// The horizontal recursion runs along the whole row, so strip k of a band continues from the filter state strip
+// k-1 reached at its right edge: 6 floats per (plane, row), published through global memory ([6][96] f2 per
+// band, 4.6 KB) with a release flag per (strip, band); the halo columns supply the 10 products of history.
+// Strips of one chain (frame, scale) therefore run as a systolic wavefront, one band apart.  Work items are
+// handed out by an atomic ticket in dependency order (strip-major), so a CTA only ever waits for CTAs that are
+// already running: no deadlock regardless of how many CTAs are resident.
+// ------------------------------------------------------------------------------------------
+constexpr int kXR = 12;                                  // rows per band
+constexpr int kXC = kVCols;                              // columns per strip (the strip list is the V pass's)
+constexpr int kXInLead = 8;                              // tile starts at column x0 - 8
+constexpr int kXInW = 76;                                // x0 - 8 .. x0 + 67
+constexpr int kXInPlane = kXR * kXInW;                   // 912 floats
+constexpr int kXInFloats = 6 * kXInPlane;
+constexpr uint32_t kXInBytes = kXInFloats * 4;           // 21888
+constexpr int kXHbPitch = 68;                            // floats; with the plane pad: conflict-free 128-bit stores
+constexpr int kXHbPlane = kXR * kXHbPitch + 8;           // 824 floats
+constexpr int kXHbFloats = 15 * kXHbPlane;
+constexpr uint32_t kXHbBytes = kXHbFloats * 4;           // 49440
+constexpr int kXHThreads = 96, kXVThreads = 96;
+constexpr int kXThreads = kXHThreads + kXVThreads + 32;  // + P warp
+constexpr int kXHsF2 = 6 * kXHThreads;                   // hand-off record: [6 state words][96 H threads] f2
+constexpr uint32_t kXHsBytes = kXHsF2 * 8;               // 4608
+constexpr uint32_t kXOffIn = 0;
+constexpr uint32_t kXOffHb = kXOffIn + 3 * kXInBytes;
+constexpr uint32_t kXOffHs = kXOffHb + 3 * kXHbBytes;
+constexpr uint32_t kXOffOnes = kXOffHs + 2 * kXHsBytes;  // one row of 76 ones (the second factor of the mu planes)
+constexpr uint32_t kXOffBars = kXOffOnes + 320;
+constexpr size_t kXSmemBytes = kXOffBars + 16 * 8;
+static_assert(kXOffHb % 16 == 0 && kXHbBytes % 16 == 0 && kXInBytes % 128 == 0 && kXOffBars % 8 == 0, "k_hv smem layout");
+
+// mbarrier wait with a watchdog: a protocol bug must end in a trap, not in a hung GPU
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t it = 0;; it++) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(a), "r"(parity), "r"(20000u)
+            : "memory");
+        if (ok) return;
+        if (it > 400000u) __trap();
+    }
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, f2 v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v.v) : "memory"); }
+
+// hstep on two rows at once (see f2_sub_prod for the form of the subtraction).
+struct HState2 {
+    f2 p1, p3, p5, pp1, pp3, pp5;
+};
+__device__ __forceinline__ f2 hstep2(HState2& s, f2 left, f2 right)
+{
+    const f2 sum = f2_add(left, right);
+    f2 o1 = f2_mul(sum, f2_splat(RG_IN_1)), o3 = f2_mul(sum, f2_splat(RG_IN_3)), o5 = f2_mul(sum, f2_splat(RG_IN_5));
+    // t = pp - o (as fma(o, -1, pp)); the wanted o - pp is its exact negation, folded into the next FMA's operand
+    const f2 t1 = f2_sub_prod(s.pp1, o1), t3 = f2_sub_prod(s.pp3, o3), t5 = f2_sub_prod(s.pp5, o5);
+    s.pp1 = s.p1; s.pp3 = s.p3; s.pp5 = s.p5;
+    o1 = f2_fma(f2_splat(RG_PREV_1), s.p1, f2_neg(t1));
+    o3 = f2_fma(f2_splat(RG_PREV_3), s.p3, f2_neg(t3));
+    o5 = f2_fma(f2_splat(RG_PREV_5), s.p5, f2_neg(t5));
+    s.p1 = o1; s.p3 = o3; s.p5 = o5;
+    return f2_add(f2_add(o1, o3), o5);
+}
+
+struct HvArgs {
+    f2* hstate;                 // [frames][total_recs][6][96]
+    uint32_t* flags;            // [frames][total_recs], == epoch once the record is published
+    uint32_t* ticket;           // work-item counter (reset by k_finalize)
+    double* partials;
+    uint32_t epoch;
+    int nframes;
+};
+
+__global__ void __launch_bounds__(kXThreads, 1) k_hv(const __grid_constant__ Geo g, const __grid_constant__ TmaMapsX maps,
+                                                     const HvArgs a)
+{
+    extern __shared__ __align__(1024) char xs[];
+    __shared__ int s_item;
+    const uint32_t sbase = smem_u32(xs);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + kXOffBars);
+    uint64_t* in_full = bars;        // [3] TMA
+    uint64_t* in_free = bars + 3;    // [3] 3 V warps
+    uint64_t* hs_full = bars + 6;    // [2] P
+    uint64_t* hs_free = bars + 8;    // [2] 3 H warps
+    uint64_t* hb_full = bars + 10;   // [3] 3 H warps
+    uint64_t* hb_free = bars + 13;   // [3] 3 V warps
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        s_item = (int)atomicAdd(a.ticket, 1u);
+        for (int i = 0; i < 3; i++) {
+            mbar_init(&in_full[i], 1);
+            mbar_init(&in_free[i], 3);
+            mbar_init(&hb_full[i], 3);
+            mbar_init(&hb_free[i], 3);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&hs_full[i], 1);
+            mbar_init(&hs_free[i], 3);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // tile slot 2 plays "the band above band 0": zeros (the vertical filter's zero padding); the ones row
+    {
+        float4* z = reinterpret_cast<float4*>(xs + kXOffHb + 2 * kXHbBytes);
+        for (int i = tid; i < (int)(kXHbBytes / 16); i += kXThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* ones = reinterpret_cast<float*>(xs + kXOffOnes);
+        if (tid < 80) ones[tid] = 1.0f;
+    }
+    __syncthreads();
+
+    // work item -> (scale, strip, frame), strip-major inside a scale so that the left neighbour has a smaller ticket
+    int item = s_item, s = 0;
+    {
+        const int nf = a.nframes;
+        while (s + 1 < g.nscales && item >= (g.sc[s].item0 + g.sc[s].n_strips) * nf) s++;
+        item -= g.sc[s].item0 * nf;
+    }
+    const int k = item / a.nframes, frame = item - k * a.nframes;
+    const ScaleDesc sd = g.sc[s];
+    const int W = sd.w, H = sd.h, nb = sd.nb;
+    const int x0 = k * kXC;
+    const size_t rec_base = (size_t)frame * g.total_recs + sd.rec0;   // + strip * nb + band
+
+    if (warp == 6) {
+        // ===== P: tile loads + hand-off fetch =====
+        const CUtensorMap* map = &maps.xyb_in[s];
+        for (int j = 0; j < nb; j++) {
+            const int si = j % 3;
+            if (j >= 3) mbar_wait_wd(&in_free[si], (uint32_t)((j / 3 - 1) & 1));
+            if (lane == 0) {
+                mbar_expect_tx(&in_full[si], kXInBytes);
+                tma_load_4d(xs + kXOffIn + si * kXInBytes, map, &in_full[si], x0 - kXInLead, j * kXR, 0, frame);
+            }
+            if (k > 0) {
+                const int hi = j & 1;
+                if (j >= 2) mbar_wait_wd(&hs_free[hi], (uint32_t)((j / 2 - 1) & 1));
+                const size_t rec = rec_base + (size_t)(k - 1) * nb + j;
+                const uint32_t* fl = a.flags + rec;
+                for (uint32_t it = 0; ld_acquire_u32(fl) != a.epoch; it++) {
+                    __nanosleep(100);
+                    if (it > 40000000u) __trap();
+                }
+                const float4* src = reinterpret_cast<const float4*>(a.hstate + rec * kXHsF2);
+                float4* dst = reinterpret_cast<float4*>(xs + kXOffHs + hi * kXHsBytes);
+#pragma unroll
+                for (int i = 0; i < (int)(kXHsBytes / 16 / 32); i++) dst[i * 32 + lane] = __ldcg(src + i * 32 + lane);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hs_full[hi]);
+            }
+        }
+        return;
+    }
+
+    if (warp < 3) {
+        // ===== H: warp = channel, lane = (quantity, row pair); lanes 30, 31 shadow lane 29 =====
+        const int ch = warp, l = lane < 30 ? lane : 29;
+        const int q = l / 6, rp = l - 6 * q;
+        const int px = (q == 1 || q == 4) ? 3 + ch : ch;
+        const int py = (q == 0) ? ch : ((q == 1 || q == 2) ? 3 + ch : -1);
+        const uint32_t offxA = (uint32_t)((px * kXInPlane + rp * kXInW) * 4), offxB = offxA + 6 * kXInW * 4;
+        const uint32_t offyA = py < 0 ? 0u : (uint32_t)((py * kXInPlane + rp * kXInW) * 4), offyB = offyA + 6 * kXInW * 4;
+        const uint32_t ones = sbase + kXOffOnes;
+        const uint32_t offo = (uint32_t)(((q * 3 + ch) * kXHbPlane + rp * kXHbPitch) * 4);
+        const int hidx = warp * 32 + lane;
+        const bool last_strip = (k == sd.n_strips - 1);
+        for (int j = 0; j < nb; j++) {
+            const int si = j % 3;
+            mbar_wait_wd(&in_full[si], (uint32_t)((j / 3) & 1));
+            if (j >= 2) mbar_wait_wd(&hb_free[si], (uint32_t)(((j - 2) / 3) & 1));
+            HState2 st;
+            if (k > 0) {
+                const int hi = j & 1;
+                mbar_wait_wd(&hs_full[hi], (uint32_t)((j / 2) & 1));
+                const uint32_t hsb = sbase + kXOffHs + hi * kXHsBytes + (uint32_t)hidx * 8u;
+                st.p1 = lds64(hsb); st.p3 = lds64(hsb + 96 * 8); st.p5 = lds64(hsb + 2 * 96 * 8);
+                st.pp1 = lds64(hsb + 3 * 96 * 8); st.pp3 = lds64(hsb + 4 * 96 * 8); st.pp5 = lds64(hsb + 5 * 96 * 8);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hs_free[hi]);
+            } else {
+                const f2 z = f2_splat(0.0f);
+                st = HState2{z, z, z, z, z, z};
+            }
+            const uint32_t inb = sbase + kXOffIn + si * kXInBytes;
+            const uint32_t axA = inb + offxA, axB = inb + offxB;
+            const uint32_t ayA = py < 0 ? ones : inb + offyA, ayB = py < 0 ? ones : inb + offyB;
+            const uint32_t ao = sbase + kXOffHb + si * kXHbBytes + offo;
+            // products of tile columns 4g .. 4g+3 for both rows
+            f2 pr[kXInW];
+#pragma unroll
+            for (int gI = 0; gI < kXInW / 4; gI++) {
+                const float4 xa = lds128(axA + gI * 16), xb = lds128(axB + gI * 16);
+                const float4 ya = lds128(ayA + gI * 16), yb = lds128(ayB + gI * 16);
+                pr[4 * gI + 0] = f2_pack(xa.x * ya.x, xb.x * yb.x);
+                pr[4 * gI + 1] = f2_pack(xa.y * ya.y, xb.y * yb.y);
+                pr[4 * gI + 2] = f2_pack(xa.z * ya.z, xb.z * yb.z);
+                pr[4 * gI + 3] = f2_pack(xa.w * ya.w, xb.w * yb.w);
+                if (gI == 2 && k == 0) {
+                    // the recursion starts at n = -4 (cpu.rs:976): four warm-up steps on x[0..3], no output
+#pragma unroll
+                    for (int e = 0; e < 4; e++) (void)hstep2(st, f2_splat(0.0f), pr[8 + e]);
+                }
+                if (gI >= 3) {
+                    // tile column c = 4 gI + e is x[n + 4] of output column n = c - 12; the left tap x[n - 6] is c - 10
+                    float oa[4], ob[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const f2 o = hstep2(st, pr[4 * gI + e - 10], pr[4 * gI + e]);
+                        f2_unpack(o, oa[e], ob[e]);
+                    }
+                    const uint32_t oo = ao + (uint32_t)(gI - 3) * 16u;
+                    sts128(oo, make_float4(oa[0], oa[1], oa[2], oa[3]));
+                    sts128(oo + 6 * kXHbPitch * 4, make_float4(ob[0], ob[1], ob[2], ob[3]));
+                }
+            }
+            if (last_strip && x0 + kXC > W) {
+                // columns past the right edge hold the filter's ring-out: the V pass must see zeros there
+                float* t0 = reinterpret_cast<float*>(xs + kXOffHb + si * kXHbBytes) + (q * 3 + ch) * kXHbPlane + rp * kXHbPitch;
+                for (int c = W - x0; c < kXC; c++) { t0[c] = 0.0f; t0[6 * kXHbPitch + c] = 0.0f; }
+            }
+            if (!last_strip) {
+                f2* rec = a.hstate + (rec_base + (size_t)k * nb + j) * kXHsF2 + hidx;
+                rec[0] = st.p1; rec[96] = st.p3; rec[2 * 96] = st.p5;
+                rec[3 * 96] = st.pp1; rec[4 * 96] = st.pp3; rec[5 * 96] = st.pp5;
+                asm volatile("bar.sync 1, %0;" ::"n"(kXHThreads) : "memory");
+                if (tid == 0) {
+                    __threadfence();
+                    st_release_u32(a.flags + rec_base + (size_t)k * nb + j, a.epoch);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hb_full[si]);
+        }
+        return;
+    }
+
+    // ===== V: warp = channel, lane = column pair =====
+    const int c = warp - 3;
+    const bool vlast = (k == sd.n_strips - 1);
+    (void)vlast;
+    const f2 zero2 = f2_splat(0.0f);
+    VState2 stq[5];
+#pragma unroll
+    for (int qi = 0; qi < 5; qi++) stq[qi] = VState2{zero2, zero2, zero2, zero2, zero2, zero2};
+    f2 tail_r[4] = {zero2, zero2, zero2, zero2}, tail_d[4] = {zero2, zero2, zero2, zero2};
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    const uint32_t lane8 = (uint32_t)lane * 8u;
+    for (int j = 0; j < nb; j++) {
+        const int si = j % 3, sp = (j + 2) % 3;
+        mbar_wait_wd(&hb_full[si], (uint32_t)((j / 3) & 1));
+        mbar_wait_wd(&in_full[si], (uint32_t)((j / 3) & 1));
+        const uint32_t cur = sbase + kXOffHb + si * kXHbBytes + lane8;
+        const uint32_t prv = sbase + kXOffHb + sp * kXHbBytes + lane8;
+        const uint32_t inb = sbase + kXOffIn + si * kXInBytes + kXInLead * 4 + lane8;
+        f2 part[6] = {zero2, zero2, zero2, zero2, zero2, zero2};
+#pragma unroll
+        for (int i = 0; i < kXR; i++) {
+            const int t = j * kXR + i;
+            f2 o[5];
+#pragma unroll
+            for (int qi = 0; qi < 5; qi++) {
+                const uint32_t pl = (uint32_t)((qi * 3 + c) * kXHbPlane * 4);
+                const f2 v = lds64(cur + pl + (uint32_t)(i * kXHbPitch * 4));
+                const f2 d = i < 10 ? lds64(prv + pl + (uint32_t)((i + 2) * kXHbPitch * 4))
+                                    : lds64(cur + pl + (uint32_t)((i - 10) * kXHbPitch * 4));
+                o[qi] = vstep2(stq[qi], d, v);
+            }
+            f2 fr, fd;
+            if (i < 4) {
+                fr = tail_r[i]; fd = tail_d[i];
+            } else {
+                fr = lds64(inb + (uint32_t)((c * kXInPlane + (i - 4) * kXInW) * 4));
+                fd = lds64(inb + (uint32_t)(((3 + c) * kXInPlane + (i - 4) * kXInW) * 4));
+            }
+            if (t >= 4 && t < H + 4) error_maps2(o, fr, fd, part);
+            if (i == kXR / 2 - 1) {
+#pragma unroll
+                for (int kk = 0; kk < 6; kk++) { acc[kk] += (double)f2_hsum(part[kk]); part[kk] = zero2; }
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++) acc[kk] += (double)f2_hsum(part[kk]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            tail_r[i] = lds64(inb + (uint32_t)((c * kXInPlane + (kXR - 4 + i) * kXInW) * 4));
+            tail_d[i] = lds64(inb + (uint32_t)(((3 + c) * kXInPlane + (kXR - 4 + i) * kXInW) * 4));
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&in_free[si]);
+            mbar_arrive(&hb_free[sp]);
+        }
+    }
+#pragma unroll
+    for (int kk = 0; kk < 6; kk++) {
+        double vsum = acc[kk];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) vsum += __shfl_down_sync(0xffffffffu, vsum, off);
+        if (lane == 0) a.partials[((size_t)frame * g.total_strips + sd.strip0 + k) * 18 + c * 6 + kk] = vsum;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // k_finalize: partial sums -> 108 norms -> score.  Replaces the host-side
 // Ssimulacra2::post_process_scores (ssimulacra2-cuda/src/lib.rs:449-623); follows
 // Msssim::score cpu.rs:728-871 (weight order [channel][scale][L1,L4][ssim,artifact,detail]).
@@ -1014,8 +1351,9 @@ __device__ const double kWeight[108] = {
 __global__ void __launch_bounds__(128) k_finalize(const __grid_constant__ Geo g, const double* __restrict__ partials,
                                                   double* __restrict__ norms_out, double* __restrict__ scores_ring,
                                                   unsigned long long first_ticket, unsigned long long ring_cap,
-                                                  double* __restrict__ scores_out)
+                                                  double* __restrict__ scores_out, uint32_t* __restrict__ hv_ticket)
 {
+    if (hv_ticket != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *hv_ticket = 0u;  // k_hv's work counter, for the next batch
     __shared__ double norms[108];
     const int frame = blockIdx.x, tid = threadIdx.x;
     if (tid < 108) norms[tid] = 0.0;

@@ -82,10 +82,25 @@ class Ssimulacra2:
 
     def __init__(self, width: int, height: int, fmt: PixelFormat = PixelFormat.LINEARF32,
                  matrix: ColorMatrix = ColorMatrix.BT709, full_range: bool = False, device: int = 0,
-                 batch: int = 0, ring: int = 0):
+                 batch: int = 0, ring: int = 0, pipeline: Optional[str] = None):
+        """pipeline (development / tests): None = the library default ("hv": front-end, fused H+V kernel,
+        finalize); "split" = four kernels with the H-pass planes in HBM (debug_read(what=1));
+        "fh" = front-end fused with the previous batch's H pass + separate V pass.  Passed to the library
+        through the SSIMU2_PIPELINE environment variable it reads in ssimu2_create."""
         self._h = C.c_void_p()
         cfg = Config(width, height, int(fmt), int(matrix), int(full_range), device, batch, ring)
-        check(_lib.lib().ssimu2_create(C.byref(self._h), C.byref(cfg)), "ssimu2_create")
+        import os
+        old = os.environ.get("SSIMU2_PIPELINE")
+        if pipeline is not None:
+            os.environ["SSIMU2_PIPELINE"] = pipeline
+        try:
+            check(_lib.lib().ssimu2_create(C.byref(self._h), C.byref(cfg)), "ssimu2_create")
+        finally:
+            if pipeline is not None:
+                if old is None:
+                    os.environ.pop("SSIMU2_PIPELINE", None)
+                else:
+                    os.environ["SSIMU2_PIPELINE"] = old
         self.width, self.height, self.format = width, height, PixelFormat(fmt)
         self._keep = {}
 

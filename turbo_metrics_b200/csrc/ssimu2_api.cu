@@ -73,6 +73,7 @@ struct ssimu2_handle {
     uint32_t cur = 0;
     int awaiting = -1;                // slot index in the `awaiting` state, or -1
     bool fuse = false;                // cross-batch fusion of front-end and H pass (pipeline "fh", ring >= 2)
+    bool frontend2 = true;            // warp-per-region front-end (SSIMU2_FRONTEND=1 selects the shared-memory tile version)
     int pipeline = 0;                 // 0 = "hv": front-end, fused H+V kernel, finalize (default)
                                       // 1 = "fh": k_fused_fh + k_vpass (ring >= 2) / 2 = "split": four kernels
     cudaStream_t main_stream = nullptr;
@@ -256,7 +257,11 @@ static int launch_unfused(ssimu2_handle* h, Slot& sl)
     const uint32_t n = sl.count;
     cudaStream_t st = sl.stream;
     if (sl.timed) cudaEventRecord(sl.ev_k[0], st);
-    {
+    if (h->frontend2) {
+        const int rx = (g.sc[0].w + kF2Region - 1) / kF2Region, ry = (g.sc[0].h + kF2Region - 1) / kF2Region;
+        const int per_cta = (kF2Threads / 32) * kF2RegionsPerWarp;
+        k_frontend2<FMT><<<dim3((rx + per_cta - 1) / per_cta, ry, n), kF2Threads, 0, st>>>(g, sl.in, sl.xyb);
+    } else {
         dim3 grid((g.sc[0].w + 63) / 64, (g.sc[0].h + 63) / 64, n);
         k_frontend<FMT><<<grid, kFThreads, kFSmemTotal, st>>>(g, sl.in, sl.xyb);
     }
@@ -285,7 +290,11 @@ static int launch_hv(ssimu2_handle* h, Slot& sl)
     const uint32_t n = sl.count;
     cudaStream_t st = sl.stream;
     if (sl.timed) cudaEventRecord(sl.ev_k[0], st);
-    {
+    if (h->frontend2) {
+        const int rx = (g.sc[0].w + kF2Region - 1) / kF2Region, ry = (g.sc[0].h + kF2Region - 1) / kF2Region;
+        const int per_cta = (kF2Threads / 32) * kF2RegionsPerWarp;
+        k_frontend2<FMT><<<dim3((rx + per_cta - 1) / per_cta, ry, n), kF2Threads, 0, st>>>(g, sl.in, sl.xyb);
+    } else {
         dim3 grid((g.sc[0].w + 63) / 64, (g.sc[0].h + 63) / 64, n);
         k_frontend<FMT><<<grid, kFThreads, kFSmemTotal, st>>>(g, sl.in, sl.xyb);
     }
@@ -588,6 +597,10 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
         // SSIMU2_PIPELINE = hv (default) | fh | split; "split" keeps the H-pass planes in HBM (ssimu2_debug_read what = 1)
         const char* pm = getenv("SSIMU2_PIPELINE");
         h->pipeline = (pm && !strcmp(pm, "fh")) ? 1 : ((pm && !strcmp(pm, "split")) ? 2 : 0);
+    }
+    {
+        const char* fe = getenv("SSIMU2_FRONTEND");
+        h->frontend2 = !(fe && !strcmp(fe, "1"));
     }
     CR(cudaFuncSetAttribute((const void*)k_hv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXSmemBytes));
     h->fuse = h->pipeline == 1 && h->ring >= 2 && getenv("SSIMU2_NO_FUSE") == nullptr;

@@ -362,6 +362,326 @@ __global__ void __launch_bounds__(kFThreads, KF_MINB) k_frontend(const __grid_co
     frontend_tile<FMT, kFThreads>(g, in, xyb_base, blockIdx.x, blockIdx.y, blockIdx.z, fsm);
 }
 
+// ------------------------------------------------------------------------------------------
+// k_frontend2: the same front-end (colour conversion, linear-RGB pyramid, XYB of every scale), organised so that a
+// WARP owns a 32x32 source region and needs no shared-memory pyramid:
+//   lane = a 4x4 pixel patch (8 x 4 patches per pass, two passes): levels 0, 1 and 2 of the pyramid are formed in
+//   registers; levels 3 and 4 by warp shuffles; level 5 from the two passes.  XYB of levels 0-2 is evaluated at full
+//   lane occupancy; the 16 + 4 + 1 pixels of levels 3-5 of a region share ONE evaluation.
+// YUV 4:2:0 patches are read with 64/32-bit loads (4 luma samples, 2 chroma pairs); the chroma work (g', the row
+// pointers of the exact R / B memo tables) is done once per 2x2 block; XYB rows leave as 128-bit stores.
+// Arithmetic is that of k_frontend, operation for operation (box sum order (0,0),(1,0),(0,1),(1,1), edge clamp at
+// every level, cpu.rs:545-579).
+// ------------------------------------------------------------------------------------------
+struct YuvChroma {
+    float g_, r_, b_;
+    const float* rrow;     // memo rows (null: arithmetic path)
+    const float* brow;
+};
+
+template <int FMT>
+__device__ __forceinline__ YuvChroma yuv_chroma(int cbi, int cri, const YuvCoef& k, const float* __restrict__ lut, int lut_n,
+                                                int lut_shift)
+{
+    YuvChroma c;
+    const float cb = (float)(cbi - k.neutral), cr = (float)(cri - k.neutral);
+    c.g_ = fmaf(k.g1, cb, k.g2 * cr);
+    c.r_ = k.r * cr;
+    c.b_ = k.b * cb;
+    const bool ok = lut != nullptr && ((cbi | cri) & ((1 << lut_shift) - 1)) == 0;
+    c.rrow = ok ? lut + (size_t)(cri >> lut_shift) * lut_n : nullptr;
+    c.brow = ok ? lut + (size_t)lut_n * lut_n + (size_t)(cbi >> lut_shift) * lut_n : nullptr;
+    return c;
+}
+
+// one luma sample + its block's chroma -> linear RGB (same expressions as load_px)
+__device__ __forceinline__ void yuv_px(int Y, const YuvChroma& c, const YuvCoef& k, const exact_math::PowfTables& T, int lut_shift,
+                                       float& r, float& g, float& b)
+{
+    const float luma = (float)(max(Y, k.luma_min) - k.luma_min) * k.y;
+    g = clamp01(bt709_eotf(luma + c.g_, T));
+    if (c.rrow != nullptr && (Y & ((1 << lut_shift) - 1)) == 0) {
+        const int yc = Y >> lut_shift;
+        r = __ldg(c.rrow + yc);
+        b = __ldg(c.brow + yc);
+    } else {
+        r = clamp01(bt709_eotf(luma + c.r_, T));
+        b = clamp01(bt709_eotf(luma + c.b_, T));
+    }
+}
+
+// XYB for the pixel formats whose linear values are guaranteed in [0, 1] (every integer format): no range check
+template <int FMT>
+__device__ __forceinline__ void xyb_of(float r, float g, float b, const exact_math::CbrtScale& S, float& X, float& Y, float& B)
+{
+    if constexpr (FMT == kSRGBF32 || FMT == kLINEARF32) {
+        linear_to_xyb(r, g, b, S, X, Y, B);
+    } else {
+        const float K_M02 = 0.078f, K_M00 = 0.30f, K_M01 = 1.0f - K_M02 - K_M00;
+        const float K_M12 = 0.078f, K_M10 = 0.23f, K_M11 = 1.0f - K_M12 - K_M10;
+        const float K_M20 = 0.24342269f, K_M21 = 0.20476745f, K_M22 = 1.0f - K_M20 - K_M21;
+        const float K_B0 = 0.0037930734f;
+        const float K_B0_ROOT = 0.1559542025327239180319220163705f;
+        float rg = fmaf(K_M00, r, fmaf(K_M01, g, fmaf(K_M02, b, K_B0)));
+        float gr = fmaf(K_M10, r, fmaf(K_M11, g, fmaf(K_M12, b, K_B0)));
+        float bb = fmaf(K_M20, r, fmaf(K_M21, g, fmaf(K_M22, b, K_B0)));
+        rg = fmaxf(rg, 0.0f); gr = fmaxf(gr, 0.0f); bb = fmaxf(bb, 0.0f);
+        rg = exact_math::cbrtf_glibc<false>(rg, kEM, &S) - K_B0_ROOT;
+        gr = exact_math::cbrtf_glibc<false>(gr, kEM, &S) - K_B0_ROOT;
+        bb = exact_math::cbrtf_glibc<false>(bb, kEM, &S) - K_B0_ROOT;
+        const float x = 0.5f * (rg - gr), y = 0.5f * (rg + gr);
+        X = fmaf(x, 14.0f, 0.42f);
+        Y = y + 0.01f;
+        B = (bb - y) + 0.55f;
+    }
+}
+
+struct Rgb {
+    float r, g, b;
+};
+// 2x2 box of a (x,y), b (x+1,y), c (x,y+1), d (x+1,y+1) with the edge clamp of downscale_by_2: a neighbour past the
+// edge is replaced by the clamped one.
+__device__ __forceinline__ Rgb box_clamped(Rgb a, Rgb b, Rgb c, Rgb d, bool xin, bool yin)
+{
+    if (!xin) { b = a; d = c; }
+    if (!yin) { c = a; d = b; }
+    return Rgb{box4(a.r, b.r, c.r, d.r), box4(a.g, b.g, c.g, d.g), box4(a.b, b.b, c.b, d.b)};
+}
+__device__ __forceinline__ Rgb shfl_rgb_xor(Rgb v, int m)
+{
+    return Rgb{__shfl_xor_sync(0xffffffffu, v.r, m), __shfl_xor_sync(0xffffffffu, v.g, m), __shfl_xor_sync(0xffffffffu, v.b, m)};
+}
+__device__ __forceinline__ Rgb shfl_rgb(Rgb v, int src)
+{
+    return Rgb{__shfl_sync(0xffffffffu, v.r, src), __shfl_sync(0xffffffffu, v.g, src), __shfl_sync(0xffffffffu, v.b, src)};
+}
+
+constexpr int kF2Region = 32;
+constexpr int kF2Threads = 256;
+constexpr int kF2RegionsPerWarp = 2;    // consecutive regions along x
+
+// One 32x32 region of one image of one frame; executed by a full warp.
+template <int FMT>
+__device__ __forceinline__ void frontend_region(const Geo& g, const FrameIn& f, float* __restrict__ ximg /* slot base + image */,
+                                                int img, int X0, int Y0, const exact_math::PowfTables& T,
+                                                const exact_math::CbrtScale& S)
+{
+    const int lane = threadIdx.x & 31;
+    const int pxi = lane & 7, pyi = lane >> 3;
+    const int ns = g.nscales;
+    const int W0 = g.sc[0].w, H0 = g.sc[0].h;
+    auto plane_of = [&](int s) { return (size_t)g.sc[s].h * g.sc[s].pitch; };
+    auto base_of = [&](int s) { return ximg + g.sc[s].xyb_off + (size_t)img * 3 * plane_of(s); };
+    const bool vec_ok = (FMT == kNV12 || FMT == kP016) &&
+                        ((((uintptr_t)f.p0 | (uintptr_t)f.p1 | (uintptr_t)f.pitch) & 7u) == 0);
+    Rgb l3a = Rgb{0.f, 0.f, 0.f}, l3b = l3a, l4a = l3a, l4b = l3a;   // level 3 / 4 pixels of pass 0 / 1
+
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        const int px0 = X0 + 4 * pxi, py0 = Y0 + 4 * (pyi + 4 * pass);
+        Rgb l1[2][2];
+#pragma unroll
+        for (int br = 0; br < 2; br++) {
+            const int y = py0 + 2 * br;
+            Rgb lin[2][4];
+            if (px0 + 4 <= W0 && y + 2 <= H0 && vec_ok) {
+                // ---- interior YUV patch row pair: vector loads, chroma shared by the 2x2 blocks
+                if constexpr (FMT == kNV12 || FMT == kP016) {
+                    int Ys[2][4], cbv[2], crv[2];
+                    if constexpr (FMT == kP016) {
+                        const uint2 a = __ldg(reinterpret_cast<const uint2*>(f.p0 + (size_t)y * f.pitch + 2 * px0));
+                        const uint2 b = __ldg(reinterpret_cast<const uint2*>(f.p0 + (size_t)(y + 1) * f.pitch + 2 * px0));
+                        const uint2 c = __ldg(reinterpret_cast<const uint2*>(f.p1 + (size_t)(y >> 1) * f.pitch + 2 * px0));
+                        Ys[0][0] = a.x & 0xffff; Ys[0][1] = a.x >> 16; Ys[0][2] = a.y & 0xffff; Ys[0][3] = a.y >> 16;
+                        Ys[1][0] = b.x & 0xffff; Ys[1][1] = b.x >> 16; Ys[1][2] = b.y & 0xffff; Ys[1][3] = b.y >> 16;
+                        cbv[0] = c.x & 0xffff; crv[0] = c.x >> 16; cbv[1] = c.y & 0xffff; crv[1] = c.y >> 16;
+                    } else {
+                        const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(f.p0 + (size_t)y * f.pitch + px0));
+                        const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(f.p0 + (size_t)(y + 1) * f.pitch + px0));
+                        const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(f.p1 + (size_t)(y >> 1) * f.pitch + px0));
+#pragma unroll
+                        for (int i = 0; i < 4; i++) { Ys[0][i] = (a >> (8 * i)) & 0xff; Ys[1][i] = (b >> (8 * i)) & 0xff; }
+                        cbv[0] = c & 0xff; crv[0] = (c >> 8) & 0xff; cbv[1] = (c >> 16) & 0xff; crv[1] = c >> 24;
+                    }
+#pragma unroll
+                    for (int bx = 0; bx < 2; bx++) {
+                        const YuvChroma ch = yuv_chroma<FMT>(cbv[bx], crv[bx], g.coef, g.eotf_lut, g.lut_n, g.lut_shift);
+#pragma unroll
+                        for (int j = 0; j < 2; j++)
+#pragma unroll
+                            for (int i = 0; i < 2; i++) {
+                                Rgb& o = lin[j][2 * bx + i];
+                                yuv_px(Ys[j][2 * bx + i], ch, g.coef, T, g.lut_shift, o.r, o.g, o.b);
+                            }
+                    }
+                }
+            } else {
+                // ---- generic path: per-pixel loads at clamped coordinates (edge patches, packed RGB formats)
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        Rgb& o = lin[j][i];
+                        load_px<FMT>(f, min(px0 + i, W0 - 1), min(y + j, H0 - 1), g.coef, T, g.eotf_lut, g.lut_n, g.lut_shift, o.r, o.g, o.b);
+                    }
+            }
+            // ---- scale 0: XYB rows out
+            {
+                const ScaleDesc& sd = g.sc[0];
+                const size_t plane = plane_of(0);
+                float* gd = base_of(0);
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    float X[4], Yv[4], B[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) xyb_of<FMT>(lin[j][i].r, lin[j][i].g, lin[j][i].b, S, X[i], Yv[i], B[i]);
+                    const int yy = y + j;
+                    if (yy < H0) {
+                        float* q = gd + (size_t)yy * sd.pitch + px0;
+                        if (px0 + 4 <= W0) {
+                            *reinterpret_cast<float4*>(q) = make_float4(X[0], X[1], X[2], X[3]);
+                            *reinterpret_cast<float4*>(q + plane) = make_float4(Yv[0], Yv[1], Yv[2], Yv[3]);
+                            *reinterpret_cast<float4*>(q + 2 * plane) = make_float4(B[0], B[1], B[2], B[3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; i++)
+                                if (px0 + i < W0) { q[i] = X[i]; q[plane + i] = Yv[i]; q[2 * plane + i] = B[i]; }
+                        }
+                    }
+                }
+            }
+            // ---- level 1 (clamped loads make the out-of-frame level-0 neighbours equal to the clamped ones already)
+#pragma unroll
+            for (int bx = 0; bx < 2; bx++)
+                l1[br][bx] = box_clamped(lin[0][2 * bx], lin[0][2 * bx + 1], lin[1][2 * bx], lin[1][2 * bx + 1], true, true);
+        }
+        Rgb l2 = Rgb{0.f, 0.f, 0.f};
+        if (ns > 1) {
+            const ScaleDesc& sd = g.sc[1];
+            const size_t plane = plane_of(1);
+            float* gd = base_of(1);
+            const int ox = px0 >> 1, oy = py0 >> 1;
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                float X[2], Yv[2], B[2];
+#pragma unroll
+                for (int i = 0; i < 2; i++) xyb_of<FMT>(l1[j][i].r, l1[j][i].g, l1[j][i].b, S, X[i], Yv[i], B[i]);
+                if (oy + j < sd.h) {
+                    float* q = gd + (size_t)(oy + j) * sd.pitch + ox;
+                    if (ox + 2 <= sd.w) {
+                        *reinterpret_cast<float2*>(q) = make_float2(X[0], X[1]);
+                        *reinterpret_cast<float2*>(q + plane) = make_float2(Yv[0], Yv[1]);
+                        *reinterpret_cast<float2*>(q + 2 * plane) = make_float2(B[0], B[1]);
+                    } else if (ox < sd.w) {
+                        q[0] = X[0]; q[plane] = Yv[0]; q[2 * plane] = B[0];
+                    }
+                }
+            }
+            // level 2: one pixel per patch
+            l2 = box_clamped(l1[0][0], l1[0][1], l1[1][0], l1[1][1], ox + 1 < sd.w, oy + 1 < sd.h);
+        }
+        if (ns > 2) {
+            const ScaleDesc& sd = g.sc[2];
+            const int ox = px0 >> 2, oy = py0 >> 2;
+            float X, Yv, B;
+            xyb_of<FMT>(l2.r, l2.g, l2.b, S, X, Yv, B);
+            if (ox < sd.w && oy < sd.h) {
+                const size_t plane = plane_of(2);
+                float* q = base_of(2) + (size_t)oy * sd.pitch + ox;
+                q[0] = X; q[plane] = Yv; q[2 * plane] = B;
+            }
+            // level 3: lanes with even (pxi, pyi) own a pixel; neighbours by shuffle
+            const Rgb b = shfl_rgb_xor(l2, 1), c = shfl_rgb_xor(l2, 8), d = shfl_rgb_xor(l2, 9);
+            const Rgb v3 = box_clamped(l2, b, c, d, ox + 1 < sd.w, oy + 1 < sd.h);
+            if (pass == 0) l3a = v3; else l3b = v3;
+        }
+        if (ns > 3) {
+            // level 4: lanes with pxi % 4 == 0, pyi == 0
+            const ScaleDesc& sd = g.sc[3];
+            const int ox = px0 >> 3, oy = py0 >> 3;
+            const Rgb v = pass == 0 ? l3a : l3b;
+            const Rgb b = shfl_rgb_xor(v, 2), c = shfl_rgb_xor(v, 16), d = shfl_rgb_xor(v, 18);
+            const Rgb v4 = box_clamped(v, b, c, d, ox + 1 < sd.w, oy + 1 < sd.h);
+            if (pass == 0) l4a = v4; else l4b = v4;
+        }
+    }
+
+    if (ns <= 3) return;
+    // ---- levels 3, 4, 5 of the region: 16 + 4 + 1 pixels, one XYB evaluation.
+    //   lanes 0-7 and 16-23 (pyi 0 / 2): level 3; even pxi = pass 0's pixel of that lane, odd pxi = pass 1's of lane - 1
+    //   lanes 8-11: level 4 (pass = bit 1, source lane = 4 * bit 0);  lane 12: level 5
+    Rgb v = Rgb{0.f, 0.f, 0.f};
+    int s = -1, ox = 0, oy = 0;
+    {
+        const Rgb up1 = shfl_rgb(l3b, lane - 1 < 0 ? 0 : lane - 1);
+        if ((pyi & 1) == 0) {
+            const int pass = pxi & 1;
+            v = pass ? up1 : l3a;
+            s = 3;
+            ox = (X0 >> 3) + (pxi >> 1);
+            oy = (Y0 >> 3) + (pyi >> 1) + 2 * pass;
+        }
+        const int src4 = 4 * (lane & 1);
+        const Rgb a0 = shfl_rgb(l4a, src4), a1 = shfl_rgb(l4b, src4);
+        if (lane >= 8 && lane < 12) {
+            const int pass = (lane >> 1) & 1;
+            v = pass ? a1 : a0;
+            s = 4;
+            ox = (X0 >> 4) + (lane & 1);
+            oy = (Y0 >> 4) + pass;
+        }
+        if (ns > 5) {
+            // level 5 from the four level-4 pixels: (0,0) pass 0 lane 0, (1,0) pass 0 lane 4, (0,1) pass 1 lane 0, (1,1) pass 1 lane 4
+            const ScaleDesc& sd = g.sc[4];
+            const Rgb p00 = shfl_rgb(l4a, 0), p10 = shfl_rgb(l4a, 4), p01 = shfl_rgb(l4b, 0), p11 = shfl_rgb(l4b, 4);
+            if (lane == 12) {
+                const int x4 = X0 >> 4, y4 = Y0 >> 4;
+                v = box_clamped(p00, p10, p01, p11, x4 + 1 < sd.w, y4 + 1 < sd.h);
+                s = 5;
+                ox = X0 >> 5;
+                oy = Y0 >> 5;
+            }
+        }
+    }
+    float X, Yv, B;
+    xyb_of<FMT>(v.r, v.g, v.b, S, X, Yv, B);
+    if (s >= 3 && s < ns) {
+        const ScaleDesc& sd = g.sc[s];
+        if (ox < sd.w && oy < sd.h) {
+            const size_t plane = plane_of(s);
+            float* q = base_of(s) + (size_t)oy * sd.pitch + ox;
+            q[0] = X; q[plane] = Yv; q[2 * plane] = B;
+        }
+    }
+}
+
+// grid: (ceil(regions_x / (8 * kF2RegionsPerWarp)), regions_y, frames); warp w of a CTA owns kF2RegionsPerWarp regions along x
+template <int FMT>
+__global__ void __launch_bounds__(kF2Threads, 2) k_frontend2(const __grid_constant__ Geo g, const __grid_constant__ BatchIn in,
+                                                             float* __restrict__ xyb_base)
+{
+    __shared__ exact_math::PowfTables T;
+    __shared__ exact_math::CbrtScale S;
+    {
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(&kPowfTablesInit);
+        uint64_t* dst = reinterpret_cast<uint64_t*>(&T);
+        for (int i = threadIdx.x; i < (int)(sizeof(exact_math::PowfTables) / 8); i += kF2Threads) dst[i] = src[i];
+        S.tab[threadIdx.x] = exact_math::cbrt_scale_entry(threadIdx.x);
+    }
+    __syncthreads();
+    const int frame = blockIdx.z, warp = threadIdx.x >> 5;
+    const int rx_n = (g.sc[0].w + kF2Region - 1) / kF2Region;
+    float* xyb_slot = xyb_base + (size_t)frame * g.xyb_stride;
+#pragma unroll 1
+    for (int i = 0; i < kF2RegionsPerWarp; i++) {
+        const int rx = (blockIdx.x * (kF2Threads / 32) + warp) * kF2RegionsPerWarp + i;
+        if (rx >= rx_n) break;
+#pragma unroll 1
+        for (int img = 0; img < 2; img++)
+            frontend_region<FMT>(g, img ? in.dis[frame] : in.ref[frame], xyb_slot, img, rx * kF2Region, blockIdx.y * kF2Region, T, S);
+    }
+}
+
 // ---- TMA / mbarrier plumbing (PTX; sm_90+ instructions, SASS: UTMALDG / SYNCS) -------------------
 // Tensor maps of one batch slot, per scale.  All are 4-D {x, y, plane, frame} views of [frame][plane][h][pitch] f32.
 struct alignas(64) TmaMaps {

@@ -394,6 +394,9 @@ __device__ __forceinline__ YuvChroma yuv_chroma(int cbi, int cri, const YuvCoef&
     return c;
 }
 
+// out-of-line copy of the transfer function for the rarely taken arithmetic R / B path (keeps the hot loop small)
+__device__ __noinline__ float bt709_eotf_cold(float v, const exact_math::PowfTables* T) { return clamp01(bt709_eotf(v, *T)); }
+
 // one luma sample + its block's chroma -> linear RGB (same expressions as load_px)
 __device__ __forceinline__ void yuv_px(int Y, const YuvChroma& c, const YuvCoef& k, const exact_math::PowfTables& T, int lut_shift,
                                        float& r, float& g, float& b)
@@ -405,8 +408,8 @@ __device__ __forceinline__ void yuv_px(int Y, const YuvChroma& c, const YuvCoef&
         r = __ldg(c.rrow + yc);
         b = __ldg(c.brow + yc);
     } else {
-        r = clamp01(bt709_eotf(luma + c.r_, T));
-        b = clamp01(bt709_eotf(luma + c.b_, T));
+        r = bt709_eotf_cold(luma + c.r_, &T);
+        b = bt709_eotf_cold(luma + c.b_, &T);
     }
 }
 
@@ -456,6 +459,9 @@ __device__ __forceinline__ Rgb shfl_rgb(Rgb v, int src)
     return Rgb{__shfl_sync(0xffffffffu, v.r, src), __shfl_sync(0xffffffffu, v.g, src), __shfl_sync(0xffffffffu, v.b, src)};
 }
 
+#ifndef KF2_MINB
+#define KF2_MINB 4
+#endif
 constexpr int kF2Region = 32;
 constexpr int kF2Threads = 256;
 constexpr int kF2RegionsPerWarp = 2;    // consecutive regions along x
@@ -473,112 +479,98 @@ __device__ __forceinline__ void frontend_region(const Geo& g, const FrameIn& f, 
     auto plane_of = [&](int s) { return (size_t)g.sc[s].h * g.sc[s].pitch; };
     auto base_of = [&](int s) { return ximg + g.sc[s].xyb_off + (size_t)img * 3 * plane_of(s); };
     const bool vec_ok = (FMT == kNV12 || FMT == kP016) &&
-                        ((((uintptr_t)f.p0 | (uintptr_t)f.p1 | (uintptr_t)f.pitch) & 7u) == 0);
+                        ((((uintptr_t)f.p0 | (uintptr_t)f.p1 | (uintptr_t)f.pitch) & 3u) == 0);
     Rgb l3a = Rgb{0.f, 0.f, 0.f}, l3b = l3a, l4a = l3a, l4b = l3a;   // level 3 / 4 pixels of pass 0 / 1
+    float* const gd0 = base_of(0);
+    const size_t plane0 = plane_of(0);
+    const int pitch0 = g.sc[0].pitch;
 
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
         const int px0 = X0 + 4 * pxi, py0 = Y0 + 4 * (pyi + 4 * pass);
-        Rgb l1[2][2];
-#pragma unroll
-        for (int br = 0; br < 2; br++) {
-            const int y = py0 + 2 * br;
-            Rgb lin[2][4];
-            if (px0 + 4 <= W0 && y + 2 <= H0 && vec_ok) {
-                // ---- interior YUV patch row pair: vector loads, chroma shared by the 2x2 blocks
-                if constexpr (FMT == kNV12 || FMT == kP016) {
-                    int Ys[2][4], cbv[2], crv[2];
+        Rgb qa = Rgb{0.f, 0.f, 0.f}, qb = qa, qc = qa, l2 = qa;
+        // the patch is walked as four 2x2 blocks (one copy of the colour / XYB code, 4 pixels = 12 cube roots in flight)
+#pragma unroll 1
+        for (int blk = 0; blk < 4; blk++) {
+            const int x = px0 + 2 * (blk & 1), y = py0 + (blk & 2);
+            Rgb lin[2][2];
+            bool done = false;
+            if constexpr (FMT == kNV12 || FMT == kP016) {
+                if (vec_ok && x + 2 <= W0 && y + 2 <= H0) {
+                    // interior block: two luma samples per row in one load, one chroma pair for all four pixels
+                    int Y00, Y01, Y10, Y11, cbi, cri;
                     if constexpr (FMT == kP016) {
-                        const uint2 a = __ldg(reinterpret_cast<const uint2*>(f.p0 + (size_t)y * f.pitch + 2 * px0));
-                        const uint2 b = __ldg(reinterpret_cast<const uint2*>(f.p0 + (size_t)(y + 1) * f.pitch + 2 * px0));
-                        const uint2 c = __ldg(reinterpret_cast<const uint2*>(f.p1 + (size_t)(y >> 1) * f.pitch + 2 * px0));
-                        Ys[0][0] = a.x & 0xffff; Ys[0][1] = a.x >> 16; Ys[0][2] = a.y & 0xffff; Ys[0][3] = a.y >> 16;
-                        Ys[1][0] = b.x & 0xffff; Ys[1][1] = b.x >> 16; Ys[1][2] = b.y & 0xffff; Ys[1][3] = b.y >> 16;
-                        cbv[0] = c.x & 0xffff; crv[0] = c.x >> 16; cbv[1] = c.y & 0xffff; crv[1] = c.y >> 16;
+                        const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(f.p0 + (size_t)y * f.pitch + 2 * x));
+                        const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(f.p0 + (size_t)(y + 1) * f.pitch + 2 * x));
+                        const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(f.p1 + (size_t)(y >> 1) * f.pitch + 2 * x));
+                        Y00 = a & 0xffff; Y01 = a >> 16; Y10 = b & 0xffff; Y11 = b >> 16; cbi = c & 0xffff; cri = c >> 16;
                     } else {
-                        const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(f.p0 + (size_t)y * f.pitch + px0));
-                        const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(f.p0 + (size_t)(y + 1) * f.pitch + px0));
-                        const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(f.p1 + (size_t)(y >> 1) * f.pitch + px0));
-#pragma unroll
-                        for (int i = 0; i < 4; i++) { Ys[0][i] = (a >> (8 * i)) & 0xff; Ys[1][i] = (b >> (8 * i)) & 0xff; }
-                        cbv[0] = c & 0xff; crv[0] = (c >> 8) & 0xff; cbv[1] = (c >> 16) & 0xff; crv[1] = c >> 24;
+                        const uint32_t a = __ldg(reinterpret_cast<const uint16_t*>(f.p0 + (size_t)y * f.pitch + x));
+                        const uint32_t b = __ldg(reinterpret_cast<const uint16_t*>(f.p0 + (size_t)(y + 1) * f.pitch + x));
+                        const uint32_t c = __ldg(reinterpret_cast<const uint16_t*>(f.p1 + (size_t)(y >> 1) * f.pitch + x));
+                        Y00 = a & 0xff; Y01 = a >> 8; Y10 = b & 0xff; Y11 = b >> 8; cbi = c & 0xff; cri = c >> 8;
                     }
-#pragma unroll
-                    for (int bx = 0; bx < 2; bx++) {
-                        const YuvChroma ch = yuv_chroma<FMT>(cbv[bx], crv[bx], g.coef, g.eotf_lut, g.lut_n, g.lut_shift);
-#pragma unroll
-                        for (int j = 0; j < 2; j++)
-#pragma unroll
-                            for (int i = 0; i < 2; i++) {
-                                Rgb& o = lin[j][2 * bx + i];
-                                yuv_px(Ys[j][2 * bx + i], ch, g.coef, T, g.lut_shift, o.r, o.g, o.b);
-                            }
-                    }
+                    const YuvChroma ch = yuv_chroma<FMT>(cbi, cri, g.coef, g.eotf_lut, g.lut_n, g.lut_shift);
+                    yuv_px(Y00, ch, g.coef, T, g.lut_shift, lin[0][0].r, lin[0][0].g, lin[0][0].b);
+                    yuv_px(Y01, ch, g.coef, T, g.lut_shift, lin[0][1].r, lin[0][1].g, lin[0][1].b);
+                    yuv_px(Y10, ch, g.coef, T, g.lut_shift, lin[1][0].r, lin[1][0].g, lin[1][0].b);
+                    yuv_px(Y11, ch, g.coef, T, g.lut_shift, lin[1][1].r, lin[1][1].g, lin[1][1].b);
+                    done = true;
                 }
-            } else {
-                // ---- generic path: per-pixel loads at clamped coordinates (edge patches, packed RGB formats)
+            }
+            if (!done) {
+                // generic path: per-pixel loads at clamped coordinates (edge blocks, packed RGB formats); rolled for the
+                // YUV formats, where it only serves the frame edges
+#pragma unroll(FMT == kNV12 || FMT == kP016 ? 1 : 4)
+                for (int p = 0; p < 4; p++) {
+                    Rgb o;
+                    load_px<FMT>(f, min(x + (p & 1), W0 - 1), min(y + (p >> 1), H0 - 1), g.coef, T, g.eotf_lut, g.lut_n, g.lut_shift, o.r,
+                                 o.g, o.b);
+                    if (p == 0) lin[0][0] = o;
+                    else if (p == 1) lin[0][1] = o;
+                    else if (p == 2) lin[1][0] = o;
+                    else lin[1][1] = o;
+                }
+            }
+            // ---- scale 0: XYB of the four pixels
+            {
+                float X[2][2], Yv[2][2], B[2][2];
 #pragma unroll
                 for (int j = 0; j < 2; j++)
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        Rgb& o = lin[j][i];
-                        load_px<FMT>(f, min(px0 + i, W0 - 1), min(y + j, H0 - 1), g.coef, T, g.eotf_lut, g.lut_n, g.lut_shift, o.r, o.g, o.b);
-                    }
-            }
-            // ---- scale 0: XYB rows out
-            {
-                const ScaleDesc& sd = g.sc[0];
-                const size_t plane = plane_of(0);
-                float* gd = base_of(0);
+                    for (int i = 0; i < 2; i++) xyb_of<FMT>(lin[j][i].r, lin[j][i].g, lin[j][i].b, S, X[j][i], Yv[j][i], B[j][i]);
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
-                    float X[4], Yv[4], B[4];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) xyb_of<FMT>(lin[j][i].r, lin[j][i].g, lin[j][i].b, S, X[i], Yv[i], B[i]);
-                    const int yy = y + j;
-                    if (yy < H0) {
-                        float* q = gd + (size_t)yy * sd.pitch + px0;
-                        if (px0 + 4 <= W0) {
-                            *reinterpret_cast<float4*>(q) = make_float4(X[0], X[1], X[2], X[3]);
-                            *reinterpret_cast<float4*>(q + plane) = make_float4(Yv[0], Yv[1], Yv[2], Yv[3]);
-                            *reinterpret_cast<float4*>(q + 2 * plane) = make_float4(B[0], B[1], B[2], B[3]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 4; i++)
-                                if (px0 + i < W0) { q[i] = X[i]; q[plane + i] = Yv[i]; q[2 * plane + i] = B[i]; }
+                    if (y + j < H0) {
+                        float* q = gd0 + (size_t)(y + j) * pitch0 + x;
+                        if (x + 2 <= W0) {
+                            *reinterpret_cast<float2*>(q) = make_float2(X[j][0], X[j][1]);
+                            *reinterpret_cast<float2*>(q + plane0) = make_float2(Yv[j][0], Yv[j][1]);
+                            *reinterpret_cast<float2*>(q + 2 * plane0) = make_float2(B[j][0], B[j][1]);
+                        } else if (x < W0) {
+                            q[0] = X[j][0]; q[plane0] = Yv[j][0]; q[2 * plane0] = B[j][0];
                         }
                     }
                 }
             }
             // ---- level 1 (clamped loads make the out-of-frame level-0 neighbours equal to the clamped ones already)
-#pragma unroll
-            for (int bx = 0; bx < 2; bx++)
-                l1[br][bx] = box_clamped(lin[0][2 * bx], lin[0][2 * bx + 1], lin[1][2 * bx], lin[1][2 * bx + 1], true, true);
-        }
-        Rgb l2 = Rgb{0.f, 0.f, 0.f};
-        if (ns > 1) {
-            const ScaleDesc& sd = g.sc[1];
-            const size_t plane = plane_of(1);
-            float* gd = base_of(1);
-            const int ox = px0 >> 1, oy = py0 >> 1;
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                float X[2], Yv[2], B[2];
-#pragma unroll
-                for (int i = 0; i < 2; i++) xyb_of<FMT>(l1[j][i].r, l1[j][i].g, l1[j][i].b, S, X[i], Yv[i], B[i]);
-                if (oy + j < sd.h) {
-                    float* q = gd + (size_t)(oy + j) * sd.pitch + ox;
-                    if (ox + 2 <= sd.w) {
-                        *reinterpret_cast<float2*>(q) = make_float2(X[0], X[1]);
-                        *reinterpret_cast<float2*>(q + plane) = make_float2(Yv[0], Yv[1]);
-                        *reinterpret_cast<float2*>(q + 2 * plane) = make_float2(B[0], B[1]);
-                    } else if (ox < sd.w) {
-                        q[0] = X[0]; q[plane] = Yv[0]; q[2 * plane] = B[0];
-                    }
+            const Rgb v1 = box_clamped(lin[0][0], lin[0][1], lin[1][0], lin[1][1], true, true);
+            if (ns > 1) {
+                const ScaleDesc& sd = g.sc[1];
+                const int ox = x >> 1, oy = y >> 1;
+                float X, Yv, B;
+                xyb_of<FMT>(v1.r, v1.g, v1.b, S, X, Yv, B);
+                if (ox < sd.w && oy < sd.h) {
+                    const size_t plane = plane_of(1);
+                    float* q = base_of(1) + (size_t)oy * sd.pitch + ox;
+                    q[0] = X; q[plane] = Yv; q[2 * plane] = B;
                 }
+                // level 2 = box of the four level-1 pixels of the patch, in block order (0,0),(1,0),(0,1),(1,1)
+                if (blk == 0) qa = v1;
+                else if (blk == 1) qb = v1;
+                else if (blk == 2) qc = v1;
+                else l2 = box_clamped(qa, qb, qc, v1, (px0 >> 1) + 1 < sd.w, (py0 >> 1) + 1 < sd.h);
             }
-            // level 2: one pixel per patch
-            l2 = box_clamped(l1[0][0], l1[0][1], l1[1][0], l1[1][1], ox + 1 < sd.w, oy + 1 < sd.h);
         }
         if (ns > 2) {
             const ScaleDesc& sd = g.sc[2];
@@ -657,7 +649,7 @@ __device__ __forceinline__ void frontend_region(const Geo& g, const FrameIn& f, 
 
 // grid: (ceil(regions_x / (8 * kF2RegionsPerWarp)), regions_y, frames); warp w of a CTA owns kF2RegionsPerWarp regions along x
 template <int FMT>
-__global__ void __launch_bounds__(kF2Threads, 2) k_frontend2(const __grid_constant__ Geo g, const __grid_constant__ BatchIn in,
+__global__ void __launch_bounds__(kF2Threads, KF2_MINB) k_frontend2(const __grid_constant__ Geo g, const __grid_constant__ BatchIn in,
                                                              float* __restrict__ xyb_base)
 {
     __shared__ exact_math::PowfTables T;
@@ -1343,13 +1335,14 @@ constexpr int kXHbPlane = kXR * kXHbPitch + 8;           // 824 floats
 constexpr int kXHbFloats = 15 * kXHbPlane;
 constexpr uint32_t kXHbBytes = kXHbFloats * 4;           // 49440
 constexpr int kXHThreads = 96, kXVThreads = 96;
-constexpr int kXThreads = kXHThreads + kXVThreads + 32;  // + P warp
+constexpr int kXThreads = kXHThreads + kXVThreads + 64;  // + the two helper warps
 constexpr int kXHsF2 = 6 * kXHThreads;                   // hand-off record: [6 state words][96 H threads] f2
 constexpr uint32_t kXHsBytes = kXHsF2 * 8;               // 4608
 constexpr uint32_t kXOffIn = 0;
 constexpr uint32_t kXOffHb = kXOffIn + 3 * kXInBytes;
-constexpr uint32_t kXOffHs = kXOffHb + 3 * kXHbBytes;
-constexpr uint32_t kXOffOnes = kXOffHs + 2 * kXHsBytes;  // one row of 76 ones (the second factor of the mu planes)
+constexpr uint32_t kXOffHsIn = kXOffHb + 3 * kXHbBytes;  // state arriving from the left strip (1 record)
+constexpr uint32_t kXOffHsOut = kXOffHsIn + kXHsBytes;   // state leaving for the right strip (1 record)
+constexpr uint32_t kXOffOnes = kXOffHsOut + kXHsBytes;   // one row of 76 ones (the second factor of the mu planes)
 constexpr uint32_t kXOffBars = kXOffOnes + 320;
 constexpr size_t kXSmemBytes = kXOffBars + 16 * 8;
 static_assert(kXOffHb % 16 == 0 && kXHbBytes % 16 == 0 && kXInBytes % 128 == 0 && kXOffBars % 8 == 0, "k_hv smem layout");
@@ -1373,10 +1366,10 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity)
         if (it > 400000u) __trap();
     }
 }
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p)
 {
     uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
@@ -1412,7 +1405,25 @@ struct HvArgs {
     int nframes;
 };
 
-__global__ void __launch_bounds__(kXThreads, 1) k_hv(const __grid_constant__ Geo g, const __grid_constant__ TmaMapsX maps,
+// the four column groups (16 tile columns) of one H-scan iteration: products of both rows, 16 filter steps, stores
+struct HGroupLoad {
+    float4 xa, xb, ya, yb;
+};
+__device__ __forceinline__ HGroupLoad h_load(uint32_t axA, uint32_t axB, uint32_t ayA, uint32_t ayB, uint32_t off)
+{
+    HGroupLoad L;
+    L.xa = lds128(axA + off); L.xb = lds128(axB + off); L.ya = lds128(ayA + off); L.yb = lds128(ayB + off);
+    return L;
+}
+__device__ __forceinline__ void h_products(const HGroupLoad& L, f2 (&w)[16], int at)
+{
+    w[(at + 0) & 15] = f2_pack(L.xa.x * L.ya.x, L.xb.x * L.yb.x);
+    w[(at + 1) & 15] = f2_pack(L.xa.y * L.ya.y, L.xb.y * L.yb.y);
+    w[(at + 2) & 15] = f2_pack(L.xa.z * L.ya.z, L.xb.z * L.yb.z);
+    w[(at + 3) & 15] = f2_pack(L.xa.w * L.ya.w, L.xb.w * L.yb.w);
+}
+
+__global__ void __launch_bounds__(kXThreads, 2) k_hv(const __grid_constant__ Geo g, const __grid_constant__ TmaMapsX maps,
                                                      const HvArgs a)
 {
     extern __shared__ __align__(1024) char xs[];
@@ -1421,10 +1432,12 @@ __global__ void __launch_bounds__(kXThreads, 1) k_hv(const __grid_constant__ Geo
     uint64_t* bars = reinterpret_cast<uint64_t*>(xs + kXOffBars);
     uint64_t* in_full = bars;        // [3] TMA
     uint64_t* in_free = bars + 3;    // [3] 3 V warps
-    uint64_t* hs_full = bars + 6;    // [2] P
-    uint64_t* hs_free = bars + 8;    // [2] 3 H warps
-    uint64_t* hb_full = bars + 10;   // [3] 3 H warps
-    uint64_t* hb_free = bars + 13;   // [3] 3 V warps
+    uint64_t* hb_full = bars + 6;    // [3] 3 H warps
+    uint64_t* hb_free = bars + 9;    // [3] 3 V warps
+    uint64_t* hsi_full = bars + 12;  // P_in
+    uint64_t* hsi_free = bars + 13;  // 3 H warps
+    uint64_t* hso_full = bars + 14;  // 3 H warps
+    uint64_t* hso_free = bars + 15;  // P_out
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
@@ -1435,10 +1448,10 @@ __global__ void __launch_bounds__(kXThreads, 1) k_hv(const __grid_constant__ Geo
             mbar_init(&hb_full[i], 3);
             mbar_init(&hb_free[i], 3);
         }
-        for (int i = 0; i < 2; i++) {
-            mbar_init(&hs_full[i], 1);
-            mbar_init(&hs_free[i], 3);
-        }
+        mbar_init(hsi_full, 1);
+        mbar_init(hsi_free, 3);
+        mbar_init(hso_full, 3);
+        mbar_init(hso_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // tile slot 2 plays "the band above band 0": zeros (the vertical filter's zero padding); the ones row
@@ -1462,9 +1475,10 @@ __global__ void __launch_bounds__(kXThreads, 1) k_hv(const __grid_constant__ Geo
     const int W = sd.w, H = sd.h, nb = sd.nb;
     const int x0 = k * kXC;
     const size_t rec_base = (size_t)frame * g.total_recs + sd.rec0;   // + strip * nb + band
+    const bool last_strip = (k == sd.n_strips - 1);
 
     if (warp == 6) {
-        // ===== P: tile loads + hand-off fetch =====
+        // ===== P_in: tile loads + the state the left strip left behind =====
         const CUtensorMap* map = &maps.xyb_in[s];
         for (int j = 0; j < nb; j++) {
             const int si = j % 3;
@@ -1474,20 +1488,39 @@ __global__ void __launch_bounds__(kXThreads, 1) k_hv(const __grid_constant__ Geo
                 tma_load_4d(xs + kXOffIn + si * kXInBytes, map, &in_full[si], x0 - kXInLead, j * kXR, 0, frame);
             }
             if (k > 0) {
-                const int hi = j & 1;
-                if (j >= 2) mbar_wait_wd(&hs_free[hi], (uint32_t)((j / 2 - 1) & 1));
+                if (j >= 1) mbar_wait_wd(hsi_free, (uint32_t)((j - 1) & 1));
                 const size_t rec = rec_base + (size_t)(k - 1) * nb + j;
                 const uint32_t* fl = a.flags + rec;
-                for (uint32_t it = 0; ld_acquire_u32(fl) != a.epoch; it++) {
-                    __nanosleep(100);
+                for (uint32_t it = 0; ld_relaxed_u32(fl) != a.epoch; it++) {
+                    __nanosleep(64);
                     if (it > 40000000u) __trap();
                 }
+                __threadfence();   // acquire: the record was written before the flag
                 const float4* src = reinterpret_cast<const float4*>(a.hstate + rec * kXHsF2);
-                float4* dst = reinterpret_cast<float4*>(xs + kXOffHs + hi * kXHsBytes);
+                float4* dst = reinterpret_cast<float4*>(xs + kXOffHsIn);
 #pragma unroll
                 for (int i = 0; i < (int)(kXHsBytes / 16 / 32); i++) dst[i * 32 + lane] = __ldcg(src + i * 32 + lane);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&hs_full[hi]);
+                if (lane == 0) mbar_arrive(hsi_full);
+            }
+        }
+        return;
+    }
+    if (warp == 7) {
+        // ===== P_out: publishes the state at the right edge of every band =====
+        if (last_strip) return;
+        for (int j = 0; j < nb; j++) {
+            mbar_wait_wd(hso_full, (uint32_t)(j & 1));
+            const size_t rec = rec_base + (size_t)k * nb + j;
+            float4* dst = reinterpret_cast<float4*>(a.hstate + rec * kXHsF2);
+            const float4* src = reinterpret_cast<const float4*>(xs + kXOffHsOut);
+#pragma unroll
+            for (int i = 0; i < (int)(kXHsBytes / 16 / 32); i++) __stcg(dst + i * 32 + lane, src[i * 32 + lane]);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(hso_free);
+                __threadfence();
+                st_release_u32(a.flags + rec, a.epoch);
             }
         }
         return;
@@ -1504,20 +1537,18 @@ __global__ void __launch_bounds__(kXThreads, 1) k_hv(const __grid_constant__ Geo
         const uint32_t ones = sbase + kXOffOnes;
         const uint32_t offo = (uint32_t)(((q * 3 + ch) * kXHbPlane + rp * kXHbPitch) * 4);
         const int hidx = warp * 32 + lane;
-        const bool last_strip = (k == sd.n_strips - 1);
         for (int j = 0; j < nb; j++) {
             const int si = j % 3;
             mbar_wait_wd(&in_full[si], (uint32_t)((j / 3) & 1));
             if (j >= 2) mbar_wait_wd(&hb_free[si], (uint32_t)(((j - 2) / 3) & 1));
             HState2 st;
             if (k > 0) {
-                const int hi = j & 1;
-                mbar_wait_wd(&hs_full[hi], (uint32_t)((j / 2) & 1));
-                const uint32_t hsb = sbase + kXOffHs + hi * kXHsBytes + (uint32_t)hidx * 8u;
+                mbar_wait_wd(hsi_full, (uint32_t)(j & 1));
+                const uint32_t hsb = sbase + kXOffHsIn + (uint32_t)hidx * 8u;
                 st.p1 = lds64(hsb); st.p3 = lds64(hsb + 96 * 8); st.p5 = lds64(hsb + 2 * 96 * 8);
                 st.pp1 = lds64(hsb + 3 * 96 * 8); st.pp3 = lds64(hsb + 4 * 96 * 8); st.pp5 = lds64(hsb + 5 * 96 * 8);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&hs_free[hi]);
+                if (lane == 0) mbar_arrive(hsi_free);
             } else {
                 const f2 z = f2_splat(0.0f);
                 st = HState2{z, z, z, z, z, z};
@@ -1525,34 +1556,42 @@ __global__ void __launch_bounds__(kXThreads, 1) k_hv(const __grid_constant__ Geo
             const uint32_t inb = sbase + kXOffIn + si * kXInBytes;
             const uint32_t axA = inb + offxA, axB = inb + offxB;
             const uint32_t ayA = py < 0 ? ones : inb + offyA, ayB = py < 0 ? ones : inb + offyB;
-            const uint32_t ao = sbase + kXOffHb + si * kXHbBytes + offo;
-            // products of tile columns 4g .. 4g+3 for both rows
-            f2 pr[kXInW];
-#pragma unroll
-            for (int gI = 0; gI < kXInW / 4; gI++) {
-                const float4 xa = lds128(axA + gI * 16), xb = lds128(axB + gI * 16);
-                const float4 ya = lds128(ayA + gI * 16), yb = lds128(ayB + gI * 16);
-                pr[4 * gI + 0] = f2_pack(xa.x * ya.x, xb.x * yb.x);
-                pr[4 * gI + 1] = f2_pack(xa.y * ya.y, xb.y * yb.y);
-                pr[4 * gI + 2] = f2_pack(xa.z * ya.z, xb.z * yb.z);
-                pr[4 * gI + 3] = f2_pack(xa.w * ya.w, xb.w * yb.w);
-                if (gI == 2 && k == 0) {
+            uint32_t ao = sbase + kXOffHb + si * kXHbBytes + offo;
+            // w[c & 15] = product of tile column c (both rows).  Tile column c is x[n + 4] of output column n = c - 12;
+            // the left tap x[n - 6] is tile column c - 10.
+            f2 w[16];
+            {
+                const HGroupLoad L0 = h_load(axA, axB, ayA, ayB, 0), L1 = h_load(axA, axB, ayA, ayB, 16),
+                                 L2 = h_load(axA, axB, ayA, ayB, 32);
+                h_products(L0, w, 0);
+                h_products(L1, w, 4);
+                h_products(L2, w, 8);
+                if (k == 0) {
                     // the recursion starts at n = -4 (cpu.rs:976): four warm-up steps on x[0..3], no output
 #pragma unroll
-                    for (int e = 0; e < 4; e++) (void)hstep2(st, f2_splat(0.0f), pr[8 + e]);
+                    for (int e = 0; e < 4; e++) (void)hstep2(st, f2_splat(0.0f), w[8 + e]);
                 }
-                if (gI >= 3) {
-                    // tile column c = 4 gI + e is x[n + 4] of output column n = c - 12; the left tap x[n - 6] is c - 10
+            }
+            HGroupLoad nxt = h_load(axA, axB, ayA, ayB, 48);
+#pragma unroll 1
+            for (int it = 0; it < 4; it++) {
+#pragma unroll
+                for (int gg = 0; gg < 4; gg++) {
+                    const HGroupLoad cur = nxt;
+                    // prefetch the next group's operands before this group's 4 steps (the last one re-reads in range)
+                    const int gnext = 4 * it + gg + 4;   // tile group index of the next load (3 .. 18)
+                    nxt = h_load(axA, axB, ayA, ayB, (uint32_t)(gnext < 19 ? gnext : 18) * 16u);
+                    h_products(cur, w, 12 + 4 * gg);
                     float oa[4], ob[4];
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
-                        const f2 o = hstep2(st, pr[4 * gI + e - 10], pr[4 * gI + e]);
+                        const f2 o = hstep2(st, w[(4 * gg + e + 2) & 15], w[(4 * gg + e + 12) & 15]);
                         f2_unpack(o, oa[e], ob[e]);
                     }
-                    const uint32_t oo = ao + (uint32_t)(gI - 3) * 16u;
-                    sts128(oo, make_float4(oa[0], oa[1], oa[2], oa[3]));
-                    sts128(oo + 6 * kXHbPitch * 4, make_float4(ob[0], ob[1], ob[2], ob[3]));
+                    sts128(ao + (uint32_t)gg * 16u, make_float4(oa[0], oa[1], oa[2], oa[3]));
+                    sts128(ao + (uint32_t)gg * 16u + 6 * kXHbPitch * 4, make_float4(ob[0], ob[1], ob[2], ob[3]));
                 }
+                ao += 64;
             }
             if (last_strip && x0 + kXC > W) {
                 // columns past the right edge hold the filter's ring-out: the V pass must see zeros there
@@ -1560,30 +1599,27 @@ __global__ void __launch_bounds__(kXThreads, 1) k_hv(const __grid_constant__ Geo
                 for (int c = W - x0; c < kXC; c++) { t0[c] = 0.0f; t0[6 * kXHbPitch + c] = 0.0f; }
             }
             if (!last_strip) {
-                f2* rec = a.hstate + (rec_base + (size_t)k * nb + j) * kXHsF2 + hidx;
-                rec[0] = st.p1; rec[96] = st.p3; rec[2 * 96] = st.p5;
-                rec[3 * 96] = st.pp1; rec[4 * 96] = st.pp3; rec[5 * 96] = st.pp5;
-                asm volatile("bar.sync 1, %0;" ::"n"(kXHThreads) : "memory");
-                if (tid == 0) {
-                    __threadfence();
-                    st_release_u32(a.flags + rec_base + (size_t)k * nb + j, a.epoch);
-                }
+                if (j >= 1) mbar_wait_wd(hso_free, (uint32_t)((j - 1) & 1));
+                const uint32_t hso = sbase + kXOffHsOut + (uint32_t)hidx * 8u;
+                sts64(hso, st.p1); sts64(hso + 96 * 8, st.p3); sts64(hso + 2 * 96 * 8, st.p5);
+                sts64(hso + 3 * 96 * 8, st.pp1); sts64(hso + 4 * 96 * 8, st.pp3); sts64(hso + 5 * 96 * 8, st.pp5);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&hb_full[si]);
+            if (lane == 0) {
+                mbar_arrive(&hb_full[si]);
+                if (!last_strip) mbar_arrive(hso_full);
+            }
         }
         return;
     }
 
     // ===== V: warp = channel, lane = column pair =====
     const int c = warp - 3;
-    const bool vlast = (k == sd.n_strips - 1);
-    (void)vlast;
     const f2 zero2 = f2_splat(0.0f);
     VState2 stq[5];
 #pragma unroll
     for (int qi = 0; qi < 5; qi++) stq[qi] = VState2{zero2, zero2, zero2, zero2, zero2, zero2};
-    f2 tail_r[4] = {zero2, zero2, zero2, zero2}, tail_d[4] = {zero2, zero2, zero2, zero2};
+    f2 fifo_r[4] = {zero2, zero2, zero2, zero2}, fifo_d[4] = {zero2, zero2, zero2, zero2};  // XYB rows t-4 .. t-1
     double acc[6] = {0, 0, 0, 0, 0, 0};
     const uint32_t lane8 = (uint32_t)lane * 8u;
     for (int j = 0; j < nb; j++) {
@@ -1592,39 +1628,29 @@ __global__ void __launch_bounds__(kXThreads, 1) k_hv(const __grid_constant__ Geo
         mbar_wait_wd(&in_full[si], (uint32_t)((j / 3) & 1));
         const uint32_t cur = sbase + kXOffHb + si * kXHbBytes + lane8;
         const uint32_t prv = sbase + kXOffHb + sp * kXHbBytes + lane8;
-        const uint32_t inb = sbase + kXOffIn + si * kXInBytes + kXInLead * 4 + lane8;
+        const uint32_t inb = sbase + kXOffIn + si * kXInBytes + kXInLead * 4 + lane8 + (uint32_t)(c * kXInPlane * 4);
         f2 part[6] = {zero2, zero2, zero2, zero2, zero2, zero2};
+#pragma unroll 1
+        for (int i4 = 0; i4 < kXR; i4 += 4) {
 #pragma unroll
-        for (int i = 0; i < kXR; i++) {
-            const int t = j * kXR + i;
-            f2 o[5];
+            for (int r = 0; r < 4; r++) {
+                const int i = i4 + r, t = j * kXR + i;
+                // x[t] is row i of this band's tile; x[t - 10] is 10 rows up: in the previous band's tile for i < 10
+                const uint32_t a_t = cur + (uint32_t)(i * kXHbPitch * 4);
+                const uint32_t a_d = i < 10 ? prv + (uint32_t)((i + 2) * kXHbPitch * 4) : cur + (uint32_t)((i - 10) * kXHbPitch * 4);
+                f2 o[5];
 #pragma unroll
-            for (int qi = 0; qi < 5; qi++) {
-                const uint32_t pl = (uint32_t)((qi * 3 + c) * kXHbPlane * 4);
-                const f2 v = lds64(cur + pl + (uint32_t)(i * kXHbPitch * 4));
-                const f2 d = i < 10 ? lds64(prv + pl + (uint32_t)((i + 2) * kXHbPitch * 4))
-                                    : lds64(cur + pl + (uint32_t)((i - 10) * kXHbPitch * 4));
-                o[qi] = vstep2(stq[qi], d, v);
+                for (int qi = 0; qi < 5; qi++) {
+                    const uint32_t pl = (uint32_t)((qi * 3 + c) * kXHbPlane * 4);
+                    o[qi] = vstep2(stq[qi], lds64(a_d + pl), lds64(a_t + pl));
+                }
+                const f2 fr = fifo_r[r], fd = fifo_d[r];   // XYB of output row t - 4
+                fifo_r[r] = lds64(inb + (uint32_t)(i * kXInW * 4));
+                fifo_d[r] = lds64(inb + (uint32_t)((3 * kXInPlane + i * kXInW) * 4));
+                if (t >= 4 && t < H + 4) error_maps2(o, fr, fd, part);
             }
-            f2 fr, fd;
-            if (i < 4) {
-                fr = tail_r[i]; fd = tail_d[i];
-            } else {
-                fr = lds64(inb + (uint32_t)((c * kXInPlane + (i - 4) * kXInW) * 4));
-                fd = lds64(inb + (uint32_t)(((3 + c) * kXInPlane + (i - 4) * kXInW) * 4));
-            }
-            if (t >= 4 && t < H + 4) error_maps2(o, fr, fd, part);
-            if (i == kXR / 2 - 1) {
 #pragma unroll
-                for (int kk = 0; kk < 6; kk++) { acc[kk] += (double)f2_hsum(part[kk]); part[kk] = zero2; }
-            }
-        }
-#pragma unroll
-        for (int kk = 0; kk < 6; kk++) acc[kk] += (double)f2_hsum(part[kk]);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            tail_r[i] = lds64(inb + (uint32_t)((c * kXInPlane + (kXR - 4 + i) * kXInW) * 4));
-            tail_d[i] = lds64(inb + (uint32_t)(((3 + c) * kXInPlane + (kXR - 4 + i) * kXInW) * 4));
+            for (int kk = 0; kk < 6; kk++) { acc[kk] += (double)f2_hsum(part[kk]); part[kk] = zero2; }
         }
         __syncwarp();
         if (lane == 0) {

@@ -58,6 +58,7 @@ struct Slot {
     bool staged = false;              // holds host frames copied on the slot stream
     bool was_timed = false;
     cudaEvent_t ev_mid = nullptr;     // main stream -> slot stream hand-off
+    cudaEvent_t ev_f = nullptr;       // front-end of this slot done (two-stream pipeline)
     bool timed = false;
     void* last_stream = nullptr;
     bool have_dep = false;
@@ -77,6 +78,9 @@ struct ssimu2_handle {
     int pipeline = 0;                 // 0 = "hv": front-end, fused H+V kernel, finalize (default)
                                       // 1 = "fh": k_fused_fh + k_vpass (ring >= 2) / 2 = "split": four kernels
     cudaStream_t main_stream = nullptr;
+    cudaStream_t f_stream = nullptr, hv_stream = nullptr;  // pipeline "hv", ring >= 2: front-end stream / H+V stream
+    bool two_stream = false;
+    int num_sms = 0, f2p_ctas = 1;
     uint64_t next_ticket = 0;
     double* scores_ring_d = nullptr;  // [kResultCap] device score stream
     float* eotf_lut = nullptr;        // exact R / B transfer memo for YUV sources (see Geo)
@@ -282,23 +286,15 @@ static int launch_unfused(ssimu2_handle* h, Slot& sl)
     return 0;
 }
 
-// pipeline "hv": front-end, fused H+V kernel, finalize, back to back on the slot's stream
+// pipeline "hv": front-end, fused H+V kernel, finalize.
+//   ring == 1 : back to back on the slot's stream, with timing events between the kernels.
+//   ring >= 2 : two handle-wide streams.  The persistent front-end of batch k+1 (f_stream) runs WHILE the H+V kernel
+//               of batch k (hv_stream) does: both are sized to share every SM (see k_frontend2p).
 template <int FMT>
 static int launch_hv(ssimu2_handle* h, Slot& sl)
 {
     const Geo& g = h->geo;
     const uint32_t n = sl.count;
-    cudaStream_t st = sl.stream;
-    if (sl.timed) cudaEventRecord(sl.ev_k[0], st);
-    if (h->frontend2) {
-        const int rx = (g.sc[0].w + kF2Region - 1) / kF2Region, ry = (g.sc[0].h + kF2Region - 1) / kF2Region;
-        const int per_cta = (kF2Threads / 32) * kF2RegionsPerWarp;
-        k_frontend2<FMT><<<dim3((rx + per_cta - 1) / per_cta, ry, n), kF2Threads, 0, st>>>(g, sl.in, sl.xyb);
-    } else {
-        dim3 grid((g.sc[0].w + 63) / 64, (g.sc[0].h + 63) / 64, n);
-        k_frontend<FMT><<<grid, kFThreads, kFSmemTotal, st>>>(g, sl.in, sl.xyb);
-    }
-    if (sl.timed) cudaEventRecord(sl.ev_k[1], st);
     HvArgs a{};
     a.hstate = sl.hstate;
     a.flags = sl.hvflags;
@@ -306,8 +302,27 @@ static int launch_hv(ssimu2_handle* h, Slot& sl)
     a.partials = sl.partials;
     a.epoch = ++sl.epoch;
     a.nframes = (int)n;
-    k_hv<<<(unsigned)(g.items_v * n), kXThreads, kXSmemBytes, st>>>(g, sl.maps_x, a);
+    cudaStream_t fs = h->two_stream ? h->f_stream : sl.stream;
+    cudaStream_t st = h->two_stream ? h->hv_stream : sl.stream;
+    // timing marks: [0,1] around the front-end (on its stream), [2,3] around k_hv, [3,4] around finalize
+    if (sl.timed) cudaEventRecord(sl.ev_k[0], fs);
+    if (h->two_stream) {
+        k_frontend2p<FMT><<<h->num_sms * h->f2p_ctas, kF2PThreads, 0, fs>>>(g, sl.in, sl.xyb, a.ticket + 1, (int)n);
+    } else if (h->frontend2) {
+        const int rx = (g.sc[0].w + kF2Region - 1) / kF2Region, ry = (g.sc[0].h + kF2Region - 1) / kF2Region;
+        const int per_cta = (kF2Threads / 32) * kF2RegionsPerWarp;
+        k_frontend2<FMT><<<dim3((rx + per_cta - 1) / per_cta, ry, n), kF2Threads, 0, fs>>>(g, sl.in, sl.xyb);
+    } else {
+        dim3 grid((g.sc[0].w + 63) / 64, (g.sc[0].h + 63) / 64, n);
+        k_frontend<FMT><<<grid, kFThreads, kFSmemTotal, fs>>>(g, sl.in, sl.xyb);
+    }
+    if (sl.timed) cudaEventRecord(sl.ev_k[1], fs);
+    if (h->two_stream) {
+        CU_TRY(cudaEventRecord(sl.ev_f, fs));
+        CU_TRY(cudaStreamWaitEvent(st, sl.ev_f, 0));
+    }
     if (sl.timed) cudaEventRecord(sl.ev_k[2], st);
+    k_hv<<<(unsigned)(g.items_v * n), kXThreads, kXSmemBytes, st>>>(g, sl.maps_x, a);
     if (sl.timed) cudaEventRecord(sl.ev_k[3], st);
     k_finalize<<<n, 128, 0, st>>>(g, sl.partials, sl.norms_d, h->scores_ring_d, sl.first_ticket, kResultCap, sl.scores_d, a.ticket);
     if (sl.timed) cudaEventRecord(sl.ev_k[4], st);
@@ -415,16 +430,16 @@ static int launch_batch(ssimu2_handle* h, int si)
 {
     Slot& sl = h->slots[si];
     if (sl.count == 0 || sl.inflight || sl.awaiting) return 0;
-    cudaStream_t first = h->fuse ? h->main_stream : sl.stream;
+    cudaStream_t first = h->fuse ? h->main_stream : (h->two_stream ? h->f_stream : sl.stream);
     if (sl.have_dep && sl.last_stream != (void*)first) {
         // order the batch after everything the submitter enqueued so far on its stream
         CU_TRY(cudaEventRecord(sl.ev_in, (cudaStream_t)sl.last_stream));
         CU_TRY(cudaStreamWaitEvent(first, sl.ev_in, 0));
     }
-    if (h->fuse && sl.staged) {
-        // host frames were copied on the slot's stream: the front-end on the main stream must see them
+    if ((h->fuse || h->two_stream) && sl.staged) {
+        // host frames were copied on the slot's stream: the front-end on the shared stream must see them
         CU_TRY(cudaEventRecord(sl.ev_in, sl.stream));
-        CU_TRY(cudaStreamWaitEvent(h->main_stream, sl.ev_in, 0));
+        CU_TRY(cudaStreamWaitEvent(first, sl.ev_in, 0));
     }
     sl.have_dep = false;
     sl.staged = false;
@@ -455,7 +470,14 @@ static int harvest(ssimu2_handle* h, uint32_t si)
     }
     if (sl.was_timed) {
         for (int k = 0; k < 4; k++) {
-            cudaEventElapsedTime(&h->last_ms[k], sl.ev_k[k], sl.ev_k[k + 1]);
+            if (h->pipeline == 0) {
+                // front-end [0,1], k_hv [2,3], (no separate V pass), finalize [3,4]
+                static const int a[4] = {0, 2, 3, 3}, b[4] = {1, 3, 3, 4};
+                h->last_ms[k] = 0.f;
+                if (a[k] != b[k]) cudaEventElapsedTime(&h->last_ms[k], sl.ev_k[a[k]], sl.ev_k[b[k]]);
+            } else {
+                cudaEventElapsedTime(&h->last_ms[k], sl.ev_k[k], sl.ev_k[k + 1]);
+            }
             h->total_ms[k] += h->last_ms[k];
         }
         h->timed_batches++;
@@ -604,6 +626,15 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
     }
     CR(cudaFuncSetAttribute((const void*)k_hv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXSmemBytes));
     h->fuse = h->pipeline == 1 && h->ring >= 2 && getenv("SSIMU2_NO_FUSE") == nullptr;
+    h->two_stream = h->pipeline == 0 && h->ring >= 2 && getenv("SSIMU2_TWO_STREAM") != nullptr;  // experimental, off by default
+    h->num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("SSIMU2_F2P_CTAS")) h->f2p_ctas = atoi(e) > 0 ? atoi(e) : 1;
+    if (h->two_stream) {
+        int lo = 0, hi = 0;
+        CR(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CR(cudaStreamCreateWithPriority(&h->f_stream, cudaStreamNonBlocking, lo));
+        CR(cudaStreamCreateWithPriority(&h->hv_stream, cudaStreamNonBlocking, hi));  // k_hv CTAs are placed first
+    }
     CR(cudaStreamCreateWithFlags(&h->main_stream, cudaStreamNonBlocking));
     {
         static const void* ffn[6] = {(const void*)k_frontend<kNV12>,    (const void*)k_frontend<kP016>,
@@ -633,12 +664,13 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
         size_t xyb_b = (size_t)g.xyb_stride * h->batch * sizeof(float);
         size_t hb_b = h->pipeline == 0 ? 0 : (size_t)g.hb_stride * h->batch * sizeof(float);
         size_t hs_b = h->pipeline == 0 ? (size_t)g.total_recs * h->batch * kXHsBytes : 0;
-        size_t fl_b = h->pipeline == 0 ? ((size_t)g.total_recs * h->batch + 1) * sizeof(uint32_t) : 0;
+        size_t fl_b = h->pipeline == 0 ? ((size_t)g.total_recs * h->batch + 2) * sizeof(uint32_t) : 0;
         size_t part_b = (size_t)g.total_strips * 18 * h->batch * sizeof(double);
         CR(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         CR(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
         CR(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
         CR(cudaEventCreateWithFlags(&sl.ev_mid, cudaEventDisableTiming));
+        CR(cudaEventCreateWithFlags(&sl.ev_f, cudaEventDisableTiming));
         for (int k = 0; k < 5; k++) CR(cudaEventCreate(&sl.ev_k[k]));
         CR(cudaMalloc(&sl.xyb, xyb_b));
         if (hb_b) CR(cudaMalloc(&sl.hb, hb_b));
@@ -670,9 +702,12 @@ int ssimu2_destroy(ssimu2_t* h)
     if (!h) return SSIMU2_OK;
     cudaSetDevice(h->cfg.device);
     if (h->main_stream) cudaStreamSynchronize(h->main_stream);
+    if (h->f_stream) cudaStreamSynchronize(h->f_stream);
+    if (h->hv_stream) cudaStreamSynchronize(h->hv_stream);
     for (auto& sl : h->slots) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
         if (sl.ev_mid) cudaEventDestroy(sl.ev_mid);
+        if (sl.ev_f) cudaEventDestroy(sl.ev_f);
         if (sl.ev_in) cudaEventDestroy(sl.ev_in);
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
         for (int k = 0; k < 5; k++)
@@ -686,6 +721,8 @@ int ssimu2_destroy(ssimu2_t* h)
     cudaFree(h->scores_ring_d);
     cudaFree(h->eotf_lut);
     if (h->main_stream) cudaStreamDestroy(h->main_stream);
+    if (h->f_stream) cudaStreamDestroy(h->f_stream);
+    if (h->hv_stream) cudaStreamDestroy(h->hv_stream);
     delete h;
     return SSIMU2_OK;
 }
@@ -704,10 +741,11 @@ int ssimu2_submit(ssimu2_t* h, const ssimu2_frame* ref, const ssimu2_frame* dis,
     int r = prepare_cur(h);
     if (r) return r;
     Slot& sl = h->slots[h->cur];
-    if (sl.have_dep && sl.last_stream != stream && sl.last_stream != (void*)sl.stream) {
+    cudaStream_t first = h->fuse ? h->main_stream : (h->two_stream ? h->f_stream : sl.stream);
+    if (sl.have_dep && sl.last_stream != stream && sl.last_stream != (void*)first) {
         // submitter switched streams inside one batch: pin the dependency on the previous one now
         CU_TRY(cudaEventRecord(sl.ev_in, (cudaStream_t)sl.last_stream));
-        CU_TRY(cudaStreamWaitEvent(sl.stream, sl.ev_in, 0));
+        CU_TRY(cudaStreamWaitEvent(first, sl.ev_in, 0));
     }
     sl.last_stream = stream;
     sl.have_dep = true;

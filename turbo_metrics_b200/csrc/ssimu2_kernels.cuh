@@ -674,6 +674,42 @@ __global__ void __launch_bounds__(kF2Threads, KF2_MINB) k_frontend2(const __grid
     }
 }
 
+// Persistent form of the same front-end: one 512-thread CTA per SM, every warp pulls 32x32 regions from an atomic
+// counter.  It is sized (64 registers x 512 threads, 3 KB of shared memory) to share each SM with one k_hv CTA of the
+// PREVIOUS batch: the front-end is bound by the FP64 / conversion / integer pipes and the issue rate, k_hv by the
+// FP32 pipe, so the two kernels run side by side on two streams instead of one after the other.
+constexpr int kF2PThreads = 512;
+template <int FMT>
+__global__ void __launch_bounds__(kF2PThreads, 2) k_frontend2p(const __grid_constant__ Geo g, const __grid_constant__ BatchIn in,
+                                                               float* __restrict__ xyb_base, uint32_t* __restrict__ counter, int nframes)
+{
+    __shared__ exact_math::PowfTables T;
+    __shared__ exact_math::CbrtScale S;
+    {
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(&kPowfTablesInit);
+        uint64_t* dst = reinterpret_cast<uint64_t*>(&T);
+        for (int i = threadIdx.x; i < (int)(sizeof(exact_math::PowfTables) / 8); i += kF2PThreads) dst[i] = src[i];
+        if (threadIdx.x < 256) S.tab[threadIdx.x] = exact_math::cbrt_scale_entry(threadIdx.x);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int rx_n = (g.sc[0].w + kF2Region - 1) / kF2Region, ry_n = (g.sc[0].h + kF2Region - 1) / kF2Region;
+    const uint32_t per_frame = (uint32_t)(rx_n * ry_n), total = per_frame * (uint32_t)nframes;
+    for (;;) {
+        uint32_t id = 0;
+        if (lane == 0) id = atomicAdd(counter, 1u);
+        id = __shfl_sync(0xffffffffu, id, 0);
+        if (id >= total) break;
+        const int frame = (int)(id / per_frame);
+        const int rem = (int)(id - (uint32_t)frame * per_frame);
+        const int ry = rem / rx_n, rx = rem - ry * rx_n;
+        float* xyb_slot = xyb_base + (size_t)frame * g.xyb_stride;
+#pragma unroll 1
+        for (int img = 0; img < 2; img++)
+            frontend_region<FMT>(g, img ? in.dis[frame] : in.ref[frame], xyb_slot, img, rx * kF2Region, ry * kF2Region, T, S);
+    }
+}
+
 // ---- TMA / mbarrier plumbing (PTX; sm_90+ instructions, SASS: UTMALDG / SYNCS) -------------------
 // Tensor maps of one batch slot, per scale.  All are 4-D {x, y, plane, frame} views of [frame][plane][h][pitch] f32.
 struct alignas(64) TmaMaps {
@@ -1423,7 +1459,7 @@ __device__ __forceinline__ void h_products(const HGroupLoad& L, f2 (&w)[16], int
     w[(at + 3) & 15] = f2_pack(L.xa.w * L.ya.w, L.xb.w * L.yb.w);
 }
 
-__global__ void __launch_bounds__(kXThreads, 2) k_hv(const __grid_constant__ Geo g, const __grid_constant__ TmaMapsX maps,
+__global__ void __launch_bounds__(kXThreads, 1) k_hv(const __grid_constant__ Geo g, const __grid_constant__ TmaMapsX maps,
                                                      const HvArgs a)
 {
     extern __shared__ __align__(1024) char xs[];
@@ -1699,7 +1735,7 @@ __global__ void __launch_bounds__(128) k_finalize(const __grid_constant__ Geo g,
                                                   unsigned long long first_ticket, unsigned long long ring_cap,
                                                   double* __restrict__ scores_out, uint32_t* __restrict__ hv_ticket)
 {
-    if (hv_ticket != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *hv_ticket = 0u;  // k_hv's work counter, for the next batch
+    if (hv_ticket != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { hv_ticket[0] = 0u; hv_ticket[1] = 0u; }  // work counters of k_hv / k_frontend2p, for the next batch
     __shared__ double norms[108];
     const int frame = blockIdx.x, tid = threadIdx.x;
     if (tid < 108) norms[tid] = 0.0;

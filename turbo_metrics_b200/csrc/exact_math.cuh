@@ -129,6 +129,25 @@ EM_HD double ddiv_normal(double n, double d)
 #endif
 }
 
+// Same quotient with ONE Newton step on the reciprocal: y then carries ~2^-44 relative error, q = n*y likewise, and
+// Markstein's correction fma(r, y, q) with the exact residual r lands within 2^-88 of n/d before its single rounding --
+// the rounded result differs from n/d's correct rounding only if n/d lies that close to a rounding boundary, which for
+// a quotient of two doubles cannot happen.  Used by the hot cbrtf path; verified against libm by the same tests.
+EM_HD double ddiv_normal_fast(double n, double d)
+{
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    const double q = n * y;
+    const double r = fma(-d, q, n);
+    return fma(r, y, q);
+#else
+    return n / d;
+#endif
+}
+
 EM_HD float fdiv_normal(float n, float d)
 {
 #if defined(__CUDA_ARCH__)
@@ -181,8 +200,13 @@ EM_HD float cbrtf_glibc(float x, const Consts& K, const CbrtScale* S = nullptr)
         }
     }
     // frexpf: |x| = xm * 2^e, xm in [0.5, 1); the double of xm is built directly from the mantissa bits
+    // (on the device: one LOP3 + one exact F2F instead of assembling the double from the mantissa bits)
+#if defined(__CUDA_ARCH__)
+    const double xm = (double)u2f((ix & 0x007fffffu) | 0x3f000000u);
+#else
     const uint32_t m = ix & 0x007fffffu;
     const double xm = u2d(((uint64_t)(0x3fe00000u | (m >> 3)) << 32) | (uint64_t)(m << 29));
+#endif
     // u = 0.4926... + (0.6975... - 0.1915... * xm) * xm   (mulsd, subsd, mulsd, addsd; then cvtsd2ss)
     double t = K.cb2 * xm;
     t = K.cb1 - t;
@@ -193,12 +217,13 @@ EM_HD float cbrtf_glibc(float x, const Consts& K, const CbrtScale* S = nullptr)
     const double t2d = (double)t2, ud = (double)u;
     // ym = u * (t2 + 2.0 * xm) / (2.0 * t2 + xm) * factor[2 + e % 3], then ldexpf(ym, e / 3): the power of
     // two commutes with the rounding to float, so both scalings are one multiplication by an exact double
-    double num = (xm + xm) + t2d;
+    // (xm + xm) + t2 and (t2 + t2) + xm: the doublings are exact, so each sum is one fused operation
+    double num = fma(2.0, xm, t2d);
     num = num * ud;
-    const double den = (t2d + t2d) + xm;
+    const double den = fma(2.0, t2d, xm);
     const int eb = (int)(ix >> 23);
     const double f = S ? S->tab[eb] : cbrt_scale_entry(eb);
-    const float r = (float)(ddiv_normal(num, den) * f);
+    const float r = (float)((CHECKED ? ddiv_normal(num, den) : ddiv_normal_fast(num, den)) * f);
     if (!CHECKED) return r;
     return (f2u(x) >> 31) ? -r : r;
 }

@@ -297,7 +297,7 @@ def run_ours(args, rank, world, local_rank):
                     "DRAM traffic (traffic) is far below its algorithmic bytes and the kernel is FP32-pipe bound, not HBM bound"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic_r1.json")
     if os.path.exists(traffic_file):
-        tr = json.load(open(traffic_file)).get(args.workload, {})
+        tr = {k: v for k, v in json.load(open(traffic_file)).get(args.workload, {}).items()}
         if names[dom] in tr:
             roof["traffic"] = tr[names[dom]] * pairs_per_launch   # bytes per launch from the ncu --set full capture
         roof["dram_bytes_per_pair_ncu"] = {k: v for k, v in tr.items()}

@@ -340,10 +340,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="4k", choices=list(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--batch", type=int, default=0, help="pairs per launch group (default: 8 at 4K, 16 at 1080p, 32 for 512x512)")
     ap.add_argument("--ring", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.batch <= 0:
+        args.batch = {"4k": 8, "1080p": 16, "512": 32}[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

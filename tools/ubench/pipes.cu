@@ -33,6 +33,10 @@ __global__ void __launch_bounds__(512) k(float* out, int iters, float a0, float 
                 if (OP == 11) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
                 if (OP == 12) d[i] = (double)(float)d[i] + 1.0;                         // F2F pair + DADD
                 if (OP == 13) asm volatile("rcp.approx.ftz.f64 %0, %0;" : "+d"(d[i]));
+                if (OP == 14) asm volatile("{ .reg .b64 c; mov.b64 c, {0f3F8000A8, 0f3F8000A8}; fma.rn.f32x2 %0, %0, c, %1; }" : "+l"(p[i]) : "l"(pb));
+                if (OP == 15) asm volatile("{ .reg .b64 c, e; mov.b64 c, {0f3F8000A8, 0f3F8000A8}; mov.b64 e, {0f3F000000, 0f3F000000}; fma.rn.f32x2 %0, %0, c, e; }" : "+l"(p[i]));
+                if (OP == 16) asm volatile("{ .reg .b64 c; mov.b64 c, {0f3F8000A8, 0f3F8000A8}; mul.rn.f32x2 %0, %0, c; }" : "+l"(p[i]));
+                if (OP == 17) { asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(pa), "l"(pb)); x[i] = fmaxf(x[i], x[i + CH]) ; x[i+CH] = fminf(x[i + CH], b + i);}
             }
         }
     }
@@ -74,5 +78,9 @@ int main()
     run<11>("MUFU.RCP", 1);
     run<12>("F2F.F32.F64+F2F.F64.F32+DADD", 3);
     run<13>("rcp.f64 seq", 1);
+    run<14>("FFMA2 r,imm,r", 1);
+    run<15>("FFMA2 r,imm,imm", 1);
+    run<16>("FMUL2 r,imm", 1);
+    run<17>("FFMA2 + 2 FMNMX", 3);
     return 0;
 }

@@ -1459,7 +1459,10 @@ __device__ __forceinline__ void h_products(const HGroupLoad& L, f2 (&w)[16], int
     w[(at + 3) & 15] = f2_pack(L.xa.w * L.ya.w, L.xb.w * L.yb.w);
 }
 
-__global__ void __launch_bounds__(kXThreads, 1) k_hv(const __grid_constant__ Geo g, const __grid_constant__ TmaMapsX maps,
+#ifndef KX_MAXNREG
+#define KX_MAXNREG 184
+#endif
+__global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, const __grid_constant__ TmaMapsX maps,
                                                      const HvArgs a)
 {
     extern __shared__ __align__(1024) char xs[];

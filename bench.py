@@ -149,7 +149,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -319,7 +319,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": desc, "width": w, "height": h, "pairs_per_step_per_gpu": n_pairs, "distinct_pairs": n_distinct,
                    "batch": info.batch, "ring": info.ring,
                    "l2": f"inputs cycle through {n_distinct} distinct pairs = {2 * frame_bytes * n_distinct / 1e6:.0f} MB per GPU (> 126 MB L2); "
-                         "intermediates are 0.9 GB per pair",
+                         "XYB planes + strip hand-off records are 0.33 GB per pair",
                    "parallelism": f"frame-sharded x{world}, no collective"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 2 * frame_bytes * n_pairs, "d2h_bytes_per_step": 8 * n_pairs * 109,
                 "steps": e2e_steps, "note": "ssimu2_submit_host from pinned host buffers; PCIe-bound"},
@@ -330,7 +330,28 @@ def run_ours(args, rank, world, local_rank):
         "timing": timing,
         "scores": {"first": s_first, "last": s_last},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """Libraries (NCCL's version banner, torchrun) write to fd 1; the contract is ONE JSON line on stdout.  Point fd 1 at
+    stderr for the run and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
 
 
 def main():
@@ -349,6 +370,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    _guard_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -356,7 +378,7 @@ def main():
         # convenience: re-launch under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
-        sys.exit(subprocess.call(cmd))
+        sys.exit(subprocess.call(cmd, stdout=_REAL_STDOUT))
     run_ours(args, rank, world, local_rank)
     if world > 1:
         import torch.distributed as dist

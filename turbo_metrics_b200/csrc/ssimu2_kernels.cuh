@@ -470,8 +470,17 @@ constexpr int kF2RegionsPerWarp = 2;    // consecutive regions along x
 template <int FMT>
 __device__ __forceinline__ void frontend_region(const Geo& g, const FrameIn& f, float* __restrict__ ximg /* slot base + image */,
                                                 int img, int X0, int Y0, const exact_math::PowfTables& T,
-                                                const exact_math::CbrtScale& S)
+                                                const exact_math::CbrtScale& S, float* __restrict__ scr, int scr_stride)
 {
+    // scr: this thread's column of a shared-memory scratch ([15][threads] floats).  Values that are produced long before
+    // they are consumed (the level-1 pixels of a patch, pass 0's level-3 / level-4 pixels) are parked there so the
+    // pixel loop fits 64 registers without spilling.
+    auto park = [&](int slot, const Rgb& v) {
+        scr[(3 * slot + 0) * scr_stride] = v.r; scr[(3 * slot + 1) * scr_stride] = v.g; scr[(3 * slot + 2) * scr_stride] = v.b;
+    };
+    auto unpark = [&](int slot) {
+        return Rgb{scr[(3 * slot + 0) * scr_stride], scr[(3 * slot + 1) * scr_stride], scr[(3 * slot + 2) * scr_stride]};
+    };
     const int lane = threadIdx.x & 31;
     const int pxi = lane & 7, pyi = lane >> 3;
     const int ns = g.nscales;
@@ -480,7 +489,9 @@ __device__ __forceinline__ void frontend_region(const Geo& g, const FrameIn& f, 
     auto base_of = [&](int s) { return ximg + g.sc[s].xyb_off + (size_t)img * 3 * plane_of(s); };
     const bool vec_ok = (FMT == kNV12 || FMT == kP016) &&
                         ((((uintptr_t)f.p0 | (uintptr_t)f.p1 | (uintptr_t)f.pitch) & 3u) == 0);
-    Rgb l3a = Rgb{0.f, 0.f, 0.f}, l3b = l3a, l4a = l3a, l4b = l3a;   // level 3 / 4 pixels of pass 0 / 1
+    Rgb l3b = Rgb{0.f, 0.f, 0.f}, l4b = l3b;   // level 3 / 4 pixels of pass 1 (pass 0's are parked in slots 3, 4)
+    park(3, l3b);
+    park(4, l3b);
     float* const gd0 = base_of(0);
     const size_t plane0 = plane_of(0);
     const int pitch0 = g.sc[0].pitch;
@@ -488,7 +499,7 @@ __device__ __forceinline__ void frontend_region(const Geo& g, const FrameIn& f, 
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
         const int px0 = X0 + 4 * pxi, py0 = Y0 + 4 * (pyi + 4 * pass);
-        Rgb qa = Rgb{0.f, 0.f, 0.f}, qb = qa, qc = qa, l2 = qa;
+        Rgb l2 = Rgb{0.f, 0.f, 0.f};
         // the patch is walked as four 2x2 blocks (one copy of the colour / XYB code, 4 pixels = 12 cube roots in flight)
 #pragma unroll 1
         for (int blk = 0; blk < 4; blk++) {
@@ -566,10 +577,8 @@ __device__ __forceinline__ void frontend_region(const Geo& g, const FrameIn& f, 
                     q[0] = X; q[plane] = Yv; q[2 * plane] = B;
                 }
                 // level 2 = box of the four level-1 pixels of the patch, in block order (0,0),(1,0),(0,1),(1,1)
-                if (blk == 0) qa = v1;
-                else if (blk == 1) qb = v1;
-                else if (blk == 2) qc = v1;
-                else l2 = box_clamped(qa, qb, qc, v1, (px0 >> 1) + 1 < sd.w, (py0 >> 1) + 1 < sd.h);
+                if (blk < 3) park(blk, v1);
+                else l2 = box_clamped(unpark(0), unpark(1), unpark(2), v1, (px0 >> 1) + 1 < sd.w, (py0 >> 1) + 1 < sd.h);
             }
         }
         if (ns > 2) {
@@ -585,20 +594,23 @@ __device__ __forceinline__ void frontend_region(const Geo& g, const FrameIn& f, 
             // level 3: lanes with even (pxi, pyi) own a pixel; neighbours by shuffle
             const Rgb b = shfl_rgb_xor(l2, 1), c = shfl_rgb_xor(l2, 8), d = shfl_rgb_xor(l2, 9);
             const Rgb v3 = box_clamped(l2, b, c, d, ox + 1 < sd.w, oy + 1 < sd.h);
-            if (pass == 0) l3a = v3; else l3b = v3;
+            if (pass == 0) park(3, v3);
+            l3b = v3;
         }
         if (ns > 3) {
             // level 4: lanes with pxi % 4 == 0, pyi == 0
             const ScaleDesc& sd = g.sc[3];
             const int ox = px0 >> 3, oy = py0 >> 3;
-            const Rgb v = pass == 0 ? l3a : l3b;
+            const Rgb v = l3b;
             const Rgb b = shfl_rgb_xor(v, 2), c = shfl_rgb_xor(v, 16), d = shfl_rgb_xor(v, 18);
             const Rgb v4 = box_clamped(v, b, c, d, ox + 1 < sd.w, oy + 1 < sd.h);
-            if (pass == 0) l4a = v4; else l4b = v4;
+            if (pass == 0) park(4, v4);
+            l4b = v4;
         }
     }
 
     if (ns <= 3) return;
+    const Rgb l3a = unpark(3), l4a = unpark(4);
     // ---- levels 3, 4, 5 of the region: 16 + 4 + 1 pixels, one XYB evaluation.
     //   lanes 0-7 and 16-23 (pyi 0 / 2): level 3; even pxi = pass 0's pixel of that lane, odd pxi = pass 1's of lane - 1
     //   lanes 8-11: level 4 (pass = bit 1, source lane = 4 * bit 0);  lane 12: level 5
@@ -654,6 +666,7 @@ __global__ void __launch_bounds__(kF2Threads, KF2_MINB) k_frontend2(const __grid
 {
     __shared__ exact_math::PowfTables T;
     __shared__ exact_math::CbrtScale S;
+    __shared__ float scratch[15 * kF2Threads];
     {
         const uint64_t* src = reinterpret_cast<const uint64_t*>(&kPowfTablesInit);
         uint64_t* dst = reinterpret_cast<uint64_t*>(&T);
@@ -670,7 +683,8 @@ __global__ void __launch_bounds__(kF2Threads, KF2_MINB) k_frontend2(const __grid
         if (rx >= rx_n) break;
 #pragma unroll 1
         for (int img = 0; img < 2; img++)
-            frontend_region<FMT>(g, img ? in.dis[frame] : in.ref[frame], xyb_slot, img, rx * kF2Region, blockIdx.y * kF2Region, T, S);
+            frontend_region<FMT>(g, img ? in.dis[frame] : in.ref[frame], xyb_slot, img, rx * kF2Region, blockIdx.y * kF2Region, T, S,
+                                 scratch + threadIdx.x, kF2Threads);
     }
 }
 
@@ -685,6 +699,7 @@ __global__ void __launch_bounds__(kF2PThreads, 2) k_frontend2p(const __grid_cons
 {
     __shared__ exact_math::PowfTables T;
     __shared__ exact_math::CbrtScale S;
+    __shared__ float scratch[15 * kF2PThreads];
     {
         const uint64_t* src = reinterpret_cast<const uint64_t*>(&kPowfTablesInit);
         uint64_t* dst = reinterpret_cast<uint64_t*>(&T);
@@ -706,7 +721,8 @@ __global__ void __launch_bounds__(kF2PThreads, 2) k_frontend2p(const __grid_cons
         float* xyb_slot = xyb_base + (size_t)frame * g.xyb_stride;
 #pragma unroll 1
         for (int img = 0; img < 2; img++)
-            frontend_region<FMT>(g, img ? in.dis[frame] : in.ref[frame], xyb_slot, img, rx * kF2Region, ry * kF2Region, T, S);
+            frontend_region<FMT>(g, img ? in.dis[frame] : in.ref[frame], xyb_slot, img, rx * kF2Region, ry * kF2Region, T, S,
+                                 scratch + threadIdx.x, kF2PThreads);
     }
 }
 

@@ -1235,6 +1235,50 @@ __device__ __forceinline__ void error_maps2(const f2 (&o)[5], f2 ref, f2 dis, f2
     part[5] = f2_fma(det2, det2, part[5]);
 }
 
+// error_maps2 with the tails on the FP64 pipe (-DKX_F64_TAILS; measured SLOWER in k_hv: 2.60 ms against 2.19 ms per 8 4K pairs,
+// the extra issue slots and the longer dependency chains cost more than the FP32-pipe cycles they free -- kept as an experiment).
+// The SSIM quotient q is formed exactly as in error_maps2 (f32, cpu.rs:604-626); from there on everything is f64 like
+// the reference (cpu.rs:627-631, 658-674): d = max(1 - q, 0); d1 = (1 + |dis - mu2|) / (1 + |ref - mu1|) - 1, evaluated
+// as (a - b) / (1 + b) with a Newton-refined reciprocal (relative error ~2^-45); sums of x and x^4 straight into the
+// f64 accumulators of both columns.
+__device__ __forceinline__ void dp_tail(float q, float a, float b, double (&acc)[6])
+{
+    const double d = fmax(1.0 - (double)q, 0.0);
+    acc[0] += d;
+    const double dd = d * d;
+    acc[1] = fma(dd, dd, acc[1]);
+    const double ad = (double)a, bd = (double)b;
+    const double den = 1.0 + bd;
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
+    y = fma(y, fma(-den, y, 1.0), y);
+    const double d1 = (ad - bd) * y;
+    const double art = fmax(d1, 0.0), det = fmax(-d1, 0.0);
+    const double a2 = art * art, t2 = det * det;
+    acc[2] += art;
+    acc[3] = fma(a2, a2, acc[3]);
+    acc[4] += det;
+    acc[5] = fma(t2, t2, acc[5]);
+}
+__device__ __forceinline__ void error_maps_dp(const f2 (&o)[5], f2 ref, f2 dis, double (&acc)[6])
+{
+    const f2 C2 = f2_splat(0.0009f), one = f2_splat(1.0f);
+    const f2 s11 = o[0], s22 = o[1], s12 = o[2], mu1 = o[3], mu2 = o[4];
+    const f2 mu11 = f2_mul(mu1, mu1), mu22 = f2_mul(mu2, mu2), mu12 = f2_mul(mu1, mu2);
+    const f2 mu_diff = f2_sub(mu1, mu2);
+    const f2 num_m = f2_fma(mu_diff, f2_neg(mu_diff), one);
+    const f2 num_s = f2_fma(f2_splat(2.0f), f2_sub_prod(s12, mu12), C2);
+    const f2 denom_s = f2_add(f2_add(f2_sub_prod(s11, mu11), f2_sub_prod(s22, mu22)), C2);
+    const f2 q = div_rn_normal2(f2_mul(num_m, num_s), denom_s);
+    const f2 a = f2_abs(f2_sub(dis, mu2)), b = f2_abs(f2_sub(ref, mu1));
+    float q0, q1, a0, a1, b0, b1;
+    f2_unpack(q, q0, q1);
+    f2_unpack(a, a0, a1);
+    f2_unpack(b, b0, b1);
+    dp_tail(q0, a0, b0, acc);
+    dp_tail(q1, a1, b1, acc);
+}
+
 // k_vpass, TMA-fed.  CTA = one 64-column strip of one scale of one frame; 3 consumer warps (warp = channel, lane =
 // a PAIR of adjacent columns, all arithmetic packed f32x2) + 1 producer warp.  The producer streams
 // {hb rows t, t+1 ; xyb rows t-4, t-3} boxes into a 5-stage shared-memory ring with cp.async.bulk.tensor (out-of-range
@@ -1684,7 +1728,9 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
         const uint32_t cur = sbase + kXOffHb + si * kXHbBytes + lane8;
         const uint32_t prv = sbase + kXOffHb + sp * kXHbBytes + lane8;
         const uint32_t inb = sbase + kXOffIn + si * kXInBytes + kXInLead * 4 + lane8 + (uint32_t)(c * kXInPlane * 4);
+#ifndef KX_F64_TAILS
         f2 part[6] = {zero2, zero2, zero2, zero2, zero2, zero2};
+#endif
 #pragma unroll 1
         for (int i4 = 0; i4 < kXR; i4 += 4) {
 #pragma unroll
@@ -1702,10 +1748,16 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
                 const f2 fr = fifo_r[r], fd = fifo_d[r];   // XYB of output row t - 4
                 fifo_r[r] = lds64(inb + (uint32_t)(i * kXInW * 4));
                 fifo_d[r] = lds64(inb + (uint32_t)((3 * kXInPlane + i * kXInW) * 4));
+#ifndef KX_F64_TAILS
                 if (t >= 4 && t < H + 4) error_maps2(o, fr, fd, part);
+#else
+                if (t >= 4 && t < H + 4) error_maps_dp(o, fr, fd, acc);
+#endif
             }
+#ifndef KX_F64_TAILS
 #pragma unroll
             for (int kk = 0; kk < 6; kk++) { acc[kk] += (double)f2_hsum(part[kk]); part[kk] = zero2; }
+#endif
         }
         __syncwarp();
         if (lane == 0) {

@@ -20,6 +20,8 @@
 
 #include "exact_math.cuh"
 
+#include <type_traits>
+
 namespace ssimu2 {
 
 constexpr int kMaxScales = 6;
@@ -1235,6 +1237,38 @@ __device__ __forceinline__ void error_maps2(const f2 (&o)[5], f2 ref, f2 dis, f2
     part[5] = f2_fma(det2, det2, part[5]);
 }
 
+// The two halves of error_maps2 for k_hv, where the SSIM map and the edge maps of a channel run in different warps:
+// the same operations in the same order on the same operands.
+__device__ __forceinline__ void ssim_map2(f2 s11, f2 s22, f2 s12, f2 mu1, f2 mu2, f2 (&part)[2])
+{
+    const f2 C2 = f2_splat(0.0009f), one = f2_splat(1.0f);
+    const f2 mu11 = f2_mul(mu1, mu1), mu22 = f2_mul(mu2, mu2), mu12 = f2_mul(mu1, mu2);
+    const f2 mu_diff = f2_sub(mu1, mu2);
+    const f2 num_m = f2_fma(mu_diff, f2_neg(mu_diff), one);
+    const f2 num_s = f2_fma(f2_splat(2.0f), f2_sub_prod(s12, mu12), C2);
+    const f2 denom_s = f2_add(f2_add(f2_sub_prod(s11, mu11), f2_sub_prod(s22, mu22)), C2);
+    const f2 q = div_rn_normal2(f2_mul(num_m, num_s), denom_s);
+    const f2 d = f2_max0(f2_sub(one, q));
+    part[0] = f2_add(part[0], d);
+    const f2 d2 = f2_mul(d, d);
+    part[1] = f2_fma(d2, d2, part[1]);
+}
+__device__ __forceinline__ void edge_maps2(f2 mu1, f2 mu2, f2 ref, f2 dis, f2 (&part)[4])
+{
+    const f2 one = f2_splat(1.0f);
+    const f2 a = f2_abs(f2_sub(dis, mu2)), b = f2_abs(f2_sub(ref, mu1));
+    const f2 den = f2_add(one, b);
+    f2 r = f2_rcp_approx(den);
+    r = f2_fma(r, f2_fma(f2_neg(den), r, one), r);
+    const f2 d1 = f2_mul(f2_sub(a, b), r);
+    const f2 art = f2_max0(d1), det = f2_max0(f2_neg(d1));
+    const f2 art2 = f2_mul(art, art), det2 = f2_mul(det, det);
+    part[0] = f2_add(part[0], art);
+    part[1] = f2_fma(art2, art2, part[1]);
+    part[2] = f2_add(part[2], det);
+    part[3] = f2_fma(det2, det2, part[3]);
+}
+
 // error_maps2 with the tails on the FP64 pipe (-DKX_F64_TAILS; measured SLOWER in k_hv: 2.60 ms against 2.19 ms per 8 4K pairs,
 // the extra issue slots and the longer dependency chains cost more than the FP32-pipe cycles they free -- kept as an experiment).
 // The SSIM quotient q is formed exactly as in error_maps2 (f32, cpu.rs:604-626); from there on everything is f64 like
@@ -1430,23 +1464,49 @@ constexpr int kXHbPitch = 68;                            // floats; with the pla
 constexpr int kXHbPlane = kXR * kXHbPitch + 8;           // 824 floats
 constexpr int kXHbFloats = 15 * kXHbPlane;
 constexpr uint32_t kXHbBytes = kXHbFloats * 4;           // 49440
-constexpr int kXHThreads = 96, kXVThreads = 96;
-constexpr int kXThreads = kXHThreads + kXVThreads + 64;  // + the two helper warps
+constexpr int kXHThreads = 96;
+constexpr int kXWarps = 12;                              // roles by warp id, see k_hv
+constexpr int kXThreads = kXWarps * 32;
 constexpr int kXHsF2 = 6 * kXHThreads;                   // hand-off record: [6 state words][96 H threads] f2
 constexpr uint32_t kXHsBytes = kXHsF2 * 8;               // 4608
+constexpr int kXSub = 4;                                 // rows per mu hand-off between the Vb and Va warps of a channel
+constexpr int kXMuSlotF = kXSub * 2 * kXC;               // [4 rows][mu1, mu2][64 columns] floats
+constexpr uint32_t kXMuSlotBytes = kXMuSlotF * 4;        // 2048
 constexpr uint32_t kXOffIn = 0;
 constexpr uint32_t kXOffHb = kXOffIn + 3 * kXInBytes;
 constexpr uint32_t kXOffHsIn = kXOffHb + 3 * kXHbBytes;  // state arriving from the left strip (1 record)
-constexpr uint32_t kXOffHsOut = kXOffHsIn + kXHsBytes;   // state leaving for the right strip (1 record)
-constexpr uint32_t kXOffOnes = kXOffHsOut + kXHsBytes;   // one row of 76 ones (the second factor of the mu planes)
+constexpr uint32_t kXOffMu = kXOffHsIn + kXHsBytes;      // [3 channels][2 slots] mu hand-off
+constexpr uint32_t kXOffOnes = kXOffMu + 6 * kXMuSlotBytes;  // one row of 76 ones (the second factor of the mu planes)
 constexpr uint32_t kXOffBars = kXOffOnes + 320;
-constexpr size_t kXSmemBytes = kXOffBars + 16 * 8;
+constexpr int kXNumBars = 15 + 12;
+constexpr size_t kXSmemBytes = kXOffBars + kXNumBars * 8;
 static_assert(kXOffHb % 16 == 0 && kXHbBytes % 16 == 0 && kXInBytes % 128 == 0 && kXOffBars % 8 == 0, "k_hv smem layout");
+static_assert(kXSmemBytes <= 232448, "k_hv shared memory");
+static_assert(kXR % kXSub == 0, "k_hv sub-bands");
 
 // mbarrier wait with a watchdog: a protocol bug must end in a trap, not in a hung GPU
+#ifndef KX_SPIN
+#define KX_SPIN 0
+#endif
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity)
 {
     const uint32_t a = smem_u32(bar);
+#if KX_SPIN
+    for (uint32_t it = 0;; it++) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (it > 400000000u) __trap();
+    }
+#else
     for (uint32_t it = 0;; it++) {
         uint32_t ok;
         asm volatile(
@@ -1461,6 +1521,7 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity)
         if (ok) return;
         if (it > 400000u) __trap();
     }
+#endif
 }
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p)
 {
@@ -1471,6 +1532,16 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p)
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_cta_shared_inc(uint32_t addr)
+{
+    asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta_shared(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
 }
 __device__ __forceinline__ void sts64(uint32_t addr, f2 v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v.v) : "memory"); }
 
@@ -1520,8 +1591,31 @@ __device__ __forceinline__ void h_products(const HGroupLoad& L, f2 (&w)[16], int
 }
 
 #ifndef KX_MAXNREG
-#define KX_MAXNREG 184
+#define KX_MAXNREG 168
 #endif
+// timing experiments only (results are wrong unless all are at their defaults)
+#ifndef KX_EXP_HITERS
+#define KX_EXP_HITERS 4
+#endif
+#ifndef KX_EXP_VROWS
+#define KX_EXP_VROWS kXSub
+#endif
+#ifndef KX_EXP_NODEP
+#define KX_EXP_NODEP 0
+#endif
+// Warp roles.  The scheduler sub-partition of a warp is (warp id % 4); per 12-row band an H warp needs ~1660 FP32-pipe
+// cycles, a Va warp ~1150, a Vb warp ~750, so the roles are placed to load the four sub-partitions evenly:
+//   SP0: H0, Va0, P_in     SP1: H1, Va1, P_out     SP2: H2, Va2, (idle)     SP3: Vb0, Vb1, Vb2
+__device__ __forceinline__ int hv_role(int warp, int& ch)
+{
+    // 0 = H, 1 = Va, 2 = Vb, 3 = P_in, 4 = P_out, 5 = idle
+    if (warp < 3) { ch = warp; return 0; }
+    if (warp >= 4 && warp < 7) { ch = warp - 4; return 1; }
+    if ((warp & 3) == 3) { ch = warp >> 2; return 2; }
+    ch = 0;
+    return warp == 8 ? 3 : (warp == 9 ? 4 : 5);
+}
+
 __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, const __grid_constant__ TmaMapsX maps,
                                                      const HvArgs a)
 {
@@ -1530,13 +1624,15 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
     const uint32_t sbase = smem_u32(xs);
     uint64_t* bars = reinterpret_cast<uint64_t*>(xs + kXOffBars);
     uint64_t* in_full = bars;        // [3] TMA
-    uint64_t* in_free = bars + 3;    // [3] 3 V warps
+    uint64_t* in_free = bars + 3;    // [3] 3 Vb warps
     uint64_t* hb_full = bars + 6;    // [3] 3 H warps
-    uint64_t* hb_free = bars + 9;    // [3] 3 V warps
+    uint64_t* hb_free = bars + 9;    // [3] 3 Va + 3 Vb warps
     uint64_t* hsi_full = bars + 12;  // P_in
     uint64_t* hsi_free = bars + 13;  // 3 H warps
-    uint64_t* hso_full = bars + 14;  // 3 H warps
-    uint64_t* hso_free = bars + 15;  // P_out
+    // bars[14]: a plain counter, +1 per H warp per band (P_out may lag behind by any number of bands)
+    const uint32_t hso_count = sbase + kXOffBars + 14 * 8;
+    uint64_t* mu_full = bars + 15;   // [3 channels][2 slots] Vb -> Va
+    uint64_t* mu_free = bars + 21;   // [3 channels][2 slots] Va -> Vb
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
@@ -1545,12 +1641,15 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             mbar_init(&in_full[i], 1);
             mbar_init(&in_free[i], 3);
             mbar_init(&hb_full[i], 3);
-            mbar_init(&hb_free[i], 3);
+            mbar_init(&hb_free[i], 6);
         }
         mbar_init(hsi_full, 1);
         mbar_init(hsi_free, 3);
-        mbar_init(hso_full, 3);
-        mbar_init(hso_free, 1);
+        bars[14] = 0;
+        for (int i = 0; i < 6; i++) {
+            mbar_init(&mu_full[i], 1);
+            mbar_init(&mu_free[i], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // tile slot 2 plays "the band above band 0": zeros (the vertical filter's zero padding); the ones row
@@ -1575,8 +1674,10 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
     const int x0 = k * kXC;
     const size_t rec_base = (size_t)frame * g.total_recs + sd.rec0;   // + strip * nb + band
     const bool last_strip = (k == sd.n_strips - 1);
+    int c;
+    const int role = hv_role(warp, c);
 
-    if (warp == 6) {
+    if (role == 3) {
         // ===== P_in: tile loads + the state the left strip left behind =====
         const CUtensorMap* map = &maps.xyb_in[s];
         for (int j = 0; j < nb; j++) {
@@ -1586,7 +1687,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
                 mbar_expect_tx(&in_full[si], kXInBytes);
                 tma_load_4d(xs + kXOffIn + si * kXInBytes, map, &in_full[si], x0 - kXInLead, j * kXR, 0, frame);
             }
-            if (k > 0) {
+            if (k > 0 && !KX_EXP_NODEP) {
                 if (j >= 1) mbar_wait_wd(hsi_free, (uint32_t)((j - 1) & 1));
                 const size_t rec = rec_base + (size_t)(k - 1) * nb + j;
                 const uint32_t* fl = a.flags + rec;
@@ -1605,29 +1706,24 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
         }
         return;
     }
-    if (warp == 7) {
-        // ===== P_out: publishes the state at the right edge of every band =====
-        if (last_strip) return;
+    if (role == 4) {
+        // ===== P_out: releases the right-edge state record of every band (written to global memory by the H warps) =====
+        if (last_strip || lane != 0) return;
         for (int j = 0; j < nb; j++) {
-            mbar_wait_wd(hso_full, (uint32_t)(j & 1));
-            const size_t rec = rec_base + (size_t)k * nb + j;
-            float4* dst = reinterpret_cast<float4*>(a.hstate + rec * kXHsF2);
-            const float4* src = reinterpret_cast<const float4*>(xs + kXOffHsOut);
-#pragma unroll
-            for (int i = 0; i < (int)(kXHsBytes / 16 / 32); i++) __stcg(dst + i * 32 + lane, src[i * 32 + lane]);
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(hso_free);
-                __threadfence();
-                st_release_u32(a.flags + rec, a.epoch);
+            for (uint32_t it = 0; ld_acquire_cta_shared(hso_count) < 3u * (uint32_t)(j + 1); it++) {
+                __nanosleep(100);
+                if (it > 40000000u) __trap();
             }
+            __threadfence();
+            st_release_u32(a.flags + rec_base + (size_t)k * nb + j, a.epoch);
         }
         return;
     }
+    if (role == 5) return;
 
-    if (warp < 3) {
+    if (role == 0) {
         // ===== H: warp = channel, lane = (quantity, row pair); lanes 30, 31 shadow lane 29 =====
-        const int ch = warp, l = lane < 30 ? lane : 29;
+        const int ch = c, l = lane < 30 ? lane : 29;
         const int q = l / 6, rp = l - 6 * q;
         const int px = (q == 1 || q == 4) ? 3 + ch : ch;
         const int py = (q == 0) ? ch : ((q == 1 || q == 2) ? 3 + ch : -1);
@@ -1641,7 +1737,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             mbar_wait_wd(&in_full[si], (uint32_t)((j / 3) & 1));
             if (j >= 2) mbar_wait_wd(&hb_free[si], (uint32_t)(((j - 2) / 3) & 1));
             HState2 st;
-            if (k > 0) {
+            if (k > 0 && !KX_EXP_NODEP) {
                 mbar_wait_wd(hsi_full, (uint32_t)(j & 1));
                 const uint32_t hsb = sbase + kXOffHsIn + (uint32_t)hidx * 8u;
                 st.p1 = lds64(hsb); st.p3 = lds64(hsb + 96 * 8); st.p5 = lds64(hsb + 2 * 96 * 8);
@@ -1673,7 +1769,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             }
             HGroupLoad nxt = h_load(axA, axB, ayA, ayB, 48);
 #pragma unroll 1
-            for (int it = 0; it < 4; it++) {
+            for (int it = 0; it < KX_EXP_HITERS; it++) {
 #pragma unroll
                 for (int gg = 0; gg < 4; gg++) {
                     const HGroupLoad cur = nxt;
@@ -1695,78 +1791,143 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             if (last_strip && x0 + kXC > W) {
                 // columns past the right edge hold the filter's ring-out: the V pass must see zeros there
                 float* t0 = reinterpret_cast<float*>(xs + kXOffHb + si * kXHbBytes) + (q * 3 + ch) * kXHbPlane + rp * kXHbPitch;
-                for (int c = W - x0; c < kXC; c++) { t0[c] = 0.0f; t0[6 * kXHbPitch + c] = 0.0f; }
+                for (int cc = W - x0; cc < kXC; cc++) { t0[cc] = 0.0f; t0[6 * kXHbPitch + cc] = 0.0f; }
             }
             if (!last_strip) {
-                if (j >= 1) mbar_wait_wd(hso_free, (uint32_t)((j - 1) & 1));
-                const uint32_t hso = sbase + kXOffHsOut + (uint32_t)hidx * 8u;
-                sts64(hso, st.p1); sts64(hso + 96 * 8, st.p3); sts64(hso + 2 * 96 * 8, st.p5);
-                sts64(hso + 3 * 96 * 8, st.pp1); sts64(hso + 4 * 96 * 8, st.pp3); sts64(hso + 5 * 96 * 8, st.pp5);
+                // the state at the right edge of the band goes straight to the record of (strip, band): 256 B per store
+                unsigned long long* rec = reinterpret_cast<unsigned long long*>(a.hstate + (rec_base + (size_t)k * nb + j) * kXHsF2) + hidx;
+                __stcg(rec, st.p1.v); __stcg(rec + 96, st.p3.v); __stcg(rec + 2 * 96, st.p5.v);
+                __stcg(rec + 3 * 96, st.pp1.v); __stcg(rec + 4 * 96, st.pp3.v); __stcg(rec + 5 * 96, st.pp5.v);
             }
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&hb_full[si]);
-                if (!last_strip) mbar_arrive(hso_full);
+                if (!last_strip) red_release_cta_shared_inc(hso_count);
             }
         }
         return;
     }
 
-    // ===== V: warp = channel, lane = column pair =====
-    const int c = warp - 3;
+    // ===== V: lane = column pair.  Vb runs the mu1 / mu2 filters and the edge maps and hands the blurred mu rows to
+    // Va (4 rows at a time through a 2-slot ring); Va runs the s11 / s22 / s12 filters and the SSIM map. =====
     const f2 zero2 = f2_splat(0.0f);
-    VState2 stq[5];
-#pragma unroll
-    for (int qi = 0; qi < 5; qi++) stq[qi] = VState2{zero2, zero2, zero2, zero2, zero2, zero2};
-    f2 fifo_r[4] = {zero2, zero2, zero2, zero2}, fifo_d[4] = {zero2, zero2, zero2, zero2};  // XYB rows t-4 .. t-1
-    double acc[6] = {0, 0, 0, 0, 0, 0};
     const uint32_t lane8 = (uint32_t)lane * 8u;
+    const uint32_t mub = sbase + kXOffMu + (uint32_t)c * 2u * kXMuSlotBytes + lane8;
+    uint64_t* const muf = mu_full + 2 * c;
+    uint64_t* const mue = mu_free + 2 * c;
+    if (role == 2) {
+        VState2 stq[2];
+#pragma unroll
+        for (int qi = 0; qi < 2; qi++) stq[qi] = VState2{zero2, zero2, zero2, zero2, zero2, zero2};
+        f2 fifo_r[4] = {zero2, zero2, zero2, zero2}, fifo_d[4] = {zero2, zero2, zero2, zero2};  // XYB rows t-4 .. t-1
+        double acc[4] = {0, 0, 0, 0};
+        int n = 0;   // sub-band counter
+        for (int j = 0; j < nb; j++) {
+            const int si = j % 3, sp = (j + 2) % 3;
+            mbar_wait_wd(&hb_full[si], (uint32_t)((j / 3) & 1));
+            mbar_wait_wd(&in_full[si], (uint32_t)((j / 3) & 1));
+            const uint32_t cur = sbase + kXOffHb + si * kXHbBytes + lane8 + (uint32_t)((9 + c) * kXHbPlane * 4);
+            const uint32_t prv = sbase + kXOffHb + sp * kXHbBytes + lane8 + (uint32_t)((9 + c) * kXHbPlane * 4);
+            const uint32_t inb = sbase + kXOffIn + si * kXInBytes + kXInLead * 4 + lane8 + (uint32_t)(c * kXInPlane * 4);
+#pragma unroll 1
+            for (int i4 = 0; i4 < kXR; i4 += kXSub, n++) {
+                const int p = n & 1;
+                if (n >= 2) mbar_wait_wd(&mue[p], (uint32_t)(((n >> 1) - 1) & 1));
+                const uint32_t mus = mub + (uint32_t)p * kXMuSlotBytes;
+                f2 part[4] = {zero2, zero2, zero2, zero2};
+                // rows of one sub-band; CHECKED only for the sub-bands that straddle output rows -4..-1 or H..: the
+                // common path has no branch per row, so the four rows' map chains interleave
+                auto rows = [&](auto checked) {
+#pragma unroll
+                    for (int r = 0; r < KX_EXP_VROWS; r++) {
+                        const int i = i4 + r, t = j * kXR + i;
+                        const uint32_t a_t = cur + (uint32_t)(i * kXHbPitch * 4);
+                        const uint32_t a_d = i < 10 ? prv + (uint32_t)((i + 2) * kXHbPitch * 4) : cur + (uint32_t)((i - 10) * kXHbPitch * 4);
+                        const f2 m1 = vstep2(stq[0], lds64(a_d), lds64(a_t));
+                        const f2 m2 = vstep2(stq[1], lds64(a_d + 3 * kXHbPlane * 4), lds64(a_t + 3 * kXHbPlane * 4));
+                        sts64(mus + (uint32_t)(r * 2 * kXC * 4), m1);
+                        sts64(mus + (uint32_t)((r * 2 + 1) * kXC * 4), m2);
+                        const f2 fr = fifo_r[r], fd = fifo_d[r];   // XYB of output row t - 4
+                        fifo_r[r] = lds64(inb + (uint32_t)(i * kXInW * 4));
+                        fifo_d[r] = lds64(inb + (uint32_t)((3 * kXInPlane + i * kXInW) * 4));
+                        if (!decltype(checked)::value || (t >= 4 && t < H + 4)) edge_maps2(m1, m2, fr, fd, part);
+                    }
+                };
+                const int t0 = j * kXR + i4;
+                if (t0 >= 4 && t0 + kXSub <= H + 4) rows(std::false_type{}); else rows(std::true_type{});
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&muf[p]);
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) acc[kk] += (double)f2_hsum(part[kk]);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&in_free[si]);
+                mbar_arrive(&hb_free[sp]);
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            double vsum = acc[kk];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) vsum += __shfl_down_sync(0xffffffffu, vsum, off);
+            if (lane == 0) a.partials[((size_t)frame * g.total_strips + sd.strip0 + k) * 18 + c * 6 + 2 + kk] = vsum;
+        }
+        return;
+    }
+
+    // ----- Va -----
+    VState2 stq[3];
+#pragma unroll
+    for (int qi = 0; qi < 3; qi++) stq[qi] = VState2{zero2, zero2, zero2, zero2, zero2, zero2};
+    double acc[2] = {0, 0};
+    int n = 0;
     for (int j = 0; j < nb; j++) {
         const int si = j % 3, sp = (j + 2) % 3;
         mbar_wait_wd(&hb_full[si], (uint32_t)((j / 3) & 1));
-        mbar_wait_wd(&in_full[si], (uint32_t)((j / 3) & 1));
-        const uint32_t cur = sbase + kXOffHb + si * kXHbBytes + lane8;
-        const uint32_t prv = sbase + kXOffHb + sp * kXHbBytes + lane8;
-        const uint32_t inb = sbase + kXOffIn + si * kXInBytes + kXInLead * 4 + lane8 + (uint32_t)(c * kXInPlane * 4);
-#ifndef KX_F64_TAILS
-        f2 part[6] = {zero2, zero2, zero2, zero2, zero2, zero2};
-#endif
+        const uint32_t cur = sbase + kXOffHb + si * kXHbBytes + lane8 + (uint32_t)(c * kXHbPlane * 4);
+        const uint32_t prv = sbase + kXOffHb + sp * kXHbBytes + lane8 + (uint32_t)(c * kXHbPlane * 4);
 #pragma unroll 1
-        for (int i4 = 0; i4 < kXR; i4 += 4) {
+        for (int i4 = 0; i4 < kXR; i4 += kXSub, n++) {
+            const int p = n & 1;
+            f2 o[kXSub][3];
 #pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const int i = i4 + r, t = j * kXR + i;
-                // x[t] is row i of this band's tile; x[t - 10] is 10 rows up: in the previous band's tile for i < 10
+            for (int r = 0; r < kXSub; r++)
+                for (int qi = 0; qi < 3; qi++) o[r][qi] = zero2;
+#pragma unroll
+            for (int r = 0; r < KX_EXP_VROWS; r++) {
+                const int i = i4 + r;
                 const uint32_t a_t = cur + (uint32_t)(i * kXHbPitch * 4);
                 const uint32_t a_d = i < 10 ? prv + (uint32_t)((i + 2) * kXHbPitch * 4) : cur + (uint32_t)((i - 10) * kXHbPitch * 4);
-                f2 o[5];
 #pragma unroll
-                for (int qi = 0; qi < 5; qi++) {
-                    const uint32_t pl = (uint32_t)((qi * 3 + c) * kXHbPlane * 4);
-                    o[qi] = vstep2(stq[qi], lds64(a_d + pl), lds64(a_t + pl));
+                for (int qi = 0; qi < 3; qi++) {
+                    const uint32_t pl = (uint32_t)(qi * 3 * kXHbPlane * 4);
+                    o[r][qi] = vstep2(stq[qi], lds64(a_d + pl), lds64(a_t + pl));
                 }
-                const f2 fr = fifo_r[r], fd = fifo_d[r];   // XYB of output row t - 4
-                fifo_r[r] = lds64(inb + (uint32_t)(i * kXInW * 4));
-                fifo_d[r] = lds64(inb + (uint32_t)((3 * kXInPlane + i * kXInW) * 4));
-#ifndef KX_F64_TAILS
-                if (t >= 4 && t < H + 4) error_maps2(o, fr, fd, part);
-#else
-                if (t >= 4 && t < H + 4) error_maps_dp(o, fr, fd, acc);
-#endif
             }
-#ifndef KX_F64_TAILS
+            mbar_wait_wd(&muf[p], (uint32_t)((n >> 1) & 1));
+            const uint32_t mus = mub + (uint32_t)p * kXMuSlotBytes;
+            f2 part[2] = {zero2, zero2};
+            auto maps = [&](auto checked) {
 #pragma unroll
-            for (int kk = 0; kk < 6; kk++) { acc[kk] += (double)f2_hsum(part[kk]); part[kk] = zero2; }
-#endif
+                for (int r = 0; r < KX_EXP_VROWS; r++) {
+                    const int t = j * kXR + i4 + r;
+                    const f2 m1 = lds64(mus + (uint32_t)(r * 2 * kXC * 4)), m2 = lds64(mus + (uint32_t)((r * 2 + 1) * kXC * 4));
+                    if (!decltype(checked)::value || (t >= 4 && t < H + 4)) ssim_map2(o[r][0], o[r][1], o[r][2], m1, m2, part);
+                }
+            };
+            const int t0 = j * kXR + i4;
+            if (t0 >= 4 && t0 + kXSub <= H + 4) maps(std::false_type{}); else maps(std::true_type{});
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&mue[p]);
+            acc[0] += (double)f2_hsum(part[0]);
+            acc[1] += (double)f2_hsum(part[1]);
         }
         __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(&in_free[si]);
-            mbar_arrive(&hb_free[sp]);
-        }
+        if (lane == 0) mbar_arrive(&hb_free[sp]);
     }
 #pragma unroll
-    for (int kk = 0; kk < 6; kk++) {
+    for (int kk = 0; kk < 2; kk++) {
         double vsum = acc[kk];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) vsum += __shfl_down_sync(0xffffffffu, vsum, off);

@@ -780,6 +780,11 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3)
 {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
@@ -1465,7 +1470,7 @@ constexpr int kXHbPlane = kXR * kXHbPitch + 8;           // 824 floats
 constexpr int kXHbFloats = 15 * kXHbPlane;
 constexpr uint32_t kXHbBytes = kXHbFloats * 4;           // 49440
 constexpr int kXHThreads = 96;
-constexpr int kXWarps = 12;                              // roles by warp id, see k_hv
+constexpr int kXWarps = 16;                              // roles by warp id, see k_hv
 constexpr int kXThreads = kXWarps * 32;
 constexpr int kXHsF2 = 6 * kXHThreads;                   // hand-off record: [6 state words][96 H threads] f2
 constexpr uint32_t kXHsBytes = kXHsF2 * 8;               // 4608
@@ -1474,13 +1479,14 @@ constexpr int kXMuSlotF = kXSub * 2 * kXC;               // [4 rows][mu1, mu2][6
 constexpr uint32_t kXMuSlotBytes = kXMuSlotF * 4;        // 2048
 constexpr uint32_t kXOffIn = 0;
 constexpr uint32_t kXOffHb = kXOffIn + 3 * kXInBytes;
-constexpr uint32_t kXOffHsIn = kXOffHb + 3 * kXHbBytes;  // state arriving from the left strip (1 record)
-constexpr uint32_t kXOffMu = kXOffHsIn + kXHsBytes;      // [3 channels][2 slots] mu hand-off
-constexpr uint32_t kXOffOnes = kXOffMu + 6 * kXMuSlotBytes;  // one row of 76 ones (the second factor of the mu planes)
-constexpr uint32_t kXOffBars = kXOffOnes + 320;
-constexpr int kXNumBars = 15 + 12;
+constexpr uint32_t kXOffMu = kXOffHb + 3 * kXHbBytes;    // [3 channels][2 slots] mu hand-off
+constexpr uint32_t kXOffOnes = (kXOffMu + 6 * kXMuSlotBytes + 127) / 128 * 128;  // rows of ones (second factor of the mu planes)
+constexpr uint32_t kXOnesBytes = 384;
+constexpr uint32_t kXOffBars = kXOffOnes + kXOnesBytes;
+constexpr int kXNumBars = 17 + 12 + 3;
 constexpr size_t kXSmemBytes = kXOffBars + kXNumBars * 8;
-static_assert(kXOffHb % 16 == 0 && kXHbBytes % 16 == 0 && kXInBytes % 128 == 0 && kXOffBars % 8 == 0, "k_hv smem layout");
+static_assert(kXOffHb % 16 == 0 && kXHbBytes % 16 == 0 && kXInBytes % 128 == 0 && kXOffIn % 128 == 0 && kXOffOnes % 128 == 0 &&
+                  kXOffBars % 8 == 0, "k_hv smem layout");
 static_assert(kXSmemBytes <= 232448, "k_hv shared memory");
 static_assert(kXR % kXSub == 0, "k_hv sub-bands");
 
@@ -1529,13 +1535,25 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p)
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ f2 ldcg64(const void* p)
+{
+    f2 r;
+    asm volatile("ld.global.cg.b64 %0, [%1];" : "=l"(r.v) : "l"(p) : "memory");
+    return r;
+}
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void red_release_cta_shared_inc(uint32_t addr)
+__device__ __forceinline__ void st_release_cta_shared(uint32_t addr, uint32_t v)
 {
-    asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_acquire_cta_shared(uint32_t addr)
 {
@@ -1591,9 +1609,21 @@ __device__ __forceinline__ void h_products(const HGroupLoad& L, f2 (&w)[16], int
 }
 
 #ifndef KX_MAXNREG
-#define KX_MAXNREG 168
+#define KX_MAXNREG 128
 #endif
 // timing experiments only (results are wrong unless all are at their defaults)
+#ifndef KX_REL
+#define KX_REL 0   // 1: the V warps hand the previous band's tile back after 8 of the 12 rows (0: at the end of the band)
+#endif
+#ifndef KX_PF
+#define KX_PF 6   // bands of L2 prefetch ahead of the shared-memory ring (0 = off)
+#endif
+#ifndef KX_EXP_NOSTATE
+#define KX_EXP_NOSTATE 0
+#endif
+#ifndef KX_EXP_NOTMA
+#define KX_EXP_NOTMA 0
+#endif
 #ifndef KX_EXP_HITERS
 #define KX_EXP_HITERS 4
 #endif
@@ -1603,17 +1633,24 @@ __device__ __forceinline__ void h_products(const HGroupLoad& L, f2 (&w)[16], int
 #ifndef KX_EXP_NODEP
 #define KX_EXP_NODEP 0
 #endif
-// Warp roles.  The scheduler sub-partition of a warp is (warp id % 4); per 12-row band an H warp needs ~1660 FP32-pipe
-// cycles, a Va warp ~1150, a Vb warp ~750, so the roles are placed to load the four sub-partitions evenly:
-//   SP0: H0, Va0, P_in     SP1: H1, Va1, P_out     SP2: H2, Va2, (idle)     SP3: Vb0, Vb1, Vb2
-__device__ __forceinline__ int hv_role(int warp, int& ch)
+// Warp roles (16 warps).  The scheduler sub-partition of a warp is (warp id % 4).  Per 12-row band an H warp needs
+// ~1660 FP32-pipe cycles, a Va warp ~1150, a Vb warp ~750.  Every channel has TWO H warps that take alternate bands,
+// so the waits / state fetch / first loads of band j+1 overlap the scan of band j:
+//   SP0: H0a H0b Va0 P_out    SP1: H1a H1b Va1 (idle)    SP2: H2a H2b Va2 P_state    SP3: Vb0 Vb1 Vb2 P_tma
+// plane slot of quantity q (s11, s22, s12, mu1, mu2) in the H-pass tile: planes [slot * 3 + channel]
+__host__ __device__ constexpr int hv_slot(int q) { return q == 1 ? 3 : (q == 3 ? 1 : q); }
+__device__ __forceinline__ int hv_role(int warp, int& ch, int& par)
 {
-    // 0 = H, 1 = Va, 2 = Vb, 3 = P_in, 4 = P_out, 5 = idle
-    if (warp < 3) { ch = warp; return 0; }
-    if (warp >= 4 && warp < 7) { ch = warp - 4; return 1; }
-    if ((warp & 3) == 3) { ch = warp >> 2; return 2; }
-    ch = 0;
-    return warp == 8 ? 3 : (warp == 9 ? 4 : 5);
+    // 0 = H, 1 = Va, 2 = Vb, 3 = P_tma, 4 = P_out, 5 = idle, 6 = P_state
+    const int sp = warp & 3, row = warp >> 2;
+    ch = sp; par = row;
+    if (sp < 3) {
+        if (row < 2) return 0;
+        if (row == 2) return 1;
+        return sp == 0 ? 4 : (sp == 2 ? 6 : 5);
+    }
+    ch = row;
+    return row < 3 ? 2 : 3;
 }
 
 __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, const __grid_constant__ TmaMapsX maps,
@@ -1627,12 +1664,12 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
     uint64_t* in_free = bars + 3;    // [3] 3 Vb warps
     uint64_t* hb_full = bars + 6;    // [3] 3 H warps
     uint64_t* hb_free = bars + 9;    // [3] 3 Va + 3 Vb warps
-    uint64_t* hsi_full = bars + 12;  // P_in
-    uint64_t* hsi_free = bars + 13;  // 3 H warps
-    // bars[14]: a plain counter, +1 per H warp per band (P_out may lag behind by any number of bands)
-    const uint32_t hso_count = sbase + kXOffBars + 14 * 8;
-    uint64_t* mu_full = bars + 15;   // [3 channels][2 slots] Vb -> Va
-    uint64_t* mu_free = bars + 21;   // [3 channels][2 slots] Va -> Vb
+    uint64_t* hs_ready = bars + 12;  // [2] P_state: the left strip has published the state record of band j (slot j & 1)
+    uint64_t* hs_free = bars + 15;   // [2] the 3 H warps of that band parity have read it
+    // bars[29..31]: six plain words, bands completed by each H warp [parity][channel] (P_out may lag by any number of bands)
+    const uint32_t hso_done = sbase + kXOffBars + 29 * 8;
+    uint64_t* mu_full = bars + 17;   // [3 channels][2 slots] Vb -> Va
+    uint64_t* mu_free = bars + 23;   // [3 channels][2 slots] Va -> Vb
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
@@ -1643,9 +1680,11 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             mbar_init(&hb_full[i], 3);
             mbar_init(&hb_free[i], 6);
         }
-        mbar_init(hsi_full, 1);
-        mbar_init(hsi_free, 3);
-        bars[14] = 0;
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&hs_ready[i], 1);
+            mbar_init(&hs_free[i], 3);
+        }
+        bars[29] = bars[30] = bars[31] = 0;
         for (int i = 0; i < 6; i++) {
             mbar_init(&mu_full[i], 1);
             mbar_init(&mu_free[i], 1);
@@ -1657,7 +1696,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
         float4* z = reinterpret_cast<float4*>(xs + kXOffHb + 2 * kXHbBytes);
         for (int i = tid; i < (int)(kXHbBytes / 16); i += kXThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         float* ones = reinterpret_cast<float*>(xs + kXOffOnes);
-        if (tid < 80) ones[tid] = 1.0f;
+        if (tid < (int)(kXOnesBytes / 4)) ones[tid] = 1.0f;
     }
     __syncthreads();
 
@@ -1674,35 +1713,36 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
     const int x0 = k * kXC;
     const size_t rec_base = (size_t)frame * g.total_recs + sd.rec0;   // + strip * nb + band
     const bool last_strip = (k == sd.n_strips - 1);
-    int c;
-    const int role = hv_role(warp, c);
+    int c, hpar;
+    const int role = hv_role(warp, c, hpar);
 
     if (role == 3) {
-        // ===== P_in: tile loads + the state the left strip left behind =====
+        // ===== P_tma: tile loads =====
+        if (lane != 0) return;
         const CUtensorMap* map = &maps.xyb_in[s];
+        if (KX_PF > 3)
+            for (int j = 3; j < KX_PF && j < nb; j++) tma_prefetch_4d(map, x0 - kXInLead, j * kXR, 0, frame);
         for (int j = 0; j < nb; j++) {
             const int si = j % 3;
             if (j >= 3) mbar_wait_wd(&in_free[si], (uint32_t)((j / 3 - 1) & 1));
-            if (lane == 0) {
-                mbar_expect_tx(&in_full[si], kXInBytes);
-                tma_load_4d(xs + kXOffIn + si * kXInBytes, map, &in_full[si], x0 - kXInLead, j * kXR, 0, frame);
+            if (KX_EXP_NOTMA) { mbar_arrive(&in_full[si]); continue; }
+            mbar_expect_tx(&in_full[si], kXInBytes);
+            tma_load_4d(xs + kXOffIn + si * kXInBytes, map, &in_full[si], x0 - kXInLead, j * kXR, 0, frame);
+            if (KX_PF > 0 && j + KX_PF < nb) tma_prefetch_4d(map, x0 - kXInLead, (j + KX_PF) * kXR, 0, frame);
+        }
+        return;
+    }
+    if (role == 6) {
+        // ===== P_state: watches the flags of the strip to the left; the H warps then read the record from L2 =====
+        if (k == 0 || KX_EXP_NODEP || lane != 0) return;
+        for (int j = 0; j < nb; j++) {
+            if (j >= 2) mbar_wait_wd(&hs_free[j & 1], (uint32_t)(((j >> 1) - 1) & 1));
+            const uint32_t* fl = a.flags + rec_base + (size_t)(k - 1) * nb + j;
+            for (uint32_t it = 0; ld_acquire_u32(fl) != a.epoch; it++) {
+                __nanosleep(40);
+                if (it > 40000000u) __trap();
             }
-            if (k > 0 && !KX_EXP_NODEP) {
-                if (j >= 1) mbar_wait_wd(hsi_free, (uint32_t)((j - 1) & 1));
-                const size_t rec = rec_base + (size_t)(k - 1) * nb + j;
-                const uint32_t* fl = a.flags + rec;
-                for (uint32_t it = 0; ld_relaxed_u32(fl) != a.epoch; it++) {
-                    __nanosleep(64);
-                    if (it > 40000000u) __trap();
-                }
-                __threadfence();   // acquire: the record was written before the flag
-                const float4* src = reinterpret_cast<const float4*>(a.hstate + rec * kXHsF2);
-                float4* dst = reinterpret_cast<float4*>(xs + kXOffHsIn);
-#pragma unroll
-                for (int i = 0; i < (int)(kXHsBytes / 16 / 32); i++) dst[i * 32 + lane] = __ldcg(src + i * 32 + lane);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(hsi_full);
-            }
+            mbar_arrive(&hs_ready[j & 1]);
         }
         return;
     }
@@ -1710,8 +1750,10 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
         // ===== P_out: releases the right-edge state record of every band (written to global memory by the H warps) =====
         if (last_strip || lane != 0) return;
         for (int j = 0; j < nb; j++) {
-            for (uint32_t it = 0; ld_acquire_cta_shared(hso_count) < 3u * (uint32_t)(j + 1); it++) {
-                __nanosleep(100);
+            const uint32_t w0 = hso_done + (uint32_t)(j & 1) * 12u, need = (uint32_t)(j >> 1) + 1u;
+            for (uint32_t it = 0; ld_acquire_cta_shared(w0) < need || ld_acquire_cta_shared(w0 + 4) < need ||
+                                  ld_acquire_cta_shared(w0 + 8) < need; it++) {
+                __nanosleep(300);
                 if (it > 40000000u) __trap();
             }
             __threadfence();
@@ -1723,34 +1765,48 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
 
     if (role == 0) {
         // ===== H: warp = channel, lane = (quantity, row pair); lanes 30, 31 shadow lane 29 =====
+        // Lane -> (quantity q, row pair rp), chosen with the tile layouts so that every 128-bit shared-memory access of
+        // the scan is conflict-free (4 wavefronts; tools/banksim.py): lanes are grouped by quantity in the order
+        // s11, s12, mu1, s22, mu2; s12 and mu1 walk their row pairs in a rotated order; the planes of the output tile are
+        // stored in the order s11, mu1, s12, s22, mu2 (kXSlot); the rows of ones sit at a per-channel offset.
         const int ch = c, l = lane < 30 ? lane : 29;
-        const int q = l / 6, rp = l - 6 * q;
+        const int qidx = l / 6, jj = l - 6 * qidx;
+        const int q = (0x41320 >> (4 * qidx)) & 7;
+        const int rp = q == 2 ? ((0x541032 >> (4 * jj)) & 7) : (q == 3 ? ((0x325410 >> (4 * jj)) & 7) : jj);
         const int px = (q == 1 || q == 4) ? 3 + ch : ch;
         const int py = (q == 0) ? ch : ((q == 1 || q == 2) ? 3 + ch : -1);
         const uint32_t offxA = (uint32_t)((px * kXInPlane + rp * kXInW) * 4), offxB = offxA + 6 * kXInW * 4;
         const uint32_t offyA = py < 0 ? 0u : (uint32_t)((py * kXInPlane + rp * kXInW) * 4), offyB = offyA + 6 * kXInW * 4;
-        const uint32_t ones = sbase + kXOffOnes;
-        const uint32_t offo = (uint32_t)(((q * 3 + ch) * kXHbPlane + rp * kXHbPitch) * 4);
-        const int hidx = warp * 32 + lane;
+        const uint32_t onesA = sbase + kXOffOnes + (ch == 1 ? 32u : 16u), onesB = sbase + kXOffOnes + (ch == 1 ? 64u : 0u);
+        const uint32_t offo = (uint32_t)(((hv_slot(q) * 3 + ch) * kXHbPlane + rp * kXHbPitch) * 4);
+        const int hidx = ch * 32 + lane;
         for (int j = 0; j < nb; j++) {
+            // every H warp walks ALL the phases of the ring barriers in order (a parity wait must never skip a phase),
+            // but only scans the bands of its own parity
             const int si = j % 3;
+            const bool mine = ((j & 1) == hpar);
             mbar_wait_wd(&in_full[si], (uint32_t)((j / 3) & 1));
-            if (j >= 2) mbar_wait_wd(&hb_free[si], (uint32_t)(((j - 2) / 3) & 1));
             HState2 st;
-            if (k > 0 && !KX_EXP_NODEP) {
-                mbar_wait_wd(hsi_full, (uint32_t)(j & 1));
-                const uint32_t hsb = sbase + kXOffHsIn + (uint32_t)hidx * 8u;
-                st.p1 = lds64(hsb); st.p3 = lds64(hsb + 96 * 8); st.p5 = lds64(hsb + 2 * 96 * 8);
-                st.pp1 = lds64(hsb + 3 * 96 * 8); st.pp3 = lds64(hsb + 4 * 96 * 8); st.pp5 = lds64(hsb + 5 * 96 * 8);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(hsi_free);
-            } else {
-                const f2 z = f2_splat(0.0f);
-                st = HState2{z, z, z, z, z, z};
+            if (mine) {
+                if (k > 0 && !KX_EXP_NODEP) {
+                    mbar_wait_wd(&hs_ready[hpar], (uint32_t)((j >> 1) & 1));
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&hs_free[hpar]);   // P_state may go on to band j + 2
+                    const f2* rec = a.hstate + (rec_base + (size_t)(k - 1) * nb + j) * kXHsF2 + hidx;
+                    st.p1 = ldcg64(rec); st.p3 = ldcg64(rec + 96); st.p5 = ldcg64(rec + 2 * 96);
+                    st.pp1 = ldcg64(rec + 3 * 96); st.pp3 = ldcg64(rec + 4 * 96); st.pp5 = ldcg64(rec + 5 * 96);
+                } else {
+                    const f2 z = f2_splat(0.0f);
+                    st = HState2{z, z, z, z, z, z};
+                }
+            }
+            if (!mine) {
+                if (j >= 2) mbar_wait_wd(&hb_free[si], (uint32_t)(((j - 2) / 3) & 1));
+                continue;
             }
             const uint32_t inb = sbase + kXOffIn + si * kXInBytes;
             const uint32_t axA = inb + offxA, axB = inb + offxB;
-            const uint32_t ayA = py < 0 ? ones : inb + offyA, ayB = py < 0 ? ones : inb + offyB;
+            const uint32_t ayA = py < 0 ? onesA : inb + offyA, ayB = py < 0 ? onesB : inb + offyB;
             uint32_t ao = sbase + kXOffHb + si * kXHbBytes + offo;
             // w[c & 15] = product of tile column c (both rows).  Tile column c is x[n + 4] of output column n = c - 12;
             // the left tap x[n - 6] is tile column c - 10.
@@ -1768,6 +1824,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
                 }
             }
             HGroupLoad nxt = h_load(axA, axB, ayA, ayB, 48);
+            if (j >= 2) mbar_wait_wd(&hb_free[si], (uint32_t)(((j - 2) / 3) & 1));
 #pragma unroll 1
             for (int it = 0; it < KX_EXP_HITERS; it++) {
 #pragma unroll
@@ -1790,10 +1847,10 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             }
             if (last_strip && x0 + kXC > W) {
                 // columns past the right edge hold the filter's ring-out: the V pass must see zeros there
-                float* t0 = reinterpret_cast<float*>(xs + kXOffHb + si * kXHbBytes) + (q * 3 + ch) * kXHbPlane + rp * kXHbPitch;
+                float* t0 = reinterpret_cast<float*>(xs + kXOffHb + si * kXHbBytes) + (hv_slot(q) * 3 + ch) * kXHbPlane + rp * kXHbPitch;
                 for (int cc = W - x0; cc < kXC; cc++) { t0[cc] = 0.0f; t0[6 * kXHbPitch + cc] = 0.0f; }
             }
-            if (!last_strip) {
+            if (!last_strip && !KX_EXP_NOSTATE) {
                 // the state at the right edge of the band goes straight to the record of (strip, band): 256 B per store
                 unsigned long long* rec = reinterpret_cast<unsigned long long*>(a.hstate + (rec_base + (size_t)k * nb + j) * kXHsF2) + hidx;
                 __stcg(rec, st.p1.v); __stcg(rec + 96, st.p3.v); __stcg(rec + 2 * 96, st.p5.v);
@@ -1802,7 +1859,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&hb_full[si]);
-                if (!last_strip) red_release_cta_shared_inc(hso_count);
+                if (!last_strip) st_release_cta_shared(hso_done + (uint32_t)(hpar * 3 + ch) * 4u, (uint32_t)(j >> 1) + 1u);
             }
         }
         return;
@@ -1812,6 +1869,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
     // Va (4 rows at a time through a 2-slot ring); Va runs the s11 / s22 / s12 filters and the SSIM map. =====
     const f2 zero2 = f2_splat(0.0f);
     const uint32_t lane8 = (uint32_t)lane * 8u;
+    constexpr uint32_t kXMu2Off = (uint32_t)((hv_slot(4) - hv_slot(3)) * 3 * kXHbPlane * 4);   // mu2 plane - mu1 plane
     const uint32_t mub = sbase + kXOffMu + (uint32_t)c * 2u * kXMuSlotBytes + lane8;
     uint64_t* const muf = mu_full + 2 * c;
     uint64_t* const mue = mu_free + 2 * c;
@@ -1826,9 +1884,10 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             const int si = j % 3, sp = (j + 2) % 3;
             mbar_wait_wd(&hb_full[si], (uint32_t)((j / 3) & 1));
             mbar_wait_wd(&in_full[si], (uint32_t)((j / 3) & 1));
-            const uint32_t cur = sbase + kXOffHb + si * kXHbBytes + lane8 + (uint32_t)((9 + c) * kXHbPlane * 4);
-            const uint32_t prv = sbase + kXOffHb + sp * kXHbBytes + lane8 + (uint32_t)((9 + c) * kXHbPlane * 4);
+            const uint32_t cur = sbase + kXOffHb + si * kXHbBytes + lane8 + (uint32_t)((hv_slot(3) * 3 + c) * kXHbPlane * 4);
+            const uint32_t prv = sbase + kXOffHb + sp * kXHbBytes + lane8 + (uint32_t)((hv_slot(3) * 3 + c) * kXHbPlane * 4);
             const uint32_t inb = sbase + kXOffIn + si * kXInBytes + kXInLead * 4 + lane8 + (uint32_t)(c * kXInPlane * 4);
+            f2 saved[2][2] = {{zero2, zero2}, {zero2, zero2}};
 #pragma unroll 1
             for (int i4 = 0; i4 < kXR; i4 += kXSub, n++) {
                 const int p = n & 1;
@@ -1842,9 +1901,15 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
                     for (int r = 0; r < KX_EXP_VROWS; r++) {
                         const int i = i4 + r, t = j * kXR + i;
                         const uint32_t a_t = cur + (uint32_t)(i * kXHbPitch * 4);
-                        const uint32_t a_d = i < 10 ? prv + (uint32_t)((i + 2) * kXHbPitch * 4) : cur + (uint32_t)((i - 10) * kXHbPitch * 4);
-                        const f2 m1 = vstep2(stq[0], lds64(a_d), lds64(a_t));
-                        const f2 m2 = vstep2(stq[1], lds64(a_d + 3 * kXHbPlane * 4), lds64(a_t + 3 * kXHbPlane * 4));
+                        // x[t - 10]: rows 0..7 read the previous band's tile, rows 8, 9 the copies taken before that tile
+                        // was handed back (KX_REL), rows 10, 11 this band's tile
+                        const bool from_saved = KX_REL && r < 2 && i4 == 8;
+                        const uint32_t a_d = (i < 10 && !from_saved) ? prv + (uint32_t)((i + 2) * kXHbPitch * 4)
+                                                                     : cur + (uint32_t)((i < 10 ? 0 : i - 10) * kXHbPitch * 4);
+                        f2 d1 = lds64(a_d), d2 = lds64(a_d + kXMu2Off);
+                        if (from_saved) { d1 = saved[r & 1][0]; d2 = saved[r & 1][1]; }
+                        const f2 m1 = vstep2(stq[0], d1, lds64(a_t));
+                        const f2 m2 = vstep2(stq[1], d2, lds64(a_t + kXMu2Off));
                         sts64(mus + (uint32_t)(r * 2 * kXC * 4), m1);
                         sts64(mus + (uint32_t)((r * 2 + 1) * kXC * 4), m2);
                         const f2 fr = fifo_r[r], fd = fifo_d[r];   // XYB of output row t - 4
@@ -1855,16 +1920,24 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
                 };
                 const int t0 = j * kXR + i4;
                 if (t0 >= 4 && t0 + kXSub <= H + 4) rows(std::false_type{}); else rows(std::true_type{});
+                const bool rel = KX_REL ? (i4 == 4) : (i4 == 8);
+                if (KX_REL && rel) {
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        saved[e][0] = lds64(prv + (uint32_t)((10 + e) * kXHbPitch * 4));
+                        saved[e][1] = lds64(prv + (uint32_t)((10 + e) * kXHbPitch * 4 + kXMu2Off));
+                    }
+                }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&muf[p]);
+                if (lane == 0) {
+                    mbar_arrive(&muf[p]);
+                    if (rel) mbar_arrive(&hb_free[sp]);   // the previous band's tile goes back to the H warps
+                }
 #pragma unroll
                 for (int kk = 0; kk < 4; kk++) acc[kk] += (double)f2_hsum(part[kk]);
             }
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&in_free[si]);
-                mbar_arrive(&hb_free[sp]);
-            }
+            if (lane == 0) mbar_arrive(&in_free[si]);
         }
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
@@ -1887,6 +1960,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
         mbar_wait_wd(&hb_full[si], (uint32_t)((j / 3) & 1));
         const uint32_t cur = sbase + kXOffHb + si * kXHbBytes + lane8 + (uint32_t)(c * kXHbPlane * 4);
         const uint32_t prv = sbase + kXOffHb + sp * kXHbBytes + lane8 + (uint32_t)(c * kXHbPlane * 4);
+        f2 saved[2][3] = {{zero2, zero2, zero2}, {zero2, zero2, zero2}};
 #pragma unroll 1
         for (int i4 = 0; i4 < kXR; i4 += kXSub, n++) {
             const int p = n & 1;
@@ -1898,12 +1972,28 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             for (int r = 0; r < KX_EXP_VROWS; r++) {
                 const int i = i4 + r;
                 const uint32_t a_t = cur + (uint32_t)(i * kXHbPitch * 4);
-                const uint32_t a_d = i < 10 ? prv + (uint32_t)((i + 2) * kXHbPitch * 4) : cur + (uint32_t)((i - 10) * kXHbPitch * 4);
+                const bool from_saved = KX_REL && r < 2 && i4 == 8;
+                const uint32_t a_d = (i < 10 && !from_saved) ? prv + (uint32_t)((i + 2) * kXHbPitch * 4)
+                                                             : cur + (uint32_t)((i < 10 ? 0 : i - 10) * kXHbPitch * 4);
 #pragma unroll
                 for (int qi = 0; qi < 3; qi++) {
-                    const uint32_t pl = (uint32_t)(qi * 3 * kXHbPlane * 4);
-                    o[r][qi] = vstep2(stq[qi], lds64(a_d + pl), lds64(a_t + pl));
+                    const uint32_t pl = (uint32_t)(hv_slot(qi) * 3 * kXHbPlane) * 4u;
+                    f2 d = lds64(a_d + pl);
+                    if (from_saved) d = saved[r & 1][qi];
+                    o[r][qi] = vstep2(stq[qi], d, lds64(a_t + pl));
                 }
+            }
+            const bool rel = KX_REL ? (i4 == 4) : (i4 == 8);
+            if (rel) {
+                if (KX_REL) {
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+#pragma unroll
+                        for (int qi = 0; qi < 3; qi++)
+                            saved[e][qi] = lds64(prv + (uint32_t)(((10 + e) * kXHbPitch + hv_slot(qi) * 3 * kXHbPlane) * 4));
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hb_free[sp]);
             }
             mbar_wait_wd(&muf[p], (uint32_t)((n >> 1) & 1));
             const uint32_t mus = mub + (uint32_t)p * kXMuSlotBytes;
@@ -1923,8 +2013,6 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             acc[0] += (double)f2_hsum(part[0]);
             acc[1] += (double)f2_hsum(part[1]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&hb_free[sp]);
     }
 #pragma unroll
     for (int kk = 0; kk < 2; kk++) {

@@ -1615,6 +1615,9 @@ __device__ __forceinline__ void h_products(const HGroupLoad& L, f2 (&w)[16], int
 #ifndef KX_REL
 #define KX_REL 0   // 1: the V warps hand the previous band's tile back after 8 of the 12 rows (0: at the end of the band)
 #endif
+#ifndef KX_VA_EARLYWAIT
+#define KX_VA_EARLYWAIT 0
+#endif
 #ifndef KX_PF
 #define KX_PF 6   // bands of L2 prefetch ahead of the shared-memory ring (0 = off)
 #endif
@@ -1738,10 +1741,11 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
         for (int j = 0; j < nb; j++) {
             if (j >= 2) mbar_wait_wd(&hs_free[j & 1], (uint32_t)(((j >> 1) - 1) & 1));
             const uint32_t* fl = a.flags + rec_base + (size_t)(k - 1) * nb + j;
-            for (uint32_t it = 0; ld_acquire_u32(fl) != a.epoch; it++) {
+            for (uint32_t it = 0; ld_relaxed_u32(fl) != a.epoch; it++) {
                 __nanosleep(40);
                 if (it > 40000000u) __trap();
             }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire: the record was written before the flag
             mbar_arrive(&hs_ready[j & 1]);
         }
         return;
@@ -1964,6 +1968,9 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
 #pragma unroll 1
         for (int i4 = 0; i4 < kXR; i4 += kXSub, n++) {
             const int p = n & 1;
+            // the mu rows of this sub-band first (Vb runs ahead, so this rarely blocks): filters and maps then form one
+            // basic block and the long map chains interleave with the filter steps of the following rows
+            if (KX_VA_EARLYWAIT) mbar_wait_wd(&muf[p], (uint32_t)((n >> 1) & 1));
             f2 o[kXSub][3];
 #pragma unroll
             for (int r = 0; r < kXSub; r++)
@@ -1995,7 +2002,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&hb_free[sp]);
             }
-            mbar_wait_wd(&muf[p], (uint32_t)((n >> 1) & 1));
+            if (!KX_VA_EARLYWAIT) mbar_wait_wd(&muf[p], (uint32_t)((n >> 1) & 1));
             const uint32_t mus = mub + (uint32_t)p * kXMuSlotBytes;
             f2 part[2] = {zero2, zero2};
             auto maps = [&](auto checked) {

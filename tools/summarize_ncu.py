@@ -34,6 +34,6 @@ out += ["", "DRAM bytes per frame pair (read + write): " + ", ".join(f"`{k}` {v/
 open(os.path.join(root, "profiles", f"{tag}_ncu_summary.md"), "w").write("\n".join(out) + "\n")
 tf = os.path.join(root, "profiles", "traffic_r1.json")
 allt = json.load(open(tf)) if os.path.exists(tf) else {}
-allt[workload.split()[0]] = traffic
+allt.setdefault(workload.split()[0], {}).update(traffic)
 json.dump(allt, open(tf, "w"), indent=1)
 print("\n".join(out[-3:]))

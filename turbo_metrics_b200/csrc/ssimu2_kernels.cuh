@@ -1458,6 +1458,12 @@ __global__ void __launch_bounds__(kVTmaThreads, 2) k_vpass(const __grid_constant
 // handed out by an atomic ticket in dependency order (strip-major), so a CTA only ever waits for CTAs that are
 // already running: no deadlock regardless of how many CTAs are resident.
 // ------------------------------------------------------------------------------------------
+#ifndef KX_HSETS
+#define KX_HSETS 2     // H warps per channel taking alternate bands (1: 12-warp CTA, measured 9 % slower)
+#endif
+#ifndef KX_INSLOTS
+#define KX_INSLOTS 3   // depth of the XYB tile ring (2: the Vb warps copy their rows into registers at the start of a band; frees 21 KB, 7-17 % slower)
+#endif
 constexpr int kXR = 12;                                  // rows per band
 constexpr int kXC = kVCols;                              // columns per strip (the strip list is the V pass's)
 constexpr int kXInLead = 8;                              // tile starts at column x0 - 8
@@ -1470,7 +1476,8 @@ constexpr int kXHbPlane = kXR * kXHbPitch + 8;           // 824 floats
 constexpr int kXHbFloats = 15 * kXHbPlane;
 constexpr uint32_t kXHbBytes = kXHbFloats * 4;           // 49440
 constexpr int kXHThreads = 96;
-constexpr int kXWarps = 16;                              // roles by warp id, see k_hv
+constexpr int kXWarps = KX_HSETS == 1 ? 12 : 16;         // roles by warp id, see k_hv
+constexpr int kXNIn = KX_INSLOTS;
 constexpr int kXThreads = kXWarps * 32;
 constexpr int kXHsF2 = 6 * kXHThreads;                   // hand-off record: [6 state words][96 H threads] f2
 constexpr uint32_t kXHsBytes = kXHsF2 * 8;               // 4608
@@ -1478,7 +1485,7 @@ constexpr int kXSub = 4;                                 // rows per mu hand-off
 constexpr int kXMuSlotF = kXSub * 2 * kXC;               // [4 rows][mu1, mu2][64 columns] floats
 constexpr uint32_t kXMuSlotBytes = kXMuSlotF * 4;        // 2048
 constexpr uint32_t kXOffIn = 0;
-constexpr uint32_t kXOffHb = kXOffIn + 3 * kXInBytes;
+constexpr uint32_t kXOffHb = kXOffIn + kXNIn * kXInBytes;
 constexpr uint32_t kXOffMu = kXOffHb + 3 * kXHbBytes;    // [3 channels][2 slots] mu hand-off
 constexpr uint32_t kXOffOnes = (kXOffMu + 6 * kXMuSlotBytes + 127) / 128 * 128;  // rows of ones (second factor of the mu planes)
 constexpr uint32_t kXOnesBytes = 384;
@@ -1609,7 +1616,7 @@ __device__ __forceinline__ void h_products(const HGroupLoad& L, f2 (&w)[16], int
 }
 
 #ifndef KX_MAXNREG
-#define KX_MAXNREG 128
+#define KX_MAXNREG 128   // 16 warps x 128 registers = the whole register file
 #endif
 // timing experiments only (results are wrong unless all are at their defaults)
 #ifndef KX_REL
@@ -1647,6 +1654,13 @@ __device__ __forceinline__ int hv_role(int warp, int& ch, int& par)
     // 0 = H, 1 = Va, 2 = Vb, 3 = P_tma, 4 = P_out, 5 = idle, 6 = P_state
     const int sp = warp & 3, row = warp >> 2;
     ch = sp; par = row;
+#if KX_HSETS == 1
+    //   SP0: H0 Va0 P_out    SP1: H1 Va1 P_state    SP2: H2 Va2 P_tma    SP3: Vb0 Vb1 Vb2
+    par = 0;
+    if (sp < 3) return row == 0 ? 0 : (row == 1 ? 1 : (sp == 0 ? 4 : (sp == 1 ? 6 : 3)));
+    ch = row;
+    return 2;
+#else
     if (sp < 3) {
         if (row < 2) return 0;
         if (row == 2) return 1;
@@ -1654,6 +1668,7 @@ __device__ __forceinline__ int hv_role(int warp, int& ch, int& par)
     }
     ch = row;
     return row < 3 ? 2 : 3;
+#endif
 }
 
 __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, const __grid_constant__ TmaMapsX maps,
@@ -1723,11 +1738,11 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
         // ===== P_tma: tile loads =====
         if (lane != 0) return;
         const CUtensorMap* map = &maps.xyb_in[s];
-        if (KX_PF > 3)
-            for (int j = 3; j < KX_PF && j < nb; j++) tma_prefetch_4d(map, x0 - kXInLead, j * kXR, 0, frame);
+        if (KX_PF > kXNIn)
+            for (int j = kXNIn; j < KX_PF && j < nb; j++) tma_prefetch_4d(map, x0 - kXInLead, j * kXR, 0, frame);
         for (int j = 0; j < nb; j++) {
-            const int si = j % 3;
-            if (j >= 3) mbar_wait_wd(&in_free[si], (uint32_t)((j / 3 - 1) & 1));
+            const int si = j % kXNIn;
+            if (j >= kXNIn) mbar_wait_wd(&in_free[si], (uint32_t)((j / kXNIn - 1) & 1));
             if (KX_EXP_NOTMA) { mbar_arrive(&in_full[si]); continue; }
             mbar_expect_tx(&in_full[si], kXInBytes);
             tma_load_4d(xs + kXOffIn + si * kXInBytes, map, &in_full[si], x0 - kXInLead, j * kXR, 0, frame);
@@ -1787,15 +1802,15 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
         for (int j = 0; j < nb; j++) {
             // every H warp walks ALL the phases of the ring barriers in order (a parity wait must never skip a phase),
             // but only scans the bands of its own parity
-            const int si = j % 3;
-            const bool mine = ((j & 1) == hpar);
-            mbar_wait_wd(&in_full[si], (uint32_t)((j / 3) & 1));
+            const int si = j % 3, sin = j % kXNIn;
+            const bool mine = (KX_HSETS == 1) || ((j & 1) == hpar);
+            mbar_wait_wd(&in_full[sin], (uint32_t)((j / kXNIn) & 1));
             HState2 st;
             if (mine) {
                 if (k > 0 && !KX_EXP_NODEP) {
-                    mbar_wait_wd(&hs_ready[hpar], (uint32_t)((j >> 1) & 1));
+                    mbar_wait_wd(&hs_ready[j & 1], (uint32_t)((j >> 1) & 1));
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&hs_free[hpar]);   // P_state may go on to band j + 2
+                    if (lane == 0) mbar_arrive(&hs_free[j & 1]);   // P_state may go on to band j + 2
                     const f2* rec = a.hstate + (rec_base + (size_t)(k - 1) * nb + j) * kXHsF2 + hidx;
                     st.p1 = ldcg64(rec); st.p3 = ldcg64(rec + 96); st.p5 = ldcg64(rec + 2 * 96);
                     st.pp1 = ldcg64(rec + 3 * 96); st.pp3 = ldcg64(rec + 4 * 96); st.pp5 = ldcg64(rec + 5 * 96);
@@ -1808,7 +1823,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
                 if (j >= 2) mbar_wait_wd(&hb_free[si], (uint32_t)(((j - 2) / 3) & 1));
                 continue;
             }
-            const uint32_t inb = sbase + kXOffIn + si * kXInBytes;
+            const uint32_t inb = sbase + kXOffIn + sin * kXInBytes;
             const uint32_t axA = inb + offxA, axB = inb + offxB;
             const uint32_t ayA = py < 0 ? onesA : inb + offyA, ayB = py < 0 ? onesB : inb + offyB;
             uint32_t ao = sbase + kXOffHb + si * kXHbBytes + offo;
@@ -1863,7 +1878,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&hb_full[si]);
-                if (!last_strip) st_release_cta_shared(hso_done + (uint32_t)(hpar * 3 + ch) * 4u, (uint32_t)(j >> 1) + 1u);
+                if (!last_strip) st_release_cta_shared(hso_done + (uint32_t)((j & 1) * 3 + ch) * 4u, (uint32_t)(j >> 1) + 1u);
             }
         }
         return;
@@ -1885,12 +1900,24 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
         double acc[4] = {0, 0, 0, 0};
         int n = 0;   // sub-band counter
         for (int j = 0; j < nb; j++) {
-            const int si = j % 3, sp = (j + 2) % 3;
+            const int si = j % 3, sp = (j + 2) % 3, sin = j % kXNIn;
             mbar_wait_wd(&hb_full[si], (uint32_t)((j / 3) & 1));
-            mbar_wait_wd(&in_full[si], (uint32_t)((j / 3) & 1));
+            mbar_wait_wd(&in_full[sin], (uint32_t)((j / kXNIn) & 1));
             const uint32_t cur = sbase + kXOffHb + si * kXHbBytes + lane8 + (uint32_t)((hv_slot(3) * 3 + c) * kXHbPlane * 4);
             const uint32_t prv = sbase + kXOffHb + sp * kXHbBytes + lane8 + (uint32_t)((hv_slot(3) * 3 + c) * kXHbPlane * 4);
-            const uint32_t inb = sbase + kXOffIn + si * kXInBytes + kXInLead * 4 + lane8 + (uint32_t)(c * kXInPlane * 4);
+            const uint32_t inb = sbase + kXOffIn + sin * kXInBytes + kXInLead * 4 + lane8 + (uint32_t)(c * kXInPlane * 4);
+#if KX_INSLOTS == 2
+            // a 2-deep XYB ring cannot wait for the V pass: the band's ref / dis rows of this channel move into registers
+            // (a queue the sub-bands pop four rows at a time) and the slot goes straight back to the TMA warp
+            f2 qr[kXR], qd[kXR];
+#pragma unroll
+            for (int i = 0; i < kXR; i++) {
+                qr[i] = lds64(inb + (uint32_t)(i * kXInW * 4));
+                qd[i] = lds64(inb + (uint32_t)((3 * kXInPlane + i * kXInW) * 4));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&in_free[sin]);
+#endif
             f2 saved[2][2] = {{zero2, zero2}, {zero2, zero2}};
 #pragma unroll 1
             for (int i4 = 0; i4 < kXR; i4 += kXSub, n++) {
@@ -1917,8 +1944,13 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
                         sts64(mus + (uint32_t)(r * 2 * kXC * 4), m1);
                         sts64(mus + (uint32_t)((r * 2 + 1) * kXC * 4), m2);
                         const f2 fr = fifo_r[r], fd = fifo_d[r];   // XYB of output row t - 4
+#if KX_INSLOTS == 2
+                        fifo_r[r] = qr[r];
+                        fifo_d[r] = qd[r];
+#else
                         fifo_r[r] = lds64(inb + (uint32_t)(i * kXInW * 4));
                         fifo_d[r] = lds64(inb + (uint32_t)((3 * kXInPlane + i * kXInW) * 4));
+#endif
                         if (!decltype(checked)::value || (t >= 4 && t < H + 4)) edge_maps2(m1, m2, fr, fd, part);
                     }
                 };
@@ -1939,9 +1971,15 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
                 }
 #pragma unroll
                 for (int kk = 0; kk < 4; kk++) acc[kk] += (double)f2_hsum(part[kk]);
+#if KX_INSLOTS == 2
+#pragma unroll
+                for (int i = 0; i + kXSub < kXR; i++) { qr[i] = qr[i + kXSub]; qd[i] = qd[i + kXSub]; }
+#endif
             }
+#if KX_INSLOTS != 2
             __syncwarp();
-            if (lane == 0) mbar_arrive(&in_free[si]);
+            if (lane == 0) mbar_arrive(&in_free[sin]);
+#endif
         }
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {

@@ -9,7 +9,7 @@ SURVEY.md section 8d).  Frames are sharded over the ranks with no data-path coll
 every rank scores its own 300 pairs); only scalar scores leave a GPU.
 
   value      pairs/s with the frames already resident in HBM when the timed region starts
-             (device frames through the C ABI, ssimu2_submit_batch + ssimu2_get_score)
+             (device frames through the C ABI, ssimu2_submit_batch + ssimu2_get_scores)
   e2e        the same metric through the host-frame entry point of the C ABI (ssimu2_submit_host):
              pinned HOST buffers, host->device copies and the score read-back inside the timed region
   roofline   dominant kernel: algorithmic bytes per launch / its CUDA-event duration (events recorded by
@@ -201,12 +201,12 @@ def run_ours(args, rank, world, local_rank):
         return ts
 
     def submit_host():
-        ts = [m.compute_from_cpu(a, b) for a, b in zip(hrefs, hdiss)]
+        ts = m.compute_from_cpu_batch(hrefs, hdiss)
         m.flush()
         return ts
 
     def collect(ts):
-        return [m.get_score(t) for t in ts]
+        return m.get_scores(ts)
 
     def step_device():
         ts = submit_device()

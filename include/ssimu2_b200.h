@@ -106,6 +106,9 @@ int ssimu2_flush(ssimu2_t *h);
 int ssimu2_wait(ssimu2_t *h, uint64_t ticket);
 /* Score of a ticket (flushes and waits as needed).  100 = identical, unbounded below. */
 int ssimu2_get_score(ssimu2_t *h, uint64_t ticket, double *score);
+/* The scores of n consecutive tickets in submission order: the per-frame score stream of the CLI loop
+ * (turbo-metrics-cli/src/main.rs:307-322) in one call. */
+int ssimu2_get_scores(ssimu2_t *h, uint64_t first_ticket, uint32_t n, double *scores);
 /* The 108 per-scale / per-channel norms in WEIGHT order:
  * index = channel*36 + scale*6 + norm*3 + map, norm in {L1,L4}, map in {ssim, artifact, detail}. */
 int ssimu2_get_norms(ssimu2_t *h, uint64_t ticket, double *norms108);
@@ -123,6 +126,10 @@ int ssimu2_stream_wait(ssimu2_t *h, uint64_t ticket, void *stream);
  * enqueues the pair.  frame_bytes = bytes to copy starting at plane[0]. */
 int ssimu2_submit_host(ssimu2_t *h, const ssimu2_frame *ref, const ssimu2_frame *dis, size_t frame_bytes,
                        uint64_t *ticket);
+/* n host pairs at once (all frames share frame_bytes); pair i has *first_ticket + i.  The frame loop of a caller that
+ * decodes on the CPU (turbo-metrics/src/input_image.rs:206-228 copies each frame itself) becomes one call per chunk. */
+int ssimu2_submit_host_batch(ssimu2_t *h, uint32_t n, const ssimu2_frame *refs, const ssimu2_frame *diss,
+                             size_t frame_bytes, uint64_t *first_ticket);
 
 /* ---- results on the device ----------------------------------------------------------- */
 /* Device address of the f64 score ring (one entry per ticket, index ticket % capacity). */

@@ -296,6 +296,13 @@ def test_host_frames_entry_point(oracle):
         ts = [m.compute_from_cpu(tm.DeviceFrame.yuv420(rp, pitch, ch), tm.DeviceFrame.yuv420(dp, pitch, ch)) for _ in range(5)]
         scores = [m.get_score(t) for t in ts]
         _assert_norms(m.get_norms(ts[-1]), no, scores[-1], so)
+        # the batched entry point (ssimu2_submit_host_batch): same tickets-in-order contract, same scores
+        fr, fd = tm.DeviceFrame.yuv420(rp, pitch, ch), tm.DeviceFrame.yuv420(dp, pitch, ch)
+        tb = m.compute_from_cpu_batch([fr] * 5, [fd] * 5)
+        assert list(tb) == list(range(ts[-1] + 1, ts[-1] + 6))
+        assert all(m.get_score(t) == scores[0] for t in tb)
+        tb2 = m.compute_from_cpu_batch([fr] * 3, [fd] * 3)
+        np.testing.assert_array_equal(m.get_scores(tb2), np.full(3, scores[0]))
     assert all(s == scores[0] for s in scores)
 
 

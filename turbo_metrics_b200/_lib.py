@@ -44,10 +44,12 @@ SYMBOLS = {
     "ssimu2_flush": (C.c_int, [_P]),
     "ssimu2_wait": (C.c_int, [_P, C.c_uint64]),
     "ssimu2_get_score": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_double)]),
+    "ssimu2_get_scores": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.POINTER(C.c_double)]),
     "ssimu2_get_norms": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_double)]),
     "ssimu2_compute_sync": (C.c_int, [_P, _FP, _FP, _P, C.POINTER(C.c_double)]),
     "ssimu2_stream_wait": (C.c_int, [_P, C.c_uint64, _P]),
     "ssimu2_submit_host": (C.c_int, [_P, _FP, _FP, C.c_size_t, C.POINTER(C.c_uint64)]),
+    "ssimu2_submit_host_batch": (C.c_int, [_P, C.c_uint32, _FP, _FP, C.c_size_t, C.POINTER(C.c_uint64)]),
     "ssimu2_scores_device": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ssimu2_get_info": (C.c_int, [_P, C.POINTER(Info)]),
     "ssimu2_debug_read": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_size_t]),

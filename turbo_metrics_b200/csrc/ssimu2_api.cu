@@ -810,6 +810,18 @@ int ssimu2_submit_host(ssimu2_t* h, const ssimu2_frame* ref, const ssimu2_frame*
     return finish_pair(h);
 }
 
+int ssimu2_submit_host_batch(ssimu2_t* h, uint32_t n, const ssimu2_frame* refs, const ssimu2_frame* diss, size_t frame_bytes,
+                             uint64_t* first_ticket)
+{
+    if (!h || (n && (!refs || !diss))) return SSIMU2_E_INVALID;
+    if (first_ticket) *first_ticket = h->next_ticket;
+    for (uint32_t i = 0; i < n; i++) {
+        int r = ssimu2_submit_host(h, &refs[i], &diss[i], frame_bytes, nullptr);
+        if (r) return r;
+    }
+    return SSIMU2_OK;
+}
+
 int ssimu2_flush(ssimu2_t* h)
 {
     if (!h) return SSIMU2_E_INVALID;
@@ -856,6 +868,17 @@ int ssimu2_get_score(ssimu2_t* h, uint64_t ticket, double* score)
     int r = ssimu2_wait(h, ticket);
     if (r) return r;
     *score = h->res_scores[ticket % kResultCap];
+    return SSIMU2_OK;
+}
+
+int ssimu2_get_scores(ssimu2_t* h, uint64_t first_ticket, uint32_t n, double* scores)
+{
+    if (!h || (n && !scores)) return SSIMU2_E_INVALID;
+    for (uint32_t i = 0; i < n; i++) {
+        int r = ssimu2_wait(h, first_ticket + i);
+        if (r) return r;
+        scores[i] = h->res_scores[(first_ticket + i) % kResultCap];
+    }
     return SSIMU2_OK;
 }
 

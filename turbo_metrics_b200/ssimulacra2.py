@@ -175,6 +175,18 @@ class Ssimulacra2:
         self._keep[t.value] = (ref, dis)
         return t.value
 
+    def compute_from_cpu_batch(self, refs: Sequence[DeviceFrame], diss: Sequence[DeviceFrame]) -> range:
+        """n host pairs in one call (`ssimu2_submit_host_batch`)."""
+        n = len(refs)
+        assert n == len(diss) and n > 0 and all(f.nbytes == refs[0].nbytes for f in list(refs) + list(diss))
+        A = (Frame * n)(*[f.c() for f in refs])
+        B = (Frame * n)(*[f.c() for f in diss])
+        t = C.c_uint64()
+        check(_lib.lib().ssimu2_submit_host_batch(self._h, n, A, B, refs[0].nbytes, C.byref(t)), "ssimu2_submit_host_batch")
+        for i in range(n):
+            self._keep[t.value + i] = (refs[i], diss[i])
+        return range(t.value, t.value + n)
+
     def flush(self):
         check(_lib.lib().ssimu2_flush(self._h), "ssimu2_flush")
 
@@ -186,6 +198,16 @@ class Ssimulacra2:
         check(_lib.lib().ssimu2_get_score(self._h, ticket, C.byref(s)), "ssimu2_get_score")
         self._release(ticket)
         return s.value
+
+    def get_scores(self, tickets: range) -> np.ndarray:
+        """Scores of consecutive tickets (`ssimu2_get_scores`): the per-frame score stream in submission order."""
+        n = len(tickets)
+        out = np.zeros(n, np.float64)
+        if n:
+            assert tickets.step == 1
+            check(_lib.lib().ssimu2_get_scores(self._h, tickets.start, n, out.ctypes.data_as(C.POINTER(C.c_double))), "ssimu2_get_scores")
+            self._release(tickets[-1])
+        return out
 
     def get_norms(self, ticket: int) -> np.ndarray:
         out = np.zeros(108, np.float64)

@@ -1626,7 +1626,7 @@ __device__ __forceinline__ void h_products(const HGroupLoad& L, f2 (&w)[16], int
 #define KX_VA_EARLYWAIT 0
 #endif
 #ifndef KX_PF
-#define KX_PF 6   // bands of L2 prefetch ahead of the shared-memory ring (0 = off)
+#define KX_PF 0   // bands of L2 prefetch ahead of the shared-memory ring (0 = off; 6 and 12 measured no faster)
 #endif
 #ifndef KX_EXP_NOSTATE
 #define KX_EXP_NOSTATE 0
@@ -1927,16 +1927,20 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
                 f2 part[4] = {zero2, zero2, zero2, zero2};
                 // rows of one sub-band; CHECKED only for the sub-bands that straddle output rows -4..-1 or H..: the
                 // common path has no branch per row, so the four rows' map chains interleave
+                // delayed-tap rows of the sub-band: previous tile rows i4 + 2 .. i4 + 5, except that for i4 = 8 the last two
+                // (band rows 10, 11) are rows 0, 1 of this band's tile
+                const uint32_t cur_i4 = cur + (uint32_t)(i4 * kXHbPitch * 4);
+                const uint32_t d_lo = prv + (uint32_t)((i4 + 2) * kXHbPitch * 4);
+                const uint32_t d_hi = i4 == 8 ? cur - (uint32_t)(2 * kXHbPitch * 4) : d_lo;
                 auto rows = [&](auto checked) {
 #pragma unroll
                     for (int r = 0; r < KX_EXP_VROWS; r++) {
                         const int i = i4 + r, t = j * kXR + i;
-                        const uint32_t a_t = cur + (uint32_t)(i * kXHbPitch * 4);
-                        // x[t - 10]: rows 0..7 read the previous band's tile, rows 8, 9 the copies taken before that tile
-                        // was handed back (KX_REL), rows 10, 11 this band's tile
+                        const uint32_t a_t = cur_i4 + (uint32_t)(r * kXHbPitch * 4);
+                        // x[t - 10]: rows 0..9 of a band read the previous band's tile (rows 8, 9 the copies taken before
+                        // that tile was handed back, if KX_REL), rows 10, 11 this band's tile
                         const bool from_saved = KX_REL && r < 2 && i4 == 8;
-                        const uint32_t a_d = (i < 10 && !from_saved) ? prv + (uint32_t)((i + 2) * kXHbPitch * 4)
-                                                                     : cur + (uint32_t)((i < 10 ? 0 : i - 10) * kXHbPitch * 4);
+                        const uint32_t a_d = (from_saved ? cur : (r < 2 ? d_lo : d_hi)) + (uint32_t)(r * kXHbPitch * 4);
                         f2 d1 = lds64(a_d), d2 = lds64(a_d + kXMu2Off);
                         if (from_saved) { d1 = saved[r & 1][0]; d2 = saved[r & 1][1]; }
                         const f2 m1 = vstep2(stq[0], d1, lds64(a_t));
@@ -2013,13 +2017,14 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
 #pragma unroll
             for (int r = 0; r < kXSub; r++)
                 for (int qi = 0; qi < 3; qi++) o[r][qi] = zero2;
+            const uint32_t cur_i4 = cur + (uint32_t)(i4 * kXHbPitch * 4);
+            const uint32_t d_lo = prv + (uint32_t)((i4 + 2) * kXHbPitch * 4);
+            const uint32_t d_hi = i4 == 8 ? cur - (uint32_t)(2 * kXHbPitch * 4) : d_lo;
 #pragma unroll
             for (int r = 0; r < KX_EXP_VROWS; r++) {
-                const int i = i4 + r;
-                const uint32_t a_t = cur + (uint32_t)(i * kXHbPitch * 4);
+                const uint32_t a_t = cur_i4 + (uint32_t)(r * kXHbPitch * 4);
                 const bool from_saved = KX_REL && r < 2 && i4 == 8;
-                const uint32_t a_d = (i < 10 && !from_saved) ? prv + (uint32_t)((i + 2) * kXHbPitch * 4)
-                                                             : cur + (uint32_t)((i < 10 ? 0 : i - 10) * kXHbPitch * 4);
+                const uint32_t a_d = (from_saved ? cur : (r < 2 ? d_lo : d_hi)) + (uint32_t)(r * kXHbPitch * 4);
 #pragma unroll
                 for (int qi = 0; qi < 3; qi++) {
                     const uint32_t pl = (uint32_t)(hv_slot(qi) * 3 * kXHbPlane) * 4u;

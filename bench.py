@@ -58,7 +58,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", os.environ.get("BENCH_SMI_MS", "100")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -195,15 +195,13 @@ def run_ours(args, rank, world, local_rank):
     # A step = submit 300 pairs, then fetch their scores.  Like the reference's frame loop (compute() is asynchronous,
     # get_score() comes later), the timed loop fetches the scores of step i after step i+1 has been submitted, so the
     # batch ring never drains between steps; every submit and every fetch of the K steps is inside the timed region.
+    # no flush per step: a partial last batch is completed by the first pairs of the next step (ssimu2_get_scores flushes
+    # whatever is still pending when the last step is collected)
     def submit_device():
-        ts = m.compute_batch(refs, diss, stream)
-        m.flush()
-        return ts
+        return m.compute_batch(refs, diss, stream)
 
     def submit_host():
-        ts = m.compute_from_cpu_batch(hrefs, hdiss)
-        m.flush()
-        return ts
+        return m.compute_from_cpu_batch(hrefs, hdiss)
 
     def collect(ts):
         return m.get_scores(ts)
@@ -258,7 +256,7 @@ def run_ours(args, rank, world, local_rank):
     l0 = m.info().kernel_launches
     m.kernel_ms(reset=True)
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("BENCH_NO_CLOCKS"):
         sampler.start()
     ms = timed(submit_device, args.steps)
     timing = dict(timed.last)

@@ -1501,6 +1501,9 @@ static_assert(kXR % kXSub == 0, "k_hv sub-bands");
 #ifndef KX_SPIN
 #define KX_SPIN 0
 #endif
+#ifndef KX_WAIT_NS
+#define KX_WAIT_NS 0   // extra back-off between failed mbarrier try_waits (the hardware suspend hint returns early)
+#endif
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity)
 {
     const uint32_t a = smem_u32(bar);
@@ -1532,6 +1535,7 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity)
             : "r"(a), "r"(parity), "r"(20000u)
             : "memory");
         if (ok) return;
+        if (KX_WAIT_NS > 0) __nanosleep(KX_WAIT_NS);
         if (it > 400000u) __trap();
     }
 #endif

@@ -1461,9 +1461,6 @@ __global__ void __launch_bounds__(kVTmaThreads, 2) k_vpass(const __grid_constant
 #ifndef KX_HSETS
 #define KX_HSETS 2     // H warps per channel taking alternate bands (1: 12-warp CTA, measured 9 % slower)
 #endif
-#ifndef KX_INSLOTS
-#define KX_INSLOTS 3   // depth of the XYB tile ring (2: the Vb warps copy their rows into registers at the start of a band; frees 21 KB, 7-17 % slower)
-#endif
 constexpr int kXR = 12;                                  // rows per band
 constexpr int kXC = kVCols;                              // columns per strip (the strip list is the V pass's)
 constexpr int kXInLead = 8;                              // tile starts at column x0 - 8
@@ -1477,7 +1474,7 @@ constexpr int kXHbFloats = 15 * kXHbPlane;
 constexpr uint32_t kXHbBytes = kXHbFloats * 4;           // 49440
 constexpr int kXHThreads = 96;
 constexpr int kXWarps = KX_HSETS == 1 ? 12 : 16;         // roles by warp id, see k_hv
-constexpr int kXNIn = KX_INSLOTS;
+constexpr int kXNIn = 3;                                 // depth of the XYB tile ring
 constexpr int kXThreads = kXWarps * 32;
 constexpr int kXHsF2 = 6 * kXHThreads;                   // hand-off record: [6 state words][96 H threads] f2
 constexpr uint32_t kXHsBytes = kXHsF2 * 8;               // 4608
@@ -1623,12 +1620,6 @@ __device__ __forceinline__ void h_products(const HGroupLoad& L, f2 (&w)[16], int
 #define KX_MAXNREG 128   // 16 warps x 128 registers = the whole register file
 #endif
 // timing experiments only (results are wrong unless all are at their defaults)
-#ifndef KX_REL
-#define KX_REL 0   // 1: the V warps hand the previous band's tile back after 8 of the 12 rows (0: at the end of the band)
-#endif
-#ifndef KX_VA_EARLYWAIT
-#define KX_VA_EARLYWAIT 0
-#endif
 #ifndef KX_PF
 #define KX_PF 0   // bands of L2 prefetch ahead of the shared-memory ring (0 = off; 6 and 12 measured no faster)
 #endif
@@ -1889,7 +1880,9 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
     }
 
     // ===== V: lane = column pair.  Vb runs the mu1 / mu2 filters and the edge maps and hands the blurred mu rows to
-    // Va (4 rows at a time through a 2-slot ring); Va runs the s11 / s22 / s12 filters and the SSIM map. =====
+    // Va (4 rows at a time through a 2-slot ring); Va runs the s11 / s22 / s12 filters and the SSIM map.
+    // A filter step for input row t = 12 j + i reads x[t] (row i of this band's tile) and x[t - 10] (10 rows up: row i + 2
+    // of the previous band's tile for i < 10, else row i - 10 of this one) and yields output row t - 4. =====
     const f2 zero2 = f2_splat(0.0f);
     const uint32_t lane8 = (uint32_t)lane * 8u;
     constexpr uint32_t kXMu2Off = (uint32_t)((hv_slot(4) - hv_slot(3)) * 3 * kXHbPlane * 4);   // mu2 plane - mu1 plane
@@ -1904,90 +1897,54 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
         double acc[4] = {0, 0, 0, 0};
         int n = 0;   // sub-band counter
         for (int j = 0; j < nb; j++) {
-            const int si = j % 3, sp = (j + 2) % 3, sin = j % kXNIn;
+            const int si = j % 3, sp = (j + 2) % 3;
             mbar_wait_wd(&hb_full[si], (uint32_t)((j / 3) & 1));
-            mbar_wait_wd(&in_full[sin], (uint32_t)((j / kXNIn) & 1));
+            mbar_wait_wd(&in_full[si], (uint32_t)((j / 3) & 1));
             const uint32_t cur = sbase + kXOffHb + si * kXHbBytes + lane8 + (uint32_t)((hv_slot(3) * 3 + c) * kXHbPlane * 4);
             const uint32_t prv = sbase + kXOffHb + sp * kXHbBytes + lane8 + (uint32_t)((hv_slot(3) * 3 + c) * kXHbPlane * 4);
-            const uint32_t inb = sbase + kXOffIn + sin * kXInBytes + kXInLead * 4 + lane8 + (uint32_t)(c * kXInPlane * 4);
-#if KX_INSLOTS == 2
-            // a 2-deep XYB ring cannot wait for the V pass: the band's ref / dis rows of this channel move into registers
-            // (a queue the sub-bands pop four rows at a time) and the slot goes straight back to the TMA warp
-            f2 qr[kXR], qd[kXR];
-#pragma unroll
-            for (int i = 0; i < kXR; i++) {
-                qr[i] = lds64(inb + (uint32_t)(i * kXInW * 4));
-                qd[i] = lds64(inb + (uint32_t)((3 * kXInPlane + i * kXInW) * 4));
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&in_free[sin]);
-#endif
-            f2 saved[2][2] = {{zero2, zero2}, {zero2, zero2}};
+            const uint32_t inb = sbase + kXOffIn + si * kXInBytes + kXInLead * 4 + lane8 + (uint32_t)(c * kXInPlane * 4);
 #pragma unroll 1
             for (int i4 = 0; i4 < kXR; i4 += kXSub, n++) {
                 const int p = n & 1;
                 if (n >= 2) mbar_wait_wd(&mue[p], (uint32_t)(((n >> 1) - 1) & 1));
                 const uint32_t mus = mub + (uint32_t)p * kXMuSlotBytes;
                 f2 part[4] = {zero2, zero2, zero2, zero2};
-                // rows of one sub-band; CHECKED only for the sub-bands that straddle output rows -4..-1 or H..: the
-                // common path has no branch per row, so the four rows' map chains interleave
                 // delayed-tap rows of the sub-band: previous tile rows i4 + 2 .. i4 + 5, except that for i4 = 8 the last two
-                // (band rows 10, 11) are rows 0, 1 of this band's tile
+                // (band rows 10, 11) are rows 0, 1 of this band's tile.  Formed once per sub-band: the V warps are the
+                // busiest of the kernel and every integer instruction per row shows (-3 %).
                 const uint32_t cur_i4 = cur + (uint32_t)(i4 * kXHbPitch * 4);
                 const uint32_t d_lo = prv + (uint32_t)((i4 + 2) * kXHbPitch * 4);
                 const uint32_t d_hi = i4 == 8 ? cur - (uint32_t)(2 * kXHbPitch * 4) : d_lo;
+                // rows of one sub-band; CHECKED only for the sub-bands that straddle output rows -4..-1 or H..: the
+                // common path has no branch per row, so the four rows' map chains interleave
                 auto rows = [&](auto checked) {
 #pragma unroll
                     for (int r = 0; r < KX_EXP_VROWS; r++) {
                         const int i = i4 + r, t = j * kXR + i;
                         const uint32_t a_t = cur_i4 + (uint32_t)(r * kXHbPitch * 4);
-                        // x[t - 10]: rows 0..9 of a band read the previous band's tile (rows 8, 9 the copies taken before
-                        // that tile was handed back, if KX_REL), rows 10, 11 this band's tile
-                        const bool from_saved = KX_REL && r < 2 && i4 == 8;
-                        const uint32_t a_d = (from_saved ? cur : (r < 2 ? d_lo : d_hi)) + (uint32_t)(r * kXHbPitch * 4);
-                        f2 d1 = lds64(a_d), d2 = lds64(a_d + kXMu2Off);
-                        if (from_saved) { d1 = saved[r & 1][0]; d2 = saved[r & 1][1]; }
-                        const f2 m1 = vstep2(stq[0], d1, lds64(a_t));
-                        const f2 m2 = vstep2(stq[1], d2, lds64(a_t + kXMu2Off));
+                        const uint32_t a_d = (r < 2 ? d_lo : d_hi) + (uint32_t)(r * kXHbPitch * 4);
+                        const f2 m1 = vstep2(stq[0], lds64(a_d), lds64(a_t));
+                        const f2 m2 = vstep2(stq[1], lds64(a_d + kXMu2Off), lds64(a_t + kXMu2Off));
                         sts64(mus + (uint32_t)(r * 2 * kXC * 4), m1);
                         sts64(mus + (uint32_t)((r * 2 + 1) * kXC * 4), m2);
                         const f2 fr = fifo_r[r], fd = fifo_d[r];   // XYB of output row t - 4
-#if KX_INSLOTS == 2
-                        fifo_r[r] = qr[r];
-                        fifo_d[r] = qd[r];
-#else
                         fifo_r[r] = lds64(inb + (uint32_t)(i * kXInW * 4));
                         fifo_d[r] = lds64(inb + (uint32_t)((3 * kXInPlane + i * kXInW) * 4));
-#endif
                         if (!decltype(checked)::value || (t >= 4 && t < H + 4)) edge_maps2(m1, m2, fr, fd, part);
                     }
                 };
                 const int t0 = j * kXR + i4;
                 if (t0 >= 4 && t0 + kXSub <= H + 4) rows(std::false_type{}); else rows(std::true_type{});
-                const bool rel = KX_REL ? (i4 == 4) : (i4 == 8);
-                if (KX_REL && rel) {
-#pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        saved[e][0] = lds64(prv + (uint32_t)((10 + e) * kXHbPitch * 4));
-                        saved[e][1] = lds64(prv + (uint32_t)((10 + e) * kXHbPitch * 4 + kXMu2Off));
-                    }
-                }
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&muf[p]);
-                    if (rel) mbar_arrive(&hb_free[sp]);   // the previous band's tile goes back to the H warps
-                }
+                if (lane == 0) mbar_arrive(&muf[p]);
 #pragma unroll
                 for (int kk = 0; kk < 4; kk++) acc[kk] += (double)f2_hsum(part[kk]);
-#if KX_INSLOTS == 2
-#pragma unroll
-                for (int i = 0; i + kXSub < kXR; i++) { qr[i] = qr[i + kXSub]; qd[i] = qd[i + kXSub]; }
-#endif
             }
-#if KX_INSLOTS != 2
             __syncwarp();
-            if (lane == 0) mbar_arrive(&in_free[sin]);
-#endif
+            if (lane == 0) {
+                mbar_arrive(&in_free[si]);
+                mbar_arrive(&hb_free[sp]);   // the previous band's tile goes back to the H warps
+            }
         }
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
@@ -2010,13 +1967,9 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
         mbar_wait_wd(&hb_full[si], (uint32_t)((j / 3) & 1));
         const uint32_t cur = sbase + kXOffHb + si * kXHbBytes + lane8 + (uint32_t)(c * kXHbPlane * 4);
         const uint32_t prv = sbase + kXOffHb + sp * kXHbBytes + lane8 + (uint32_t)(c * kXHbPlane * 4);
-        f2 saved[2][3] = {{zero2, zero2, zero2}, {zero2, zero2, zero2}};
 #pragma unroll 1
         for (int i4 = 0; i4 < kXR; i4 += kXSub, n++) {
             const int p = n & 1;
-            // the mu rows of this sub-band first (Vb runs ahead, so this rarely blocks): filters and maps then form one
-            // basic block and the long map chains interleave with the filter steps of the following rows
-            if (KX_VA_EARLYWAIT) mbar_wait_wd(&muf[p], (uint32_t)((n >> 1) & 1));
             f2 o[kXSub][3];
 #pragma unroll
             for (int r = 0; r < kXSub; r++)
@@ -2027,29 +1980,18 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
 #pragma unroll
             for (int r = 0; r < KX_EXP_VROWS; r++) {
                 const uint32_t a_t = cur_i4 + (uint32_t)(r * kXHbPitch * 4);
-                const bool from_saved = KX_REL && r < 2 && i4 == 8;
-                const uint32_t a_d = (from_saved ? cur : (r < 2 ? d_lo : d_hi)) + (uint32_t)(r * kXHbPitch * 4);
+                const uint32_t a_d = (r < 2 ? d_lo : d_hi) + (uint32_t)(r * kXHbPitch * 4);
 #pragma unroll
                 for (int qi = 0; qi < 3; qi++) {
                     const uint32_t pl = (uint32_t)(hv_slot(qi) * 3 * kXHbPlane) * 4u;
-                    f2 d = lds64(a_d + pl);
-                    if (from_saved) d = saved[r & 1][qi];
-                    o[r][qi] = vstep2(stq[qi], d, lds64(a_t + pl));
+                    o[r][qi] = vstep2(stq[qi], lds64(a_d + pl), lds64(a_t + pl));
                 }
             }
-            const bool rel = KX_REL ? (i4 == 4) : (i4 == 8);
-            if (rel) {
-                if (KX_REL) {
-#pragma unroll
-                    for (int e = 0; e < 2; e++)
-#pragma unroll
-                        for (int qi = 0; qi < 3; qi++)
-                            saved[e][qi] = lds64(prv + (uint32_t)(((10 + e) * kXHbPitch + hv_slot(qi) * 3 * kXHbPlane) * 4));
-                }
+            if (i4 == kXR - kXSub) {   // last read of the previous band's tile
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&hb_free[sp]);
             }
-            if (!KX_VA_EARLYWAIT) mbar_wait_wd(&muf[p], (uint32_t)((n >> 1) & 1));
+            mbar_wait_wd(&muf[p], (uint32_t)((n >> 1) & 1));
             const uint32_t mus = mub + (uint32_t)p * kXMuSlotBytes;
             f2 part[2] = {zero2, zero2};
             auto maps = [&](auto checked) {

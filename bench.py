@@ -313,7 +313,8 @@ def run_ours(args, rank, world, local_rank):
             "pipeline": {"alg_bytes_per_pair": alg_bytes, "achieved": pipeline_gbs, "frac": pipeline_gbs / peak,
                          "note": "B_alg (SURVEY 8d) x pairs/s per GPU / peak"},
             "note": "B_alg is the two-global-pass model of SURVEY 8d; k_hv keeps the 60 B/px intermediate on chip, so its real "
-                    "DRAM traffic (traffic) is far below its algorithmic bytes and the kernel is FP32-pipe bound, not HBM bound"}
+                    "DRAM traffic (traffic) is far below its algorithmic bytes; the kernel is held by the FP32 pipe, the shared-memory pipe "
+                    "and the issue rate at ~60 % each (DESIGN.md section 4 / 8), not by HBM"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic_r1.json")
     if os.path.exists(traffic_file):
         tr = {k: v for k, v in json.load(open(traffic_file)).get(args.workload, {}).items()}

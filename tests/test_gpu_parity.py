@@ -234,7 +234,7 @@ def test_pipelines_agree(oracle, w, h):
     for i in range(n):
         for pl in ("fh", "split"):
             assert abs(out["hv"][i][0] - out[pl][i][0]) < 1e-6
-            np.testing.assert_allclose(out["hv"][i][1], out[pl][i][1], rtol=1e-7, atol=1e-12)
+            np.testing.assert_allclose(out["hv"][i][1], out[pl][i][1], rtol=5e-7, atol=1e-12)
 
 
 def test_identical_frames_score_100():
@@ -388,4 +388,4 @@ def test_strip_handoff_is_race_free_under_load():
         ts = [m.compute(F(fr[i][0]), F(fr[i][1])) for i in range(nd)]
         for i, t in enumerate(ts):
             assert abs(m.get_score(t) - s[i]) < 1e-6
-            np.testing.assert_allclose(m.get_norms(t), nrm[i], rtol=1e-7, atol=1e-12)
+            np.testing.assert_allclose(m.get_norms(t), nrm[i], rtol=5e-7, atol=1e-12)

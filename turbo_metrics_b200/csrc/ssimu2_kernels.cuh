@@ -1839,14 +1839,16 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             }
             HGroupLoad nxt = h_load(axA, axB, ayA, ayB, 48);
             if (j >= 2) mbar_wait_wd(&hb_free[si], (uint32_t)(((j - 2) / 3) & 1));
+            uint32_t axI = axA, ayI = ayA, ayIB = ayB;
 #pragma unroll 1
-            for (int it = 0; it < KX_EXP_HITERS; it++) {
+            for (int it = 0; it < KX_EXP_HITERS; it++, axI += 64, ayI += 64, ayIB += 64) {
 #pragma unroll
                 for (int gg = 0; gg < 4; gg++) {
                     const HGroupLoad cur = nxt;
-                    // prefetch the next group's operands before this group's 4 steps (the last one re-reads in range)
-                    const int gnext = 4 * it + gg + 4;   // tile group index of the next load (3 .. 18)
-                    nxt = h_load(axA, axB, ayA, ayB, (uint32_t)(gnext < 19 ? gnext : 18) * 16u);
+                    // prefetch the next group's operands before this group's 4 steps.  The very last prefetch (group 19) lies
+                    // one group past the tile row: it stays inside shared memory, is never used, and leaving it unclamped keeps
+                    // every offset of the loop body a compile-time immediate
+                    nxt = h_load(axI, axI + 6 * kXInW * 4, ayI, ayIB, (uint32_t)(gg + 4) * 16u);
                     h_products(cur, w, 12 + 4 * gg);
                     float oa[4], ob[4];
 #pragma unroll
@@ -1903,12 +1905,12 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             const uint32_t cur = sbase + kXOffHb + si * kXHbBytes + lane8 + (uint32_t)((hv_slot(3) * 3 + c) * kXHbPlane * 4);
             const uint32_t prv = sbase + kXOffHb + sp * kXHbBytes + lane8 + (uint32_t)((hv_slot(3) * 3 + c) * kXHbPlane * 4);
             const uint32_t inb = sbase + kXOffIn + si * kXInBytes + kXInLead * 4 + lane8 + (uint32_t)(c * kXInPlane * 4);
+            f2 part[4] = {zero2, zero2, zero2, zero2};   // f32 sums of one band (12 rows x 2 columns), then f64
 #pragma unroll 1
             for (int i4 = 0; i4 < kXR; i4 += kXSub, n++) {
                 const int p = n & 1;
                 if (n >= 2) mbar_wait_wd(&mue[p], (uint32_t)(((n >> 1) - 1) & 1));
                 const uint32_t mus = mub + (uint32_t)p * kXMuSlotBytes;
-                f2 part[4] = {zero2, zero2, zero2, zero2};
                 // delayed-tap rows of the sub-band: previous tile rows i4 + 2 .. i4 + 5, except that for i4 = 8 the last two
                 // (band rows 10, 11) are rows 0, 1 of this band's tile.  Formed once per sub-band: the V warps are the
                 // busiest of the kernel and every integer instruction per row shows (-3 %).
@@ -1937,9 +1939,9 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
                 if (t0 >= 4 && t0 + kXSub <= H + 4) rows(std::false_type{}); else rows(std::true_type{});
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&muf[p]);
-#pragma unroll
-                for (int kk = 0; kk < 4; kk++) acc[kk] += (double)f2_hsum(part[kk]);
             }
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) acc[kk] += (double)f2_hsum(part[kk]);
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&in_free[si]);
@@ -1967,6 +1969,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
         mbar_wait_wd(&hb_full[si], (uint32_t)((j / 3) & 1));
         const uint32_t cur = sbase + kXOffHb + si * kXHbBytes + lane8 + (uint32_t)(c * kXHbPlane * 4);
         const uint32_t prv = sbase + kXOffHb + sp * kXHbBytes + lane8 + (uint32_t)(c * kXHbPlane * 4);
+        f2 part[2] = {zero2, zero2};
 #pragma unroll 1
         for (int i4 = 0; i4 < kXR; i4 += kXSub, n++) {
             const int p = n & 1;
@@ -1993,7 +1996,6 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             }
             mbar_wait_wd(&muf[p], (uint32_t)((n >> 1) & 1));
             const uint32_t mus = mub + (uint32_t)p * kXMuSlotBytes;
-            f2 part[2] = {zero2, zero2};
             auto maps = [&](auto checked) {
 #pragma unroll
                 for (int r = 0; r < KX_EXP_VROWS; r++) {
@@ -2006,9 +2008,9 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             if (t0 >= 4 && t0 + kXSub <= H + 4) maps(std::false_type{}); else maps(std::true_type{});
             __syncwarp();
             if (lane == 0) mbar_arrive(&mue[p]);
-            acc[0] += (double)f2_hsum(part[0]);
-            acc[1] += (double)f2_hsum(part[1]);
         }
+        acc[0] += (double)f2_hsum(part[0]);
+        acc[1] += (double)f2_hsum(part[1]);
     }
 #pragma unroll
     for (int kk = 0; kk < 2; kk++) {

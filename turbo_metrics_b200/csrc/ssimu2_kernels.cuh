@@ -1569,6 +1569,10 @@ __device__ __forceinline__ uint32_t ld_acquire_cta_shared(uint32_t addr)
     asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
+// named barriers (ids 1..15): a hardware wait costs no issue slots, unlike a try_wait loop -- used for the hand-off between
+// the two V warps of a channel, which share their sub-partition with the H warps
+__device__ __forceinline__ void nbar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void sts64(uint32_t addr, f2 v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v.v) : "memory"); }
 
 // hstep on two rows at once (see f2_sub_prod for the form of the subtraction).
@@ -1889,8 +1893,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
     const uint32_t lane8 = (uint32_t)lane * 8u;
     constexpr uint32_t kXMu2Off = (uint32_t)((hv_slot(4) - hv_slot(3)) * 3 * kXHbPlane * 4);   // mu2 plane - mu1 plane
     const uint32_t mub = sbase + kXOffMu + (uint32_t)c * 2u * kXMuSlotBytes + lane8;
-    uint64_t* const muf = mu_full + 2 * c;
-    uint64_t* const mue = mu_free + 2 * c;
+    const int nsub = nb * (kXR / kXSub);
     if (role == 2) {
         VState2 stq[2];
 #pragma unroll
@@ -1909,7 +1912,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
 #pragma unroll 1
             for (int i4 = 0; i4 < kXR; i4 += kXSub, n++) {
                 const int p = n & 1;
-                if (n >= 2) mbar_wait_wd(&mue[p], (uint32_t)(((n >> 1) - 1) & 1));
+                if (n >= 2) nbar_sync(7 + 2 * c + p, 64);   // Va has read this slot's previous rows
                 const uint32_t mus = mub + (uint32_t)p * kXMuSlotBytes;
                 // delayed-tap rows of the sub-band: previous tile rows i4 + 2 .. i4 + 5, except that for i4 = 8 the last two
                 // (band rows 10, 11) are rows 0, 1 of this band's tile.  Formed once per sub-band: the V warps are the
@@ -1937,8 +1940,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
                 };
                 const int t0 = j * kXR + i4;
                 if (t0 >= 4 && t0 + kXSub <= H + 4) rows(std::false_type{}); else rows(std::true_type{});
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&muf[p]);
+                nbar_arrive(1 + 2 * c + p, 64);             // rows ready for Va
             }
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) acc[kk] += (double)f2_hsum(part[kk]);
@@ -1994,7 +1996,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&hb_free[sp]);
             }
-            mbar_wait_wd(&muf[p], (uint32_t)((n >> 1) & 1));
+            nbar_sync(1 + 2 * c + p, 64);
             const uint32_t mus = mub + (uint32_t)p * kXMuSlotBytes;
             auto maps = [&](auto checked) {
 #pragma unroll
@@ -2006,8 +2008,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             };
             const int t0 = j * kXR + i4;
             if (t0 >= 4 && t0 + kXSub <= H + 4) maps(std::false_type{}); else maps(std::true_type{});
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&mue[p]);
+            if (n + 2 < nsub) nbar_arrive(7 + 2 * c + p, 64);   // Vb waits for it before it reuses the slot (never after the last use)
         }
         acc[0] += (double)f2_hsum(part[0]);
         acc[1] += (double)f2_hsum(part[1]);

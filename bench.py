@@ -304,22 +304,34 @@ def run_ours(args, rank, world, local_rank):
     dom = max(range(2), key=lambda k: kms[k])
     per_launch_ms = kms[dom] / kbatches
     pairs_per_launch = kpairs / kbatches
-    achieved = kalg[names[dom]] * pairs_per_launch / (per_launch_ms / 1e3) / 1e9
+    kernel_alg_gbs = kalg[names[dom]] * pairs_per_launch / (per_launch_ms / 1e3) / 1e9
     pipeline_gbs = alg_bytes * value / world / 1e9
-    roof = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    # The headline figure charges the contract's B_alg (the traffic of the prescribed two-global-pass design) to the
+    # WHOLE launch group of the path (front-end + k_hv + finalize, CUDA-event times without cross-batch overlap).  Charging the
+    # dominant kernel alone with its share of B_alg gives a "fraction" above 1 (dominant_kernel.alg_rate_over_peak): k_hv never
+    # moves the 120 B per pyramid pixel of intermediates the model counts, so that number says how much traffic fusion removed,
+    # not how close the kernel is to HBM speed (its measured DRAM rate is dominant_kernel.dram_gbs).
+    step_ms = sum(kms[k] for k in range(len(names)) if names[k] != "(none)") / kbatches
+    achieved = alg_bytes * pairs_per_launch / (step_ms / 1e3) / 1e9
+    roof = {"bound": "hbm", "kernel": f"{names[dom]} (dominant: {100 * per_launch_ms / step_ms:.0f} % of the launch group)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": None, "peak_source": peak_src,
+            "basis": "B_alg (SURVEY 8d) x pairs per launch group / CUDA-event time of the group's kernels (ring = 1)",
             "kernel_ms_per_launch": {n: kms[k] / kbatches for k, n in enumerate(names) if n != "(none)"},
             "pairs_per_launch": pairs_per_launch,
             "pipeline": {"alg_bytes_per_pair": alg_bytes, "achieved": pipeline_gbs, "frac": pipeline_gbs / peak,
-                         "note": "B_alg (SURVEY 8d) x pairs/s per GPU / peak"},
+                         "note": "B_alg x measured pairs/s per GPU / peak (the timed loop, batches overlapping across ring slots)"},
+            "dominant_kernel": {"name": names[dom], "alg_bytes_per_pair": kalg[names[dom]], "alg_rate_gbs": kernel_alg_gbs,
+                                "alg_rate_over_peak": kernel_alg_gbs / peak, "dram_gbs": None},
             "note": "B_alg is the two-global-pass model of SURVEY 8d; k_hv keeps the 60 B/px intermediate on chip, so its real "
-                    "DRAM traffic (traffic) is far below its algorithmic bytes; the kernel is held by the FP32 pipe, the shared-memory pipe "
-                    "and the issue rate at ~60 % each (DESIGN.md section 4 / 8), not by HBM"}
+                    "DRAM traffic (traffic) is far below its algorithmic bytes; the kernel is held by the FP32 pipe (71 % on the "
+                    "sub-partitions of the H and Va warps), not by HBM (DESIGN.md sections 4 / 8)"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic_r1.json")
     if os.path.exists(traffic_file):
         tr = {k: v for k, v in json.load(open(traffic_file)).get(args.workload, {}).items()}
         if names[dom] in tr:
             roof["traffic"] = tr[names[dom]] * pairs_per_launch   # bytes per launch from the ncu --set full capture
+            roof["dominant_kernel"]["dram_gbs"] = roof["traffic"] / (per_launch_ms / 1e3) / 1e9
         roof["dram_bytes_per_pair_ncu"] = {k: v for k, v in tr.items()}
 
     cores = os.cpu_count() or 1

@@ -91,7 +91,8 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------ CPU oracle arm
 def oracle_pairs_per_s(workload, n_pairs, threads):
-    """Score n_pairs synthetic pairs with the CPU oracle, one pair per thread; returns pairs/s."""
+    """Score n_pairs synthetic pairs (all copies of frame 0, seed 1 = the first pair rank 0 times on the GPU) with the CPU
+    oracle, one pair per thread; returns (pairs/s, seconds, (score, norms[108]) of that pair)."""
     import torch  # noqa: F401
     from oracle import oracle
     from turbo_metrics_b200 import synth
@@ -100,11 +101,11 @@ def oracle_pairs_per_s(workload, n_pairs, threads):
     if kind == "yuv":
         rb, db, pitch, ch = synth.make_pair_yuv420(w, h, bits, frame=0, seed=1)
         rn, dn = rb.numpy(), db.numpy()
-        job = lambda: oracle.ssimu2_yuv420(rn, dn, pitch, ch, w, h, bits)[0]
+        job = lambda: oracle.ssimu2_yuv420(rn, dn, pitch, ch, w, h, bits)[:2]
     else:
         r, d = synth.make_pair_srgb8(w, h, frame=0, seed=1)
         rn, dn = r.numpy(), d.numpy()
-        job = lambda: oracle.ssimu2_srgb8(rn, dn)[0]
+        job = lambda: oracle.ssimu2_srgb8(rn, dn)[:2]
     out = [None] * n_pairs
     idx = iter(range(n_pairs))
     lock = threading.Lock()
@@ -273,8 +274,9 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- parity spot check of the timed configuration (rank 0, tiny cost): scores are finite and the
     # first pair of the sequence equals its own re-run in another batch slot
-    (s_first, s_last), _ = step_device()
+    (s_first, s_last), ts_chk = step_device()
     assert 0.0 < s_first < 100.0 and 0.0 < s_last < 100.0, (s_first, s_last)
+    norms_first = m.get_norms(ts_chk[0])
 
     # ---- per-kernel device time without cross-stream overlap: same batch size, ring = 1
     m.close()
@@ -337,12 +339,23 @@ def run_ours(args, rank, world, local_rank):
     cores = os.cpu_count() or 1
     threads = min(cores, 32)
     sample = max(2, min(threads, 16)) if args.workload != "512" else threads * 8
+    parity = None
     if args.no_cpu_baseline:
         cpu = {"value": None, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": "skipped (--no-cpu-baseline)"}
     else:
-        cv, cdt, _ = oracle_pairs_per_s(args.workload, sample, threads)
+        cv, cdt, (o_score, o_norms) = oracle_pairs_per_s(args.workload, sample, threads)
         cpu = {"value": cv, "unit": "pairs/s", "cores": min(threads, sample), "kind": "port",
                "sample": f"{sample} pairs of the same {w}x{h} workload, one pair per thread, {cdt:.1f} s"}
+        # parity of the timed configuration: the first pair of the timed sequence (frame 0, seed 1) against the oracle result the
+        # cpu_baseline leg has just computed for the same pair -- the bar of BASELINE.json, and the run FAILS above it
+        import numpy as np
+        nz = o_norms != 0
+        rel = np.zeros(108)
+        rel[nz] = np.abs(norms_first[nz] - o_norms[nz]) / np.abs(o_norms[nz])
+        rel[~nz] = np.abs(norms_first[~nz])
+        parity = {"pair": "frame 0, seed 1 (first pair of the timed sequence)", "score_gpu": s_first, "score_oracle": o_score,
+                  "dscore": abs(s_first - o_score), "max_rel_norm": float(rel.max()), "bar": {"dscore": 0.01, "max_rel_norm": 1e-4}}
+        assert parity["dscore"] <= 0.01 and parity["max_rel_norm"] <= 1e-4, parity
 
     # ---- the reference's GPU design (NPP + per-sample kernels + one graph launch and one host sync per pair) restated in
     # baseline/refgpu and timed on this GPU on a bounded sample of the same frames: measurement tooling
@@ -388,6 +401,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_reference_design": refdesign,
         "timing": timing,
         "scores": {"first": s_first, "last": s_last},
+        "parity": parity,
     }
     emit(line)
 

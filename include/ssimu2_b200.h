@@ -11,19 +11,35 @@
  *   ssimulacra2-cuda/src/lib.rs:253-266  Ssimulacra2::compute_srgb_sync             -> ssimu2_compute_sync (SSIMU2_FMT_SRGB8)
  *   ssimulacra2-cuda/src/lib.rs:232-250  Ssimulacra2::compute_from_cpu_srgb_sync    -> ssimu2_submit_host + ssimu2_get_score
  *   ssimulacra2-cuda/src/lib.rs:289-291  Ssimulacra2::get_score                     -> ssimu2_get_score
+ *   cudarse-video/src/dec.rs:277-287     FrameMapping drop (surface reuse)          -> ssimu2_stream_wait_input
  *   cuda-colorspace/src/lib.rs:33-123    ColorspaceConversion::biplanaryuv420_to_linearrgb_{8,16}
  *                                        (folded into the scorer: SSIMU2_FMT_NV12 / SSIMU2_FMT_P016)
  *   cuda-colorspace/src/lib.rs:144-169   srgb_to_linear_{u8,u16,f32}                (SSIMU2_FMT_SRGB8/16/F32)
  *   turbo-metrics/src/lib.rs:268-360     TurboMetrics::compute_one (the caller)     -> ssimu2_submit / ssimu2_get_score
- *   turbo-metrics/src/lib.rs:362-433     TurboMetrics::compute_all frame loop       -> ssimu2_submit_batch + tickets
+ *   turbo-metrics/src/lib.rs:362-433     TurboMetrics::compute_all frame loop       -> ssimu2_submit_batch + tickets;
+ *                                        across the GPUs of a box                   -> ssimu2_shard_*
  *
  * Conventions
  *   - Plain C types only.  Device pointers are CUdeviceptr-compatible 64-bit integers,
  *     streams are CUstream / cudaStream_t handles passed as void*.
  *   - Every function returns 0 (SSIMU2_OK) or a negative ssimu2_status; a positive value is
  *     a CUDA runtime error code passed through.  Nothing throws or aborts across the ABI.
- *   - Input frames are BORROWED: read-only, never freed, and must stay valid until the
- *     ticket's score has been fetched (or ssimu2_wait has returned for it).
+ *   - Input frames are BORROWED: read-only, never freed.  LIFETIME RULE: the scorer reads a frame when its batch (or,
+ *     with cfg.input_group, its input group) is LAUNCHED, which can be later than ssimu2_submit returns.  A frame must
+ *     therefore stay valid AND UNMODIFIED until one of: ssimu2_wait / ssimu2_get_score / ssimu2_get_scores has
+ *     returned for its ticket; ssimu2_completed reports a watermark above its ticket; or the stream that will
+ *     overwrite it has been made to wait with ssimu2_stream_wait_input (inputs consumed) or ssimu2_stream_wait (batch
+ *     done).  The reference enqueues its graph on the caller's stream at once and syncs per pair
+ *     (turbo-metrics/src/lib.rs:342-358); here the dependency on the caller's stream is recorded at submit time, so
+ *     everything enqueued on `stream` BEFORE the submit is seen, and nothing enqueued after it is waited for.
+ *   - Decoder-style surface pools (cudarse-video/src/dec.rs:277-287: a surface is valid until unmapped): set
+ *     cfg.input_group (pairs per front-end launch, e.g. 1-4) so that surfaces are consumed shortly after submit, and
+ *     recycle each one behind ssimu2_stream_wait_input(ticket, decoder_stream) -- no host synchronisation.
+ *   - Scales: like the reference's CPU implementation (cpu.rs:359) a frame whose scale-s size is below 8x8 stops the
+ *     pyramid at s+1 scales (fewer than 6 for min(width, height) < 113) and the 108 weights are consumed densely over
+ *     the scales that exist.  The reference's GPU op always runs 6 scales with fixed weight offsets
+ *     (ssimulacra2-cuda/src/lib.rs:61-65, 586-603) and gives a different score for such small frames; the parity
+ *     target named by BASELINE.json is the CPU implementation.  ssimu2_info.nscales tells which case applies.
  *   - A handle is bound to one device and one (width, height, format).  Calls on one handle
  *     are not re-entrant; different handles may be driven from different threads.
  *   - There is no CPU fallback: if no CUDA device is usable every entry point fails.
@@ -72,14 +88,30 @@ typedef struct {
     uint32_t reserved;
 } ssimu2_frame;
 
+typedef enum {
+    SSIMU2_PIPELINE_DEFAULT = 0, /* front-end, fused H+V filter/map/sum kernel, finalize */
+    SSIMU2_PIPELINE_SPLIT = 1    /* development: separate H and V passes, H-pass planes kept in HBM (ssimu2_debug_read) */
+} ssimu2_pipeline;
+
+/* ssimu2_config.flags */
+#define SSIMU2_FLAG_SCORE_ONLY 1u /* compute only what the score depends on: the filters and SSIM map of every (scale, channel) \
+                                     whose two SSIM weights are both zero are skipped (the reference computes them and multiplies \
+                                     by 0.0, ssimulacra2-cuda/src/lib.rs:586-603).  Scores are bit-identical to the full mode;    \
+                                     ssimu2_get_norms returns SSIMU2_E_UNSUPPORTED. */
+#define SSIMU2_FLAG_NO_TIMING 2u  /* do not record the per-kernel timing events (ssimu2_b200_debug.h) */
+
 typedef struct {
     uint32_t width, height;
-    int32_t format;     /* ssimu2_format */
-    int32_t matrix;     /* ssimu2_matrix */
-    int32_t full_range; /* 0 = limited (what the reference implements), 1 = full */
-    int32_t device;     /* CUDA device ordinal */
-    uint32_t batch;     /* frame pairs per kernel launch group (0 = default) */
-    uint32_t ring;      /* batches in flight, one stream each (0 = default) */
+    int32_t format;       /* ssimu2_format */
+    int32_t matrix;       /* ssimu2_matrix */
+    int32_t full_range;   /* 0 = limited (what the reference implements), 1 = full */
+    int32_t device;       /* CUDA device ordinal */
+    uint32_t batch;       /* frame pairs per kernel launch group (0 = default 8, at most 1024) */
+    uint32_t ring;        /* batches in flight, one stream each (0 = default 3) */
+    uint32_t pipeline;    /* ssimu2_pipeline */
+    uint32_t flags;       /* SSIMU2_FLAG_* */
+    uint32_t input_group; /* pairs per front-end launch; 0 = whole batch.  Smaller groups consume the input frames sooner */
+    uint32_t reserved[5]; /* must be 0 */
 } ssimu2_config;
 
 /* ---- lifetime ------------------------------------------------------------------------ */
@@ -104,6 +136,9 @@ int ssimu2_submit_batch(ssimu2_t *h, uint32_t n, const ssimu2_frame *refs, const
 int ssimu2_flush(ssimu2_t *h);
 /* Block until the ticket's batch has completed on the device. */
 int ssimu2_wait(ssimu2_t *h, uint64_t ticket);
+/* *watermark = the lowest ticket whose results have not reached the host yet: every pair below it has completed and its
+ * input frames are no longer referenced (batches complete out of order across ring slots; this is the in-order bound). */
+int ssimu2_completed(ssimu2_t *h, uint64_t *watermark);
 /* Score of a ticket (flushes and waits as needed).  100 = identical, unbounded below. */
 int ssimu2_get_score(ssimu2_t *h, uint64_t ticket, double *score);
 /* The scores of n consecutive tickets in submission order: the per-frame score stream of the CLI loop
@@ -117,6 +152,9 @@ int ssimu2_compute_sync(ssimu2_t *h, const ssimu2_frame *ref, const ssimu2_frame
 /* Make `stream` wait (device side) until the ticket's batch is done, so the caller may
  * recycle the input frames in stream order without a host sync. */
 int ssimu2_stream_wait(ssimu2_t *h, uint64_t ticket, void *stream);
+/* Same, but only until the ticket's INPUT FRAMES have been consumed (its front-end launch is done); launches the pending
+ * input group if the ticket is still waiting in one.  This is the call that lets a decoder reuse a surface. */
+int ssimu2_stream_wait_input(ssimu2_t *h, uint64_t ticket, void *stream);
 
 /* ---- scoring: host frames ------------------------------------------------------------ */
 /* Ssimulacra2::compute_from_cpu_srgb_sync generalised to every format: the frames live in
@@ -135,31 +173,43 @@ int ssimu2_submit_host_batch(ssimu2_t *h, uint32_t n, const ssimu2_frame *refs, 
 /* Device address of the f64 score ring (one entry per ticket, index ticket % capacity). */
 int ssimu2_scores_device(ssimu2_t *h, uint64_t *dptr, uint64_t *capacity);
 
-/* ---- introspection (used by the parity tests and bench.py) ---------------------------- */
+/* ---- introspection ----------------------------------------------------------------- */
 typedef struct {
     uint32_t nscales;
     uint32_t width[6], height[6], pitch[6]; /* pitch in floats */
     uint32_t batch, ring;
     uint64_t alg_bytes_per_pair; /* B_alg of SURVEY.md section 8(d) for this geometry */
     uint64_t kernel_launches;    /* kernels launched so far by this handle */
+    uint32_t pipeline, flags, input_group;
+    uint32_t strips_per_pair;    /* k_hv work items (64-column strips over all scales) per pair */
+    uint64_t io_bytes_per_pair;  /* B_io: compulsory input bytes of a pair + 8 */
 } ssimu2_info;
 int ssimu2_get_info(const ssimu2_t *h, ssimu2_info *info);
-/* Copy an intermediate plane set of the batch slot that served `ticket` to host memory.
- * what = 0: XYB planes of `scale`:                float[2][3][h][w]  (ref X,Y,B then dis X,Y,B)
- * what = 1: H-pass output of `scale`:            float[15][h][w]    (s11,s22,s12,mu1,mu2) x 3 channels
- * Only valid until that slot is reused (i.e. right after ssimu2_get_score). */
-int ssimu2_debug_read(ssimu2_t *h, uint64_t ticket, int what, int scale, float *out, size_t out_floats);
-/* Run the device arithmetic helpers over an array (host pointers) so the tests can compare them bit for
- * bit with libm / IEEE division:  op 0: out[i] = cbrtf(in[i]);  op 1: powf(in[i], y);  op 2: in[i] / y (f32);
- * op 3: `in` holds n (num, den) pairs of DOUBLES, `out` n doubles: num / den;
- * op 4: `in` holds n (num, den) pairs of floats: the V-pass quotient;
- * op 5 / 6: the unchecked hot-path forms of op 0 / 1 (positive normal arguments only). */
-int ssimu2_debug_math(int op, const float *in, float y, float *out, size_t n);
-/* Average device time (ms) of the last completed batch per kernel: pyramid, hpass, vpass, finalize. */
-int ssimu2_last_batch_ms(ssimu2_t *h, float ms[4]);
-/* Device time (ms, CUDA events on the batch's own stream) summed per kernel over every batch
- * completed so far: frontend, hpass, vpass, finalize; optional counters; reset != 0 clears them. */
-int ssimu2_kernel_ms(ssimu2_t *h, double ms_total[4], uint64_t *batches, uint64_t *pairs, int reset);
+
+/* ---- frame-sharded scoring across the GPUs of one box (ssimu2_shard.cu) -------------------------------------------
+ * The reference drives one GPU (device 0 is hard-coded, turbo-metrics/src/lib.rs:438-456) from one thread
+ * (frame loop turbo-metrics/src/lib.rs:362-433).  SSIMULACRA2 pairs are independent (ssimulacra2-cuda/README.md:26-27),
+ * so N GPUs = N handles, each driven by its own host thread INSIDE the library; the caller keeps the single-threaded
+ * submit / fetch loop.  Global tickets increase by one per pair in submission order; pair g goes to device
+ * (g / cfg.batch) % n_devices (whole batches stay on one GPU).  No collective, no peer access: only f64 scores leave a GPU.
+ * Frames are HOST frames (any device would need them anyway): each worker copies its pairs to its own GPU. */
+typedef struct ssimu2_shard ssimu2_shard_t;
+/* cfg->device is ignored; devices[i] are CUDA ordinals (n_devices >= 1). */
+int ssimu2_shard_create(ssimu2_shard_t **out, const ssimu2_config *cfg, const int32_t *devices, uint32_t n_devices);
+int ssimu2_shard_destroy(ssimu2_shard_t *s);
+/* n host pairs (layout as ssimu2_submit_host); returns at once, the copies and launches run on the worker threads.
+ * The frames must stay valid until their scores have been fetched.  *first_ticket = global ticket of pair 0. */
+int ssimu2_shard_submit_host(ssimu2_shard_t *s, uint32_t n, const ssimu2_frame *refs, const ssimu2_frame *diss,
+                             size_t frame_bytes, uint64_t *first_ticket);
+/* n DEVICE pairs that already live on the GPU the sharding rule assigns them to (ssimu2_shard_device_of); `streams[d]`
+ * (may be NULL = no dependency) is the stream of device d the frames were produced on. */
+int ssimu2_shard_submit_device(ssimu2_shard_t *s, uint32_t n, const ssimu2_frame *refs, const ssimu2_frame *diss,
+                               void *const *streams, uint64_t *first_ticket);
+/* CUDA ordinal that global ticket `ticket` is (or will be) scored on. */
+int ssimu2_shard_device_of(const ssimu2_shard_t *s, uint64_t ticket, int32_t *device);
+/* Scores of n consecutive global tickets, in submission order (blocks until they are done). */
+int ssimu2_shard_get_scores(ssimu2_shard_t *s, uint64_t first_ticket, uint32_t n, double *scores);
+int ssimu2_shard_flush(ssimu2_shard_t *s);
 
 #ifdef __cplusplus
 }

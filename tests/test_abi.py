@@ -1,5 +1,6 @@
-"""The C-ABI library loads and exports exactly what include/ssimu2_b200.h declares; without a GPU every
-entry point fails loudly (no CPU fallback).  No compute calls here."""
+"""The C-ABI library loads and exports exactly what include/ssimu2_b200.h (the drop-in boundary) and
+include/ssimu2_b200_debug.h (test / measurement hooks) declare; without a GPU every entry point fails loudly
+(no CPU fallback).  No compute calls here."""
 import ctypes as C
 import os
 import re
@@ -8,13 +9,17 @@ import pytest
 
 from conftest import ROOT, has_gpu
 
-HEADER = os.path.join(ROOT, "include", "ssimu2_b200.h")
+HEADERS = [os.path.join(ROOT, "include", "ssimu2_b200.h"), os.path.join(ROOT, "include", "ssimu2_b200_debug.h")]
 
 
-def _declared():
-    src = open(HEADER).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(ssimu2_[a-z0-9_]+)\s*\(", src)))
+def _declared(headers=HEADERS):
+    names = set()
+    for h in headers:
+        src = open(h).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
+        names |= set(re.findall(r"\b(ssimu2_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():
@@ -22,7 +27,11 @@ def test_library_exports_every_declared_symbol():
     assert os.path.exists(_lib.SO_PATH), "build first: python -c 'import __graft_entry__ as g; g.build()'"
     lib = C.CDLL(_lib.SO_PATH)
     names = _declared()
-    assert len(names) >= 18
+    assert len(names) >= 30
+    public = _declared(HEADERS[:1])
+    assert not any(n.startswith("ssimu2_debug") or n.endswith("_ms") for n in public), "test hooks belong in the debug header"
+    assert all(n in public for n in ["ssimu2_shard_create", "ssimu2_shard_submit_host", "ssimu2_shard_get_scores",
+                                     "ssimu2_stream_wait_input", "ssimu2_completed"])
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     # and the Python binding knows each of them
@@ -32,7 +41,7 @@ def test_library_exports_every_declared_symbol():
 def test_version_and_strerror():
     from turbo_metrics_b200 import _lib
     lib = _lib.lib()
-    assert lib.ssimu2_version() >> 16 == 1
+    assert lib.ssimu2_version() >> 16 == 2
     assert lib.ssimu2_strerror(0) == b"ok"
     assert b"unsupported" in lib.ssimu2_strerror(-2)
     assert b"ticket" in lib.ssimu2_strerror(-5)
@@ -43,10 +52,23 @@ def test_bad_arguments_are_rejected_without_touching_the_gpu():
     lib = _lib.lib()
     h = C.c_void_p()
     assert lib.ssimu2_create(None, None) == -1
-    cfg = _lib.Config(4, 4, 2, 0, 0, 0, 0, 0)            # smaller than 8x8 (cpu.rs:359)
+    from turbo_metrics_b200.ssimulacra2 import make_config
+    cfg = make_config(4, 4, 2)                           # smaller than 8x8 (cpu.rs:359)
     assert lib.ssimu2_create(C.byref(h), C.byref(cfg)) == -2
-    cfg = _lib.Config(64, 64, 17, 0, 0, 0, 0, 0)         # unknown format
+    cfg = make_config(64, 64, 17)                        # unknown format
     assert lib.ssimu2_create(C.byref(h), C.byref(cfg)) == -2
+    cfg = make_config(64, 64, 2, pipeline=7)             # unknown pipeline
+    assert lib.ssimu2_create(C.byref(h), C.byref(cfg)) == -2
+    cfg = make_config(64, 64, 2, flags=1 << 9)           # unknown flag
+    assert lib.ssimu2_create(C.byref(h), C.byref(cfg)) == -2
+    cfg = make_config(64, 64, 2, pipeline=1, flags=1)    # score-only exists for the product pipeline only
+    assert lib.ssimu2_create(C.byref(h), C.byref(cfg)) == -2
+    cfg = make_config(64, 64, 2)
+    cfg.reserved[2] = 1                                  # reserved fields must be zero
+    assert lib.ssimu2_create(C.byref(h), C.byref(cfg)) == -1
+    assert C.sizeof(_lib.Config) == 64 and C.sizeof(_lib.Frame) == 24
+    assert lib.ssimu2_shard_create(None, None, None, 0) == -1
+    assert lib.ssimu2_shard_destroy(None) == 0 and lib.ssimu2_shard_flush(None) == -1
     assert lib.ssimu2_flush(None) == -1
     assert lib.ssimu2_get_score(None, 0, None) == -1
     assert lib.ssimu2_destroy(None) == 0
@@ -54,7 +76,10 @@ def test_bad_arguments_are_rejected_without_touching_the_gpu():
 
 @pytest.mark.skipif(has_gpu(), reason="only meaningful on a box without a GPU")
 def test_no_cpu_fallback():
-    from turbo_metrics_b200 import PixelFormat, Ssimu2Error, Ssimulacra2
+    from turbo_metrics_b200 import PixelFormat, ShardedSsimulacra2, Ssimu2Error, Ssimulacra2
     with pytest.raises(Ssimu2Error) as e:
         Ssimulacra2(64, 64, PixelFormat.SRGB8)
     assert e.value.status == -4  # SSIMU2_E_NODEVICE
+    with pytest.raises(Ssimu2Error) as e:   # the worker threads fail to create their handles; create reports it and joins them
+        ShardedSsimulacra2(64, 64, PixelFormat.SRGB8, devices=[0, 1])
+    assert e.value.status == -4

@@ -19,18 +19,27 @@ class Frame(C.Structure):
 
 
 class Config(C.Structure):
+    """ssimu2_config"""
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_int32),
                 ("matrix", C.c_int32), ("full_range", C.c_int32), ("device", C.c_int32),
-                ("batch", C.c_uint32), ("ring", C.c_uint32)]
+                ("batch", C.c_uint32), ("ring", C.c_uint32), ("pipeline", C.c_uint32), ("flags", C.c_uint32),
+                ("input_group", C.c_uint32), ("reserved", C.c_uint32 * 5)]
+
+
+PIPELINE_DEFAULT, PIPELINE_SPLIT = 0, 1
+FLAG_SCORE_ONLY, FLAG_NO_TIMING = 1, 2
 
 
 class Info(C.Structure):
+    """ssimu2_info"""
     _fields_ = [("nscales", C.c_uint32), ("width", C.c_uint32 * 6), ("height", C.c_uint32 * 6),
                 ("pitch", C.c_uint32 * 6), ("batch", C.c_uint32), ("ring", C.c_uint32),
-                ("alg_bytes_per_pair", C.c_uint64), ("kernel_launches", C.c_uint64)]
+                ("alg_bytes_per_pair", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("pipeline", C.c_uint32), ("flags", C.c_uint32), ("input_group", C.c_uint32),
+                ("strips_per_pair", C.c_uint32), ("io_bytes_per_pair", C.c_uint64)]
 
 
-# every symbol include/ssimu2_b200.h declares: name -> (restype, argtypes)
+# every symbol include/ssimu2_b200.h and include/ssimu2_b200_debug.h declare: name -> (restype, argtypes)
 _P = C.c_void_p
 _FP = C.POINTER(Frame)
 SYMBOLS = {
@@ -43,11 +52,13 @@ SYMBOLS = {
     "ssimu2_submit_batch": (C.c_int, [_P, C.c_uint32, _FP, _FP, _P, C.POINTER(C.c_uint64)]),
     "ssimu2_flush": (C.c_int, [_P]),
     "ssimu2_wait": (C.c_int, [_P, C.c_uint64]),
+    "ssimu2_completed": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "ssimu2_get_score": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_double)]),
     "ssimu2_get_scores": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.POINTER(C.c_double)]),
     "ssimu2_get_norms": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_double)]),
     "ssimu2_compute_sync": (C.c_int, [_P, _FP, _FP, _P, C.POINTER(C.c_double)]),
     "ssimu2_stream_wait": (C.c_int, [_P, C.c_uint64, _P]),
+    "ssimu2_stream_wait_input": (C.c_int, [_P, C.c_uint64, _P]),
     "ssimu2_submit_host": (C.c_int, [_P, _FP, _FP, C.c_size_t, C.POINTER(C.c_uint64)]),
     "ssimu2_submit_host_batch": (C.c_int, [_P, C.c_uint32, _FP, _FP, C.c_size_t, C.POINTER(C.c_uint64)]),
     "ssimu2_scores_device": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -56,6 +67,13 @@ SYMBOLS = {
     "ssimu2_debug_math": (C.c_int, [C.c_int, C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float), C.c_size_t]),
     "ssimu2_last_batch_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "ssimu2_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]),
+    "ssimu2_shard_create": (C.c_int, [C.POINTER(_P), C.POINTER(Config), C.POINTER(C.c_int32), C.c_uint32]),
+    "ssimu2_shard_destroy": (C.c_int, [_P]),
+    "ssimu2_shard_submit_host": (C.c_int, [_P, C.c_uint32, _FP, _FP, C.c_size_t, C.POINTER(C.c_uint64)]),
+    "ssimu2_shard_submit_device": (C.c_int, [_P, C.c_uint32, _FP, _FP, C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    "ssimu2_shard_device_of": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_int32)]),
+    "ssimu2_shard_get_scores": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.POINTER(C.c_double)]),
+    "ssimu2_shard_flush": (C.c_int, [_P]),
 }
 
 _lib = None

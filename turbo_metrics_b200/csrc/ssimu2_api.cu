@@ -3,12 +3,15 @@
 // Mirrors the reference's metric op (crates/ssimulacra2-cuda/src/lib.rs:27-291) and the per-pair
 // driver that calls it (crates/turbo-metrics/src/lib.rs:268-360), re-designed for throughput:
 //   * a handle owns `ring` batch slots; each slot has its own stream, workspace and result buffers;
-//   * pairs are collected into batches of `batch` and every batch is 4 kernel launches that cover
+//   * pairs are collected into batches of `batch` and every batch is 3 kernel launches that cover
 //     all frames and all 6 scales (the reference records a 305-node graph per pair and syncs the
 //     host after every pair, lib.rs:342-352);
+//   * the front-end (the only kernel that reads the caller's frames) can run per input group of a few pairs
+//     (cfg.input_group), so that decoder surfaces are consumed soon after submit;
 //   * only the f64 scores (and, for parity tests, the 108 norms) travel back to the host.
 // There is no CPU fallback: without a usable CUDA device every call fails.
 #include "../../include/ssimu2_b200.h"
+#include "../../include/ssimu2_b200_debug.h"
 #include "ssimu2_kernels.cuh"
 
 #include <cstdio>
@@ -31,36 +34,50 @@ constexpr uint32_t kDefaultRing = 3;
         if (_e != cudaSuccess) return (int)_e;       \
     } while (0)
 
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+    int prev = -1, dev;
+    explicit DeviceGuard(int d) : dev(d)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+};
+
 struct Slot {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_in = nullptr;      // dependency on the submitter's stream
+    cudaEvent_t ev_in = nullptr;      // dependency on the submitter's stream, recorded at submit time
     cudaEvent_t ev_done = nullptr;    // batch complete (results on host)
     cudaEvent_t ev_k[5] = {};         // per-kernel timing marks
+    std::vector<cudaEvent_t> ev_fe;   // one per front-end launch of the current batch: "inputs consumed"
+    std::vector<uint16_t> fe_seq;     // [batch] front-end launch that served pair i
+    uint32_t fe_launches = 0;         // front-end launches of the current batch so far
+    uint32_t fe_pairs = 0;            // pairs of the current batch whose front-end has been launched
     float* xyb = nullptr;             // [batch] XYB planes of all scales
-    float* hb = nullptr;              // [batch] H-pass planes
+    float* hb = nullptr;              // [batch] H-pass planes (split pipeline only)
     double* partials = nullptr;       // [batch][total_strips][18]
     double* norms_d = nullptr;        // [batch][108]
     double* scores_d = nullptr;       // [batch]
     double* norms_h = nullptr;        // pinned
     double* scores_h = nullptr;       // pinned
     uint8_t* staging = nullptr;       // device staging for host frames: [batch][2][staging_frame_bytes]
-    BatchIn in{};
+    FramePair* in_h = nullptr;        // pinned frame table of the batch being recorded
+    FramePair* in_d = nullptr;        // its device copy (uploaded per front-end launch)
     TmaMaps maps{};                   // tensor maps of this slot's H-pass / XYB buffers, per scale (V pass)
     TmaMapsH maps_h{};                // (H pass)
     TmaMapsX maps_x{};                // (fused H+V kernel)
     f2* hstate = nullptr;             // k_hv hand-off records: [batch][total_recs][6][96]
-    uint32_t* hvflags = nullptr;      // [batch][total_recs] + 1 ticket counter at the end
+    uint32_t* hvflags = nullptr;      // [batch][total_recs] + the work-item counter at the end
     uint32_t epoch = 0;               // launch counter of k_hv on this slot (flag value)
     uint32_t count = 0;               // pairs recorded
     uint64_t first_ticket = 0;
     bool inflight = false;            // fully launched, results not harvested yet
-    bool awaiting = false;            // front-end launched, H pass waiting for the next batch (fused mode)
-    bool staged = false;              // holds host frames copied on the slot stream
-    bool was_timed = false;
-    cudaEvent_t ev_mid = nullptr;     // main stream -> slot stream hand-off
-    cudaEvent_t ev_f = nullptr;       // front-end of this slot done (two-stream pipeline)
-    bool timed = false;
-    void* last_stream = nullptr;
+    bool timed = false, was_timed = false;
+    void* dep_stream = nullptr;       // stream ev_in was last recorded on
     bool have_dep = false;
 };
 
@@ -69,18 +86,11 @@ struct Slot {
 struct ssimu2_handle {
     ssimu2_config cfg{};
     Geo geo{};
-    uint32_t batch = 0, ring = 0;
+    uint32_t batch = 0, ring = 0, input_group = 0;
     std::vector<Slot> slots;
     uint32_t cur = 0;
-    int awaiting = -1;                // slot index in the `awaiting` state, or -1
-    bool fuse = false;                // cross-batch fusion of front-end and H pass (pipeline "fh", ring >= 2)
-    bool frontend2 = true;            // warp-per-region front-end (SSIMU2_FRONTEND=1 selects the shared-memory tile version)
-    int pipeline = 0;                 // 0 = "hv": front-end, fused H+V kernel, finalize (default)
-                                      // 1 = "fh": k_fused_fh + k_vpass (ring >= 2) / 2 = "split": four kernels
-    cudaStream_t main_stream = nullptr;
-    cudaStream_t f_stream = nullptr, hv_stream = nullptr;  // pipeline "hv", ring >= 2: front-end stream / H+V stream
-    bool two_stream = false;
-    int num_sms = 0, f2p_ctas = 1;
+    int pipeline = 0;                 // 0 = fused (front-end, k_hv, finalize) / 1 = split (front-end, k_hpass, k_vpass, finalize)
+    bool score_only = false;
     uint64_t next_ticket = 0;
     double* scores_ring_d = nullptr;  // [kResultCap] device score stream
     float* eotf_lut = nullptr;        // exact R / B transfer memo for YUV sources (see Geo)
@@ -93,7 +103,7 @@ struct ssimu2_handle {
     float last_ms[4] = {0, 0, 0, 0};
     double total_ms[4] = {0, 0, 0, 0};  // per-kernel device time summed over harvested batches
     uint64_t timed_batches = 0, timed_pairs = 0;
-    uint64_t alg_bytes = 0;
+    uint64_t alg_bytes = 0, io_bytes = 0;
 };
 
 namespace {
@@ -194,6 +204,8 @@ static void build_geo(ssimu2_handle* h)
     g.coef = make_coef(h->cfg.format, h->cfg.matrix, h->cfg.full_range);
     // B_alg = 120*sum(P_s) + 2*in_0*P_0 + 72*sum_{s>=1}(P_s)
     h->alg_bytes = 120ULL * sum_px + 2ULL * in_bytes_per_px(h->cfg.format) * h->cfg.width * h->cfg.height + 72ULL * sum_px_ge1;
+    // compulsory I/O floor B_io = in_0 * P_0 + 8
+    h->io_bytes = (unsigned long long)in_bytes_per_px(h->cfg.format) * h->cfg.width * h->cfg.height + 8ULL;
 }
 
 // ---- TMA tensor maps (driver entry point fetched through the runtime; libcuda is not linked) ----
@@ -248,212 +260,98 @@ static int build_tma_maps(ssimu2_handle* h, Slot& sl)
 }
 
 // ---- launch logic -------------------------------------------------------------------------------
-// ring == 1 (or SSIMU2_NO_FUSE): the four kernels of a batch run back to back on the slot's stream, with
-//   CUDA events between them (this is the mode bench.py uses to time each kernel alone).
-// ring >= 2: software pipeline across batches.  The front-end of batch k is launched in the SAME kernel as the
-//   H pass of batch k-1 (k_fused_fh: compute-bound and memory-bound CTAs share the SMs) on the handle's main
-//   stream; the V pass + finalize + result copy of k-1 follow on that slot's own stream.  The last batch of a
-//   burst is completed by flush / get_score with an H-only launch.
+// All work of a batch runs on its slot's stream: [frame-table upload + front-end] x (1 .. n launches), then
+// k_hv + k_finalize (or k_hpass + k_vpass + k_finalize), then the D2H copy of scores and norms.
+
 template <int FMT>
-static int launch_unfused(ssimu2_handle* h, Slot& sl)
+static void launch_frontend_kernel(const ssimu2_handle* h, Slot& sl, uint32_t frame0, uint32_t n)
 {
     const Geo& g = h->geo;
-    const uint32_t n = sl.count;
-    cudaStream_t st = sl.stream;
-    if (sl.timed) cudaEventRecord(sl.ev_k[0], st);
-    if (h->frontend2) {
-        const int rx = (g.sc[0].w + kF2Region - 1) / kF2Region, ry = (g.sc[0].h + kF2Region - 1) / kF2Region;
-        const int per_cta = (kF2Threads / 32) * kF2RegionsPerWarp;
-        k_frontend2<FMT><<<dim3((rx + per_cta - 1) / per_cta, ry, n), kF2Threads, 0, st>>>(g, sl.in, sl.xyb);
-    } else {
-        dim3 grid((g.sc[0].w + 63) / 64, (g.sc[0].h + 63) / 64, n);
-        k_frontend<FMT><<<grid, kFThreads, kFSmemTotal, st>>>(g, sl.in, sl.xyb);
+    const int rx = (g.sc[0].w + kF2Region - 1) / kF2Region, ry = (g.sc[0].h + kF2Region - 1) / kF2Region;
+    const int per_cta = (kF2Threads / 32) * kF2RegionsPerWarp;
+    k_frontend2<FMT><<<dim3((rx + per_cta - 1) / per_cta, ry, n), kF2Threads, 0, sl.stream>>>(g, sl.in_d, sl.xyb, (int)frame0);
+}
+
+// front-end of pairs [sl.fe_pairs, upto) of the batch being recorded in `sl`
+static int launch_frontend(ssimu2_handle* h, Slot& sl, uint32_t upto, bool time_it)
+{
+    const uint32_t f0 = sl.fe_pairs;
+    if (upto <= f0) return 0;
+    const uint32_t n = upto - f0;
+    if (sl.have_dep) {
+        // ordered after everything the submitter had enqueued on its stream when it submitted these pairs
+        CU_TRY(cudaStreamWaitEvent(sl.stream, sl.ev_in, 0));
+        sl.have_dep = false;
     }
-    if (sl.timed) cudaEventRecord(sl.ev_k[1], st);
-    k_hpass<<<dim3(g.items_h, n), kHThreads, kHSmemBytes, st>>>(g, sl.maps_h);
-    if (sl.timed) cudaEventRecord(sl.ev_k[2], st);
-    k_vpass<<<dim3(g.items_v, n), kVTmaThreads, kVSmemBytes, st>>>(g, sl.maps, sl.partials);
-    if (sl.timed) cudaEventRecord(sl.ev_k[3], st);
-    k_finalize<<<n, 128, 0, st>>>(g, sl.partials, sl.norms_d, h->scores_ring_d, sl.first_ticket, kResultCap, sl.scores_d, nullptr);
-    if (sl.timed) cudaEventRecord(sl.ev_k[4], st);
-    h->launches += 4;
-    CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(sl.scores_h, sl.scores_d, n * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(sl.norms_h, sl.norms_d, (size_t)n * 108 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaEventRecord(sl.ev_done, st));
-    sl.inflight = true;
-    sl.was_timed = sl.timed;
-    return 0;
-}
-
-// pipeline "hv": front-end, fused H+V kernel, finalize.
-//   ring == 1 : back to back on the slot's stream, with timing events between the kernels.
-//   ring >= 2 : two handle-wide streams.  The persistent front-end of batch k+1 (f_stream) runs WHILE the H+V kernel
-//               of batch k (hv_stream) does: both are sized to share every SM (see k_frontend2p).
-template <int FMT>
-static int launch_hv(ssimu2_handle* h, Slot& sl)
-{
-    const Geo& g = h->geo;
-    const uint32_t n = sl.count;
-    HvArgs a{};
-    a.hstate = sl.hstate;
-    a.flags = sl.hvflags;
-    a.ticket = sl.hvflags + (size_t)h->batch * g.total_recs;
-    a.partials = sl.partials;
-    a.epoch = ++sl.epoch;
-    a.nframes = (int)n;
-    cudaStream_t fs = h->two_stream ? h->f_stream : sl.stream;
-    cudaStream_t st = h->two_stream ? h->hv_stream : sl.stream;
-    // timing marks: [0,1] around the front-end (on its stream), [2,3] around k_hv, [3,4] around finalize
-    if (sl.timed) cudaEventRecord(sl.ev_k[0], fs);
-    if (h->two_stream) {
-        k_frontend2p<FMT><<<h->num_sms * h->f2p_ctas, kF2PThreads, 0, fs>>>(g, sl.in, sl.xyb, a.ticket + 1, (int)n);
-    } else if (h->frontend2) {
-        const int rx = (g.sc[0].w + kF2Region - 1) / kF2Region, ry = (g.sc[0].h + kF2Region - 1) / kF2Region;
-        const int per_cta = (kF2Threads / 32) * kF2RegionsPerWarp;
-        k_frontend2<FMT><<<dim3((rx + per_cta - 1) / per_cta, ry, n), kF2Threads, 0, fs>>>(g, sl.in, sl.xyb);
-    } else {
-        dim3 grid((g.sc[0].w + 63) / 64, (g.sc[0].h + 63) / 64, n);
-        k_frontend<FMT><<<grid, kFThreads, kFSmemTotal, fs>>>(g, sl.in, sl.xyb);
-    }
-    if (sl.timed) cudaEventRecord(sl.ev_k[1], fs);
-    if (h->two_stream) {
-        CU_TRY(cudaEventRecord(sl.ev_f, fs));
-        CU_TRY(cudaStreamWaitEvent(st, sl.ev_f, 0));
-    }
-    if (sl.timed) cudaEventRecord(sl.ev_k[2], st);
-    k_hv<<<(unsigned)(g.items_v * n), kXThreads, kXSmemBytes, st>>>(g, sl.maps_x, a);
-    if (sl.timed) cudaEventRecord(sl.ev_k[3], st);
-    k_finalize<<<n, 128, 0, st>>>(g, sl.partials, sl.norms_d, h->scores_ring_d, sl.first_ticket, kResultCap, sl.scores_d, a.ticket);
-    if (sl.timed) cudaEventRecord(sl.ev_k[4], st);
-    h->launches += 3;
-    CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(sl.scores_h, sl.scores_d, n * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(sl.norms_h, sl.norms_d, (size_t)n * 108 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaEventRecord(sl.ev_done, st));
-    sl.inflight = true;
-    sl.was_timed = sl.timed;
-    return 0;
-}
-
-// [H pass of slot hp] + [front-end of slot fk] in one launch on the main stream; either may be null
-template <int FMT>
-static int launch_fused(ssimu2_handle* h, Slot* hp, Slot* fk)
-{
-    const Geo& g = h->geo;
-    FuseArgs fa{};
-    fa.frames_h = hp ? (int)hp->count : 1;
-    fa.n_h_blocks = hp ? g.items_h * (int)hp->count : 0;
-    fa.tiles_x = (g.sc[0].w + 63) / 64;
-    fa.tiles_y = (g.sc[0].h + 63) / 64;
-    fa.n_f_blocks = fk ? fa.tiles_x * fa.tiles_y * (int)fk->count : 0;
-    const unsigned total = (unsigned)(fa.n_h_blocks + fa.n_f_blocks);
-    if (total == 0) return 0;
-    Slot& any = hp ? *hp : *fk;
-    k_fused_fh<FMT><<<total, kHThreads, kHSmemBytes, h->main_stream>>>(g, hp ? hp->maps_h : any.maps_h, fk ? fk->in : any.in,
-                                                                    fk ? fk->xyb : any.xyb, fa);
-    h->launches += 1;
-    CU_TRY(cudaGetLastError());
-    return 0;
-}
-
-// V pass + finalize + result copy of a slot whose H pass has been enqueued on the main stream
-static int launch_tail(ssimu2_handle* h, Slot& sl)
-{
-    const Geo& g = h->geo;
-    const uint32_t n = sl.count;
-    CU_TRY(cudaEventRecord(sl.ev_mid, h->main_stream));
-    CU_TRY(cudaStreamWaitEvent(sl.stream, sl.ev_mid, 0));
-    cudaStream_t st = sl.stream;
-    k_vpass<<<dim3(g.items_v, n), kVTmaThreads, kVSmemBytes, st>>>(g, sl.maps, sl.partials);
-    k_finalize<<<n, 128, 0, st>>>(g, sl.partials, sl.norms_d, h->scores_ring_d, sl.first_ticket, kResultCap, sl.scores_d, nullptr);
-    h->launches += 2;
-    CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(sl.scores_h, sl.scores_d, n * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(sl.norms_h, sl.norms_d, (size_t)n * 108 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaEventRecord(sl.ev_done, st));
-    sl.inflight = true;
-    sl.was_timed = false;
-    return 0;
-}
-
-template <int FMT>
-static int launch_batch_fmt(ssimu2_handle* h, Slot& sl, int si)
-{
-    if (h->pipeline == 0) return launch_hv<FMT>(h, sl);
-    if (!h->fuse) return launch_unfused<FMT>(h, sl);
-    Slot* prev = h->awaiting >= 0 ? &h->slots[h->awaiting] : nullptr;
-    int r = launch_fused<FMT>(h, prev, &sl);
-    if (r) return r;
-    if (prev) {
-        r = launch_tail(h, *prev);
-        if (r) return r;
-        prev->awaiting = false;
-    }
-    sl.awaiting = true;
-    h->awaiting = si;
-    return 0;
-}
-
-// the slot whose front-end ran but whose H pass is still waiting for a partner: finish it alone
-template <int FMT>
-static int complete_awaiting_fmt(ssimu2_handle* h)
-{
-    if (h->awaiting < 0) return 0;
-    Slot& sl = h->slots[h->awaiting];
-    int r = launch_fused<FMT>(h, &sl, nullptr);
-    if (r) return r;
-    r = launch_tail(h, sl);
-    if (r) return r;
-    sl.awaiting = false;
-    h->awaiting = -1;
-    return 0;
-}
-
-static int complete_awaiting(ssimu2_handle* h)
-{
-#define CALL_(F) complete_awaiting_fmt<F>(h)
+    CU_TRY(cudaMemcpyAsync(sl.in_d + f0, sl.in_h + f0, (size_t)n * sizeof(FramePair), cudaMemcpyHostToDevice, sl.stream));
+    if (time_it) cudaEventRecord(sl.ev_k[0], sl.stream);
     switch (h->cfg.format) {
-    case kNV12: return CALL_(kNV12);
-    case kP016: return CALL_(kP016);
-    case kSRGB8: return CALL_(kSRGB8);
-    case kSRGB16: return CALL_(kSRGB16);
-    case kSRGBF32: return CALL_(kSRGBF32);
-    case kLINEARF32: return CALL_(kLINEARF32);
+    case kNV12: launch_frontend_kernel<kNV12>(h, sl, f0, n); break;
+    case kP016: launch_frontend_kernel<kP016>(h, sl, f0, n); break;
+    case kSRGB8: launch_frontend_kernel<kSRGB8>(h, sl, f0, n); break;
+    case kSRGB16: launch_frontend_kernel<kSRGB16>(h, sl, f0, n); break;
+    case kSRGBF32: launch_frontend_kernel<kSRGBF32>(h, sl, f0, n); break;
+    case kLINEARF32: launch_frontend_kernel<kLINEARF32>(h, sl, f0, n); break;
+    default: return SSIMU2_E_UNSUPPORTED;
     }
-#undef CALL_
-    return SSIMU2_E_UNSUPPORTED;
+    if (time_it) cudaEventRecord(sl.ev_k[1], sl.stream);
+    CU_TRY(cudaGetLastError());
+    h->launches += 1;
+    if (sl.fe_launches >= sl.ev_fe.size()) {
+        cudaEvent_t e = nullptr;
+        CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        sl.ev_fe.push_back(e);
+    }
+    CU_TRY(cudaEventRecord(sl.ev_fe[sl.fe_launches], sl.stream));
+    for (uint32_t i = f0; i < upto; i++) sl.fe_seq[i] = (uint16_t)sl.fe_launches;
+    sl.fe_launches++;
+    sl.fe_pairs = upto;
+    return 0;
 }
 
 // launch the batch recorded in slot si (it must hold at least one pair and not be launched yet)
 static int launch_batch(ssimu2_handle* h, int si)
 {
     Slot& sl = h->slots[si];
-    if (sl.count == 0 || sl.inflight || sl.awaiting) return 0;
-    cudaStream_t first = h->fuse ? h->main_stream : (h->two_stream ? h->f_stream : sl.stream);
-    if (sl.have_dep && sl.last_stream != (void*)first) {
-        // order the batch after everything the submitter enqueued so far on its stream
-        CU_TRY(cudaEventRecord(sl.ev_in, (cudaStream_t)sl.last_stream));
-        CU_TRY(cudaStreamWaitEvent(first, sl.ev_in, 0));
+    if (sl.count == 0 || sl.inflight) return 0;
+    const Geo& g = h->geo;
+    const uint32_t n = sl.count;
+    cudaStream_t st = sl.stream;
+    // per-kernel timing is only meaningful when the whole batch goes through one front-end launch
+    const bool timed = sl.timed && sl.fe_pairs == 0;
+    int r = launch_frontend(h, sl, n, timed);
+    if (r) return r;
+    if (h->pipeline == 0) {
+        HvArgs a{};
+        a.hstate = sl.hstate;
+        a.flags = sl.hvflags;
+        a.ticket = sl.hvflags + (size_t)h->batch * g.total_recs;
+        a.partials = sl.partials;
+        a.epoch = ++sl.epoch;
+        a.nframes = (int)n;
+        if (timed) cudaEventRecord(sl.ev_k[2], st);
+        k_hv<<<(unsigned)(g.items_v * n), kXThreads, kXSmemBytes, st>>>(g, sl.maps_x, a);
+        if (timed) cudaEventRecord(sl.ev_k[3], st);
+        k_finalize<<<n, 128, 0, st>>>(g, sl.partials, sl.norms_d, h->scores_ring_d, sl.first_ticket, kResultCap, sl.scores_d, a.ticket);
+        if (timed) cudaEventRecord(sl.ev_k[4], st);
+        h->launches += 2;
+    } else {
+        k_hpass<<<dim3(g.items_h, n), kHThreads, kHSmemBytes, st>>>(g, sl.maps_h);
+        if (timed) cudaEventRecord(sl.ev_k[2], st);
+        k_vpass<<<dim3(g.items_v, n), kVTmaThreads, kVSmemBytes, st>>>(g, sl.maps, sl.partials);
+        if (timed) cudaEventRecord(sl.ev_k[3], st);
+        k_finalize<<<n, 128, 0, st>>>(g, sl.partials, sl.norms_d, h->scores_ring_d, sl.first_ticket, kResultCap, sl.scores_d, nullptr);
+        if (timed) cudaEventRecord(sl.ev_k[4], st);
+        h->launches += 3;
     }
-    if ((h->fuse || h->two_stream) && sl.staged) {
-        // host frames were copied on the slot's stream: the front-end on the shared stream must see them
-        CU_TRY(cudaEventRecord(sl.ev_in, sl.stream));
-        CU_TRY(cudaStreamWaitEvent(first, sl.ev_in, 0));
-    }
-    sl.have_dep = false;
-    sl.staged = false;
-#define CALL_(F) launch_batch_fmt<F>(h, sl, si)
-    switch (h->cfg.format) {
-    case kNV12: return CALL_(kNV12);
-    case kP016: return CALL_(kP016);
-    case kSRGB8: return CALL_(kSRGB8);
-    case kSRGB16: return CALL_(kSRGB16);
-    case kSRGBF32: return CALL_(kSRGBF32);
-    case kLINEARF32: return CALL_(kLINEARF32);
-    }
-#undef CALL_
-    return SSIMU2_E_UNSUPPORTED;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(sl.scores_h, sl.scores_d, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (!h->score_only)
+        CU_TRY(cudaMemcpyAsync(sl.norms_h, sl.norms_d, (size_t)n * 108 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventRecord(sl.ev_done, st));
+    sl.inflight = true;
+    sl.was_timed = timed;
+    return 0;
 }
 
 // wait for a launched slot and move its results into the ticket-indexed host rings
@@ -465,19 +363,16 @@ static int harvest(ssimu2_handle* h, uint32_t si)
     for (uint32_t i = 0; i < sl.count; i++) {
         uint64_t t = sl.first_ticket + i, r = t % kResultCap;
         h->res_scores[r] = sl.scores_h[i];
-        memcpy(&h->res_norms[r * 108], &sl.norms_h[(size_t)i * 108], 108 * sizeof(double));
+        if (!h->score_only) memcpy(&h->res_norms[r * 108], &sl.norms_h[(size_t)i * 108], 108 * sizeof(double));
         h->res_slot[r] = (int32_t)si;
     }
     if (sl.was_timed) {
+        // fused: front-end [0,1], k_hv [2,3], (no separate V pass), finalize [3,4]; split: front-end [0,1], H [1,2], V [2,3], finalize [3,4]
+        static const int fa[4] = {0, 2, 3, 3}, fb[4] = {1, 3, 3, 4}, sa[4] = {0, 1, 2, 3}, sb[4] = {1, 2, 3, 4};
         for (int k = 0; k < 4; k++) {
-            if (h->pipeline == 0) {
-                // front-end [0,1], k_hv [2,3], (no separate V pass), finalize [3,4]
-                static const int a[4] = {0, 2, 3, 3}, b[4] = {1, 3, 3, 4};
-                h->last_ms[k] = 0.f;
-                if (a[k] != b[k]) cudaEventElapsedTime(&h->last_ms[k], sl.ev_k[a[k]], sl.ev_k[b[k]]);
-            } else {
-                cudaEventElapsedTime(&h->last_ms[k], sl.ev_k[k], sl.ev_k[k + 1]);
-            }
+            const int a = h->pipeline == 0 ? fa[k] : sa[k], b = h->pipeline == 0 ? fb[k] : sb[k];
+            h->last_ms[k] = 0.f;
+            if (a != b) cudaEventElapsedTime(&h->last_ms[k], sl.ev_k[a], sl.ev_k[b]);
             h->total_ms[k] += h->last_ms[k];
         }
         h->timed_batches++;
@@ -485,6 +380,8 @@ static int harvest(ssimu2_handle* h, uint32_t si)
     }
     sl.inflight = false;
     sl.count = 0;
+    sl.fe_pairs = 0;
+    sl.fe_launches = 0;
     return 0;
 }
 
@@ -492,19 +389,14 @@ static int harvest(ssimu2_handle* h, uint32_t si)
 static int prepare_cur(ssimu2_handle* h)
 {
     Slot& sl = h->slots[h->cur];
-    if (sl.awaiting) {  // the ring wrapped onto the batch whose H pass is still parked: finish it first
-        int r = complete_awaiting(h);
-        if (r) return r;
-    }
     if (sl.inflight) {
         int r = harvest(h, h->cur);
         if (r) return r;
     }
     if (sl.count == 0) {
         sl.first_ticket = h->next_ticket;
-        sl.in.first_ticket = h->next_ticket;
         sl.have_dep = false;
-        sl.last_stream = nullptr;
+        sl.dep_stream = nullptr;
     }
     return 0;
 }
@@ -518,6 +410,8 @@ static int finish_pair(ssimu2_handle* h)
         int r = launch_batch(h, (int)h->cur);
         if (r) return r;
         h->cur = (h->cur + 1) % h->ring;
+    } else if (h->input_group && sl.count - sl.fe_pairs >= h->input_group) {
+        return launch_frontend(h, sl, sl.count, false);
     }
     return 0;
 }
@@ -544,18 +438,46 @@ static int locate(ssimu2_handle* h, uint64_t ticket, uint32_t* slot_out)
     return 0;
 }
 
+// the slot that holds `ticket`, launched if it was still being filled; where = 0 when the results are already on the host
+static int locate_launched(ssimu2_handle* h, uint64_t ticket, uint32_t* si, int* where)
+{
+    *where = locate(h, ticket, si);
+    if (*where < 0) return SSIMU2_E_TICKET;
+    if (*where == 2) {
+        int r = launch_batch(h, (int)*si);
+        if (r) return r;
+        if (*si == h->cur) h->cur = (h->cur + 1) % h->ring;
+        *where = 1;
+    }
+    return 0;
+}
+
+// record the submitter's stream as a dependency of the input group being recorded
+static int note_dependency(Slot& sl, void* stream)
+{
+    if ((cudaStream_t)stream == sl.stream) return 0;
+    if (sl.have_dep && sl.dep_stream != stream) {
+        // the submitter switched streams inside one input group: pin the dependency on the previous stream now
+        CU_TRY(cudaStreamWaitEvent(sl.stream, sl.ev_in, 0));
+    }
+    CU_TRY(cudaEventRecord(sl.ev_in, (cudaStream_t)stream));
+    sl.dep_stream = stream;
+    sl.have_dep = true;
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
 
-uint32_t ssimu2_version(void) { return (1u << 16) | 0u; }
+uint32_t ssimu2_version(void) { return (2u << 16) | 0u; }
 
 const char* ssimu2_strerror(int status)
 {
     switch (status) {
     case SSIMU2_OK: return "ok";
     case SSIMU2_E_INVALID: return "invalid argument";
-    case SSIMU2_E_UNSUPPORTED: return "unsupported format or size";
+    case SSIMU2_E_UNSUPPORTED: return "unsupported format, size or mode";
     case SSIMU2_E_NOMEM: return "out of memory";
     case SSIMU2_E_NODEVICE: return "no usable CUDA device (sm_100 required)";
     case SSIMU2_E_TICKET: return "unknown or expired ticket";
@@ -572,6 +494,11 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
     if (cfg->width < 8 || cfg->height < 8 || cfg->width > 32768 || cfg->height > 32768) return SSIMU2_E_UNSUPPORTED;
     if (cfg->format < 0 || cfg->format > kLINEARF32) return SSIMU2_E_UNSUPPORTED;
     if (cfg->matrix < 0 || cfg->matrix > 2) return SSIMU2_E_UNSUPPORTED;
+    if (cfg->pipeline > SSIMU2_PIPELINE_SPLIT) return SSIMU2_E_UNSUPPORTED;
+    if (cfg->flags & ~(SSIMU2_FLAG_SCORE_ONLY | SSIMU2_FLAG_NO_TIMING)) return SSIMU2_E_UNSUPPORTED;
+    if ((cfg->flags & SSIMU2_FLAG_SCORE_ONLY) && cfg->pipeline != SSIMU2_PIPELINE_DEFAULT) return SSIMU2_E_UNSUPPORTED;
+    for (int i = 0; i < 5; i++)
+        if (cfg->reserved[i]) return SSIMU2_E_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
         cudaGetLastError();
@@ -580,7 +507,8 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
     if (cfg->device < 0 || cfg->device >= ndev) return SSIMU2_E_INVALID;
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, cfg->device));
-    if (prop.major != 10) return SSIMU2_E_NODEVICE;  // the only SASS in this library is sm_100a
+    // the only SASS in this library is sm_100a; architecture-specific targets are not forward compatible (sm_103 cannot run it)
+    if (prop.major != 10 || prop.minor != 0) return SSIMU2_E_NODEVICE;
 
     ssimu2_handle* h = new (std::nothrow) ssimu2_handle();
     if (!h) return SSIMU2_E_NOMEM;
@@ -589,22 +517,27 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
     if (h->batch > (uint32_t)kMaxBatch) h->batch = kMaxBatch;
     h->ring = cfg->ring ? cfg->ring : kDefaultRing;
     if (h->ring > 16) h->ring = 16;
+    h->input_group = cfg->input_group >= h->batch ? 0 : cfg->input_group;
+    h->pipeline = (int)cfg->pipeline;
+    h->score_only = (cfg->flags & SSIMU2_FLAG_SCORE_ONLY) != 0;
     build_geo(h);
+    DeviceGuard guard(cfg->device);
     int rc = 0;
 #define CR(expr)                                  \
     do {                                          \
         cudaError_t _e = (expr);                  \
         if (_e != cudaSuccess) {                  \
+            cudaGetLastError();                   \
             rc = (_e == cudaErrorMemoryAllocation) ? SSIMU2_E_NOMEM : (int)_e; \
             goto fail;                            \
         }                                         \
     } while (0)
-    CR(cudaSetDevice(cfg->device));
     try {
         h->slots.resize(h->ring);
         h->res_scores.assign(kResultCap, 0.0);
         h->res_norms.assign(kResultCap * 108, 0.0);
         h->res_slot.assign(kResultCap, -1);
+        for (auto& sl : h->slots) sl.fe_seq.assign(h->batch, 0);
     } catch (...) {
         rc = SSIMU2_E_NOMEM;
         goto fail;
@@ -614,45 +547,14 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
     h->device_bytes += kResultCap * sizeof(double);
     CR(cudaFuncSetAttribute((const void*)k_hpass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBytes));
     CR(cudaFuncSetAttribute((const void*)k_vpass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVSmemBytes));
-    static_assert(kHSmemBytes >= kFSmemTotal, "the fused kernel runs front-end tiles inside the H pass allocation");
-    {
-        // SSIMU2_PIPELINE = hv (default) | fh | split; "split" keeps the H-pass planes in HBM (ssimu2_debug_read what = 1)
-        const char* pm = getenv("SSIMU2_PIPELINE");
-        h->pipeline = (pm && !strcmp(pm, "fh")) ? 1 : ((pm && !strcmp(pm, "split")) ? 2 : 0);
-    }
-    {
-        const char* fe = getenv("SSIMU2_FRONTEND");
-        h->frontend2 = !(fe && !strcmp(fe, "1"));
-    }
     CR(cudaFuncSetAttribute((const void*)k_hv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXSmemBytes));
-    h->fuse = h->pipeline == 1 && h->ring >= 2 && getenv("SSIMU2_NO_FUSE") == nullptr;
-    h->two_stream = h->pipeline == 0 && h->ring >= 2 && getenv("SSIMU2_TWO_STREAM") != nullptr;  // experimental, off by default
-    h->num_sms = prop.multiProcessorCount;
-    if (const char* e = getenv("SSIMU2_F2P_CTAS")) h->f2p_ctas = atoi(e) > 0 ? atoi(e) : 1;
-    if (h->two_stream) {
-        int lo = 0, hi = 0;
-        CR(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CR(cudaStreamCreateWithPriority(&h->f_stream, cudaStreamNonBlocking, lo));
-        CR(cudaStreamCreateWithPriority(&h->hv_stream, cudaStreamNonBlocking, hi));  // k_hv CTAs are placed first
-    }
-    CR(cudaStreamCreateWithFlags(&h->main_stream, cudaStreamNonBlocking));
-    {
-        static const void* ffn[6] = {(const void*)k_frontend<kNV12>,    (const void*)k_frontend<kP016>,
-                                     (const void*)k_frontend<kSRGB8>,   (const void*)k_frontend<kSRGB16>,
-                                     (const void*)k_frontend<kSRGBF32>, (const void*)k_frontend<kLINEARF32>};
-        CR(cudaFuncSetAttribute(ffn[cfg->format], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmemTotal));
-        static const void* gfn[6] = {(const void*)k_fused_fh<kNV12>,    (const void*)k_fused_fh<kP016>,
-                                     (const void*)k_fused_fh<kSRGB8>,   (const void*)k_fused_fh<kSRGB16>,
-                                     (const void*)k_fused_fh<kSRGBF32>, (const void*)k_fused_fh<kLINEARF32>};
-        CR(cudaFuncSetAttribute(gfn[cfg->format], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBytes));
-    }
-    if ((cfg->format == kNV12 || cfg->format == kP016) && getenv("SSIMU2_NO_LUT") == nullptr) {
+    if (cfg->format == kNV12 || cfg->format == kP016) {
         const int n = cfg->format == kNV12 ? 256 : 1024, shift = cfg->format == kNV12 ? 0 : 6;
         const size_t bytes = (size_t)2 * n * n * sizeof(float);
         CR(cudaMalloc(&h->eotf_lut, bytes));
-        k_build_eotf_lut<<<(n * n + 255) / 256, 256, 0, h->main_stream>>>(h->geo.coef, n, shift, h->eotf_lut);
+        k_build_eotf_lut<<<(n * n + 255) / 256, 256>>>(h->geo.coef, n, shift, h->eotf_lut);
         CR(cudaGetLastError());
-        CR(cudaStreamSynchronize(h->main_stream));
+        CR(cudaDeviceSynchronize());
         h->geo.eotf_lut = h->eotf_lut;
         h->geo.lut_n = n;
         h->geo.lut_shift = shift;
@@ -666,11 +568,10 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
         size_t hs_b = h->pipeline == 0 ? (size_t)g.total_recs * h->batch * kXHsBytes : 0;
         size_t fl_b = h->pipeline == 0 ? ((size_t)g.total_recs * h->batch + 2) * sizeof(uint32_t) : 0;
         size_t part_b = (size_t)g.total_strips * 18 * h->batch * sizeof(double);
+        size_t in_b = (size_t)h->batch * sizeof(FramePair);
         CR(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         CR(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
         CR(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
-        CR(cudaEventCreateWithFlags(&sl.ev_mid, cudaEventDisableTiming));
-        CR(cudaEventCreateWithFlags(&sl.ev_f, cudaEventDisableTiming));
         for (int k = 0; k < 5; k++) CR(cudaEventCreate(&sl.ev_k[k]));
         CR(cudaMalloc(&sl.xyb, xyb_b));
         if (hb_b) CR(cudaMalloc(&sl.hb, hb_b));
@@ -680,15 +581,19 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
             CR(cudaMemset(sl.hvflags, 0, fl_b));
         }
         CR(cudaMalloc(&sl.partials, part_b));
+        CR(cudaMemset(sl.partials, 0, part_b));
         CR(cudaMalloc(&sl.norms_d, (size_t)h->batch * 108 * sizeof(double)));
         CR(cudaMalloc(&sl.scores_d, (size_t)h->batch * sizeof(double)));
+        CR(cudaMalloc(&sl.in_d, in_b));
+        CR(cudaMallocHost(&sl.in_h, in_b));
         CR(cudaMallocHost(&sl.norms_h, (size_t)h->batch * 108 * sizeof(double)));
         CR(cudaMallocHost(&sl.scores_h, (size_t)h->batch * sizeof(double)));
-        h->device_bytes += xyb_b + hb_b + hs_b + fl_b + part_b + (size_t)h->batch * 109 * sizeof(double);
+        h->device_bytes += xyb_b + hb_b + hs_b + fl_b + part_b + in_b + (size_t)h->batch * 109 * sizeof(double);
         rc = build_tma_maps(h, sl);
         if (rc) goto fail;
-        sl.timed = !h->fuse && getenv("SSIMU2_NO_TIMING") == nullptr;
+        sl.timed = (cfg->flags & SSIMU2_FLAG_NO_TIMING) == 0;
     }
+    CR(cudaDeviceSynchronize());
     *out = h;
     return SSIMU2_OK;
 fail:
@@ -700,29 +605,23 @@ fail:
 int ssimu2_destroy(ssimu2_t* h)
 {
     if (!h) return SSIMU2_OK;
-    cudaSetDevice(h->cfg.device);
-    if (h->main_stream) cudaStreamSynchronize(h->main_stream);
-    if (h->f_stream) cudaStreamSynchronize(h->f_stream);
-    if (h->hv_stream) cudaStreamSynchronize(h->hv_stream);
+    DeviceGuard guard(h->cfg.device);
     for (auto& sl : h->slots) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
-        if (sl.ev_mid) cudaEventDestroy(sl.ev_mid);
-        if (sl.ev_f) cudaEventDestroy(sl.ev_f);
         if (sl.ev_in) cudaEventDestroy(sl.ev_in);
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
         for (int k = 0; k < 5; k++)
             if (sl.ev_k[k]) cudaEventDestroy(sl.ev_k[k]);
-        cudaFree(sl.xyb); cudaFree(sl.hb); cudaFree(sl.hstate); cudaFree(sl.hvflags); cudaFree(sl.partials); cudaFree(sl.norms_d); cudaFree(sl.scores_d);
-        cudaFree(sl.staging);
+        for (cudaEvent_t e : sl.ev_fe) cudaEventDestroy(e);
+        cudaFree(sl.xyb); cudaFree(sl.hb); cudaFree(sl.hstate); cudaFree(sl.hvflags); cudaFree(sl.partials);
+        cudaFree(sl.norms_d); cudaFree(sl.scores_d); cudaFree(sl.staging); cudaFree(sl.in_d);
+        if (sl.in_h) cudaFreeHost(sl.in_h);
         if (sl.norms_h) cudaFreeHost(sl.norms_h);
         if (sl.scores_h) cudaFreeHost(sl.scores_h);
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     cudaFree(h->scores_ring_d);
     cudaFree(h->eotf_lut);
-    if (h->main_stream) cudaStreamDestroy(h->main_stream);
-    if (h->f_stream) cudaStreamDestroy(h->f_stream);
-    if (h->hv_stream) cudaStreamDestroy(h->hv_stream);
     delete h;
     return SSIMU2_OK;
 }
@@ -737,22 +636,15 @@ int ssimu2_mem_usage(const ssimu2_t* h, size_t* bytes)
 int ssimu2_submit(ssimu2_t* h, const ssimu2_frame* ref, const ssimu2_frame* dis, void* stream, uint64_t* ticket)
 {
     if (!h || !frame_ok(h, ref) || !frame_ok(h, dis)) return SSIMU2_E_INVALID;
-    CU_TRY(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     int r = prepare_cur(h);
     if (r) return r;
     Slot& sl = h->slots[h->cur];
-    cudaStream_t first = h->fuse ? h->main_stream : (h->two_stream ? h->f_stream : sl.stream);
-    if (sl.have_dep && sl.last_stream != stream && sl.last_stream != (void*)first) {
-        // submitter switched streams inside one batch: pin the dependency on the previous one now
-        CU_TRY(cudaEventRecord(sl.ev_in, (cudaStream_t)sl.last_stream));
-        CU_TRY(cudaStreamWaitEvent(first, sl.ev_in, 0));
-    }
-    sl.last_stream = stream;
-    sl.have_dep = true;
-    FrameIn& a = sl.in.ref[sl.count];
-    FrameIn& b = sl.in.dis[sl.count];
-    a.p0 = (const uint8_t*)ref->plane[0]; a.p1 = (const uint8_t*)ref->plane[1]; a.pitch = ref->pitch; a.pad = 0;
-    b.p0 = (const uint8_t*)dis->plane[0]; b.p1 = (const uint8_t*)dis->plane[1]; b.pitch = dis->pitch; b.pad = 0;
+    r = note_dependency(sl, stream);
+    if (r) return r;
+    FramePair& fp = sl.in_h[sl.count];
+    fp.ref.p0 = (const uint8_t*)ref->plane[0]; fp.ref.p1 = (const uint8_t*)ref->plane[1]; fp.ref.pitch = ref->pitch; fp.ref.pad = 0;
+    fp.dis.p0 = (const uint8_t*)dis->plane[0]; fp.dis.p1 = (const uint8_t*)dis->plane[1]; fp.dis.pitch = dis->pitch; fp.dis.pad = 0;
     if (ticket) *ticket = h->next_ticket;
     return finish_pair(h);
 }
@@ -776,7 +668,7 @@ int ssimu2_submit_host(ssimu2_t* h, const ssimu2_frame* ref, const ssimu2_frame*
     if (yuv && (ref->plane[1] <= ref->plane[0] || dis->plane[1] <= dis->plane[0] ||
                 ref->plane[1] - ref->plane[0] >= frame_bytes || dis->plane[1] - dis->plane[0] >= frame_bytes))
         return SSIMU2_E_INVALID;
-    CU_TRY(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     if (frame_bytes > h->staging_frame_bytes) {
         // (re)allocate the staging rings; rare (first call), so a full drain is acceptable
         int fr = ssimu2_flush(h);
@@ -801,11 +693,9 @@ int ssimu2_submit_host(ssimu2_t* h, const ssimu2_frame* ref, const ssimu2_frame*
     uint8_t* db = da + h->staging_frame_bytes;
     CU_TRY(cudaMemcpyAsync(da, (const void*)ref->plane[0], frame_bytes, cudaMemcpyHostToDevice, sl.stream));
     CU_TRY(cudaMemcpyAsync(db, (const void*)dis->plane[0], frame_bytes, cudaMemcpyHostToDevice, sl.stream));
-    FrameIn& a = sl.in.ref[sl.count];
-    FrameIn& b = sl.in.dis[sl.count];
-    a.p0 = da; a.p1 = yuv ? da + (ref->plane[1] - ref->plane[0]) : nullptr; a.pitch = ref->pitch; a.pad = 0;
-    b.p0 = db; b.p1 = yuv ? db + (dis->plane[1] - dis->plane[0]) : nullptr; b.pitch = dis->pitch; b.pad = 0;
-    sl.staged = true;
+    FramePair& fp = sl.in_h[sl.count];
+    fp.ref.p0 = da; fp.ref.p1 = yuv ? da + (ref->plane[1] - ref->plane[0]) : nullptr; fp.ref.pitch = ref->pitch; fp.ref.pad = 0;
+    fp.dis.p0 = db; fp.dis.p1 = yuv ? db + (dis->plane[1] - dis->plane[0]) : nullptr; fp.dis.pitch = dis->pitch; fp.dis.pad = 0;
     if (ticket) *ticket = h->next_ticket;
     return finish_pair(h);
 }
@@ -825,40 +715,35 @@ int ssimu2_submit_host_batch(ssimu2_t* h, uint32_t n, const ssimu2_frame* refs, 
 int ssimu2_flush(ssimu2_t* h)
 {
     if (!h) return SSIMU2_E_INVALID;
-    CU_TRY(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     Slot& sl = h->slots[h->cur];
-    if (sl.count && !sl.inflight && !sl.awaiting) {
+    if (sl.count && !sl.inflight) {
         int r = launch_batch(h, (int)h->cur);
         if (r) return r;
         h->cur = (h->cur + 1) % h->ring;
     }
-    // nothing may stay parked after a flush: the last batch gets its H pass without a partner
-    return h->fuse ? complete_awaiting(h) : SSIMU2_OK;
+    return SSIMU2_OK;
 }
 
 int ssimu2_wait(ssimu2_t* h, uint64_t ticket)
 {
     if (!h) return SSIMU2_E_INVALID;
-    CU_TRY(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     uint32_t si = 0;
-    int where = locate(h, ticket, &si);
-    if (where < 0) return SSIMU2_E_TICKET;
-    if (where == 2) {
-        // not fully launched yet: a partial batch still being filled, or a batch parked between its front-end and
-        // its H pass.  Launch what is missing for THIS ticket only.
-        Slot& sl = h->slots[si];
-        if (!sl.awaiting) {
-            int r = launch_batch(h, (int)si);
-            if (r) return r;
-            if (si == h->cur) h->cur = (h->cur + 1) % h->ring;
-        }
-        if (sl.awaiting) {
-            int r = complete_awaiting(h);
-            if (r) return r;
-        }
-        where = 1;
-    }
+    int where = 0;
+    int r = locate_launched(h, ticket, &si, &where);
+    if (r) return r;
     if (where == 1) return harvest(h, si);
+    return SSIMU2_OK;
+}
+
+int ssimu2_completed(ssimu2_t* h, uint64_t* watermark)
+{
+    if (!h || !watermark) return SSIMU2_E_INVALID;
+    uint64_t w = h->next_ticket;
+    for (const Slot& sl : h->slots)
+        if (sl.count && sl.first_ticket < w) w = sl.first_ticket;
+    *watermark = w;
     return SSIMU2_OK;
 }
 
@@ -885,6 +770,7 @@ int ssimu2_get_scores(ssimu2_t* h, uint64_t first_ticket, uint32_t n, double* sc
 int ssimu2_get_norms(ssimu2_t* h, uint64_t ticket, double* norms108)
 {
     if (!h || !norms108) return SSIMU2_E_INVALID;
+    if (h->score_only) return SSIMU2_E_UNSUPPORTED;
     int r = ssimu2_wait(h, ticket);
     if (r) return r;
     memcpy(norms108, &h->res_norms[(ticket % kResultCap) * 108], 108 * sizeof(double));
@@ -902,24 +788,31 @@ int ssimu2_compute_sync(ssimu2_t* h, const ssimu2_frame* ref, const ssimu2_frame
 int ssimu2_stream_wait(ssimu2_t* h, uint64_t ticket, void* stream)
 {
     if (!h) return SSIMU2_E_INVALID;
-    CU_TRY(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     uint32_t si = 0;
-    int where = locate(h, ticket, &si);
-    if (where < 0) return SSIMU2_E_TICKET;
-    if (where == 2) {
-        Slot& sl = h->slots[si];
-        if (!sl.awaiting) {
-            int r = launch_batch(h, (int)si);
-            if (r) return r;
-            if (si == h->cur) h->cur = (h->cur + 1) % h->ring;
-        }
-        if (sl.awaiting) {
-            int r = complete_awaiting(h);
-            if (r) return r;
-        }
-        where = 1;
-    }
+    int where = 0;
+    int r = locate_launched(h, ticket, &si, &where);
+    if (r) return r;
     if (where == 1) CU_TRY(cudaStreamWaitEvent((cudaStream_t)stream, h->slots[si].ev_done, 0));
+    return SSIMU2_OK;
+}
+
+int ssimu2_stream_wait_input(ssimu2_t* h, uint64_t ticket, void* stream)
+{
+    if (!h) return SSIMU2_E_INVALID;
+    DeviceGuard guard(h->cfg.device);
+    uint32_t si = 0;
+    const int where = locate(h, ticket, &si);
+    if (where < 0) return SSIMU2_E_TICKET;
+    if (where == 0) return SSIMU2_OK;   // completed long ago
+    Slot& sl = h->slots[si];
+    const uint32_t idx = (uint32_t)(ticket - sl.first_ticket);
+    if (idx >= sl.fe_pairs) {
+        // still waiting in an input group: launch the front-end for everything recorded so far
+        int r = launch_frontend(h, sl, sl.count, false);
+        if (r) return r;
+    }
+    CU_TRY(cudaStreamWaitEvent((cudaStream_t)stream, sl.ev_fe[sl.fe_seq[idx]], 0));
     return SSIMU2_OK;
 }
 
@@ -945,14 +838,21 @@ int ssimu2_get_info(const ssimu2_t* h, ssimu2_info* info)
     info->ring = h->ring;
     info->alg_bytes_per_pair = h->alg_bytes;
     info->kernel_launches = h->launches;
+    info->pipeline = (uint32_t)h->pipeline;
+    info->flags = h->cfg.flags;
+    info->input_group = h->input_group;
+    info->strips_per_pair = (uint32_t)h->geo.items_v;
+    info->io_bytes_per_pair = h->io_bytes;
     return SSIMU2_OK;
 }
 
+// ---- include/ssimu2_b200_debug.h ---------------------------------------------------------------
 int ssimu2_debug_read(ssimu2_t* h, uint64_t ticket, int what, int scale, float* out, size_t out_floats)
 {
     if (!h || !out || scale < 0 || scale >= h->geo.nscales) return SSIMU2_E_INVALID;
     int r = ssimu2_wait(h, ticket);
     if (r) return r;
+    DeviceGuard guard(h->cfg.device);
     int si = h->res_slot[ticket % kResultCap];
     if (si < 0) return SSIMU2_E_TICKET;
     Slot& sl = h->slots[si];

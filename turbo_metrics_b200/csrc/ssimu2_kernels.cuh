@@ -1,12 +1,13 @@
 // ssimu2_kernels.cuh -- device code of the B200-native SSIMULACRA2 frame-pair scorer (sm_100a).
 //
-// Pipeline per batch of frame pairs (4 launches, every launch covers all frames and all 6 scales):
-//   k_frontend : source pair -> linear RGB -> 2x box pyramid (kept on chip) -> XYB planes of all scales
-//   k_hpass    : per scale: XYB -> 5 products -> HORIZONTAL recursive Gaussian of
-//                {ref^2, dis^2, ref*dis, ref, dis} x 3 channels -> 15 planes
-//   k_vpass    : per scale: VERTICAL recursive Gaussian of the 15 planes, fused with the SSIM /
-//                artifact / detail-loss maps and their L1 / L4 partial sums (f64)
-//   k_finalize : partial sums -> 108 norms -> weighted sum -> score (f64)
+// Pipeline per batch of frame pairs (3 launches, every launch covers all frames and all 6 scales):
+//   k_frontend2 : source pair -> linear RGB -> 2x box pyramid (kept in registers) -> XYB planes of all scales
+//   k_hv        : per scale: products -> HORIZONTAL recursive Gaussian of {ref^2, dis^2, ref*dis, ref, dis} x 3 channels
+//                 -> VERTICAL recursive Gaussian -> SSIM / artifact / detail-loss maps -> L1 / L4 partial sums (f64);
+//                 the 15 H-pass planes never leave the SM
+//   k_finalize  : partial sums -> 108 norms -> weighted sum -> score (f64)
+// The development pipeline "split" runs the two passes as k_hpass + k_vpass with the H-pass planes in HBM (what the
+// bit-identity tests read back).
 //
 // Arithmetic contract: everything that feeds the recursive filters replicates, operation for
 // operation, the reference's CPU implementation (crates/ssimulacra2-cuda/examples/cpu.rs), including
@@ -25,7 +26,7 @@
 namespace ssimu2 {
 
 constexpr int kMaxScales = 6;
-constexpr int kMaxBatch = 32;
+constexpr int kMaxBatch = 1024;   // frame pairs per launch group (the frame table lives in device memory)
 
 enum Fmt : int { kNV12 = 0, kP016 = 1, kSRGB8 = 2, kSRGB16 = 3, kSRGBF32 = 4, kLINEARF32 = 5 };
 
@@ -71,10 +72,8 @@ struct FrameIn {
     uint32_t pad;
 };
 
-struct BatchIn {
-    FrameIn ref[kMaxBatch];
-    FrameIn dis[kMaxBatch];
-    unsigned long long first_ticket;
+struct FramePair {         // one entry of a batch slot's frame table (device memory, uploaded with the batch)
+    FrameIn ref, dis;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -217,152 +216,13 @@ __device__ __forceinline__ void linear_to_xyb(float r, float g, float b, const e
 }
 
 // ------------------------------------------------------------------------------------------
-// k_frontend: colour conversion + linear-RGB pyramid + XYB of every scale.
+// Front-end: colour conversion + linear-RGB pyramid + XYB of every scale.
 // Replaces the colour conversion kernels, downscale_by_2 (ssimulacra2-cuda-kernel/src/downscale.rs:4-35,
 // host loop ssimulacra2-cuda/src/lib.rs:162-183) and linear_to_xyb_packed (xyb.rs:82-102, lib.rs:188-210);
 // follows cpu.rs:545-579 (box sum order (0,0),(1,0),(0,1),(1,1), edge clamp min(src-1), x0.25) and
 // cpu.rs:363-377 (downscale in LINEAR RGB, XYB recomputed per scale).
 // ------------------------------------------------------------------------------------------
-// One CTA = one 64x64 source tile of one frame, both images (one after the other); 256 threads.
-// The linear-RGB tile and its 5 pyramid levels live in shared memory; only XYB planes are written.
-// All pixel loops are rolled (one inlined copy of the powf / cbrtf bodies each) to keep the kernel
-// inside the instruction cache.
 __device__ __forceinline__ float box4(float a, float b, float c, float d) { return ((((0.0f + a) + b) + c) + d) * 0.25f; }
-
-#ifndef KF_UNROLL
-#define KF_UNROLL 1
-#endif
-#ifndef KF_MINB
-#define KF_MINB 3
-#endif
-constexpr int kFUnroll = KF_UNROLL;
-constexpr int kFTile = 64;
-constexpr int kFThreads = 256;
-// shared linear-RGB levels: [3][side][side + 1]
-constexpr int kFOff0 = 0;
-constexpr int kFOff1 = kFOff0 + 3 * 64 * 65;
-constexpr int kFOff2 = kFOff1 + 3 * 32 * 33;
-constexpr int kFOff3 = kFOff2 + 3 * 16 * 17;
-constexpr int kFOff4 = kFOff3 + 3 * 8 * 9;
-constexpr int kFSmemFloats = kFOff4 + 3 * 4 * 5;
-constexpr size_t kFSmemBytes = (size_t)kFSmemFloats * sizeof(float);  // 65.4 KB
-
-// One 2x downscale step inside the tile: src level (side 2n, global size srcW x srcH) -> dst level (side n),
-// XYB of the dst level written to global.  cpu.rs:545-579 (sum order (0,0),(1,0),(0,1),(1,1); clamp; x0.25).
-template <int N, bool KEEP, int NT>
-__device__ __forceinline__ void down_level(const float* __restrict__ src, float* __restrict__ dst, int srcW, int srcH,
-                                           int ox0, int oy0, const ScaleDesc& sd, float* __restrict__ gdst,
-                                           const exact_math::CbrtScale& S)
-{
-    constexpr int SP = 2 * N + 1, DP = N + 1;
-    const size_t plane = (size_t)sd.h * sd.pitch;
-#pragma unroll 1
-    for (int idx = threadIdx.x; idx < N * N; idx += NT) {
-        const int lx = idx % N, ly = idx / N;
-        const int ox = ox0 + lx, oy = oy0 + ly;
-        const bool valid = ox < sd.w && oy < sd.h;
-        const int i1 = (2 * ox + 1 <= srcW - 1) ? 1 : 0, j1 = (2 * oy + 1 <= srcH - 1) ? 1 : 0;
-        float v[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const float* p = src + (c * 2 * N + 2 * ly) * SP + 2 * lx;
-            v[c] = valid ? box4(p[0], p[i1], p[j1 * SP], p[j1 * SP + i1]) : 0.0f;
-            if (KEEP) dst[(c * N + ly) * DP + lx] = v[c];
-        }
-        if (valid) {
-            float X, Y, B;
-            linear_to_xyb(v[0], v[1], v[2], S, X, Y, B);
-            const size_t off = (size_t)oy * sd.pitch + ox;
-            gdst[off] = X; gdst[plane + off] = Y; gdst[2 * plane + off] = B;
-        }
-    }
-}
-
-// shared-memory carve-up of one frontend tile: linear levels, then the two tables
-constexpr size_t kFOffT = (kFSmemBytes + 15) / 16 * 16;
-constexpr size_t kFOffS = kFOffT + sizeof(exact_math::PowfTables);
-constexpr size_t kFSmemTotal = kFOffS + sizeof(exact_math::CbrtScale);  // 68.2 KB
-
-// One 64x64 source tile of one frame, both images; NT threads (256 standalone, 512 inside the fused kernel).
-template <int FMT, int NT>
-__device__ __forceinline__ void frontend_tile(const Geo& g, const BatchIn& in, float* __restrict__ xyb_base, int tbx, int tby,
-                                              int frame, char* smem)
-{
-    float* fs = reinterpret_cast<float*>(smem);
-    exact_math::PowfTables& T = *reinterpret_cast<exact_math::PowfTables*>(smem + kFOffT);
-    exact_math::CbrtScale& S = *reinterpret_cast<exact_math::CbrtScale*>(smem + kFOffS);
-    {
-        const uint64_t* src = reinterpret_cast<const uint64_t*>(&kPowfTablesInit);
-        uint64_t* dst = reinterpret_cast<uint64_t*>(&T);
-        for (int i = threadIdx.x; i < (int)(sizeof(exact_math::PowfTables) / 8); i += NT) dst[i] = src[i];
-        if (threadIdx.x < 256) S.tab[threadIdx.x] = exact_math::cbrt_scale_entry(threadIdx.x);
-    }
-    __syncthreads();
-    float* xyb_slot = xyb_base + (size_t)frame * g.xyb_stride;
-    const int W0 = g.sc[0].w, H0 = g.sc[0].h;
-    const int X0 = tbx * kFTile, Y0 = tby * kFTile;
-    const int ns = g.nscales;
-    constexpr int kRowsPerIter = NT / 64;
-
-    for (int img = 0; img < 2; img++) {
-        const FrameIn& f = img ? in.dis[frame] : in.ref[frame];
-        // ---- scale 0: source -> linear RGB (shared) -> XYB (global); thread = column lx, rows ly0 + kRowsPerIter*k
-        {
-            const ScaleDesc& sd = g.sc[0];
-            const size_t plane = (size_t)sd.h * sd.pitch;
-            float* gdst = xyb_slot + sd.xyb_off + (size_t)img * 3 * plane;
-            const int lx = threadIdx.x & 63, x = X0 + lx;
-#pragma unroll kFUnroll
-            for (int k = 0; k < kFTile / kRowsPerIter; k++) {
-                const int ly = (threadIdx.x >> 6) + kRowsPerIter * k, y = Y0 + ly;
-                float r = 0.f, gg = 0.f, b = 0.f;
-                if (x < W0 && y < H0) {
-                    load_px<FMT>(f, x, y, g.coef, T, g.eotf_lut, g.lut_n, g.lut_shift, r, gg, b);
-                    float X, Y, B;
-                    linear_to_xyb(r, gg, b, S, X, Y, B);
-                    const size_t off = (size_t)y * sd.pitch + x;
-                    gdst[off] = X; gdst[plane + off] = Y; gdst[2 * plane + off] = B;
-                }
-                fs[kFOff0 + (0 * 64 + ly) * 65 + lx] = r;
-                fs[kFOff0 + (1 * 64 + ly) * 65 + lx] = gg;
-                fs[kFOff0 + (2 * 64 + ly) * 65 + lx] = b;
-            }
-        }
-        auto gplane = [&](int s) {
-            const ScaleDesc& sd = g.sc[s];
-            return xyb_slot + sd.xyb_off + (size_t)img * 3 * (size_t)sd.h * sd.pitch;
-        };
-        if (ns > 1) {
-            __syncthreads();
-            down_level<32, true, NT>(fs + kFOff0, fs + kFOff1, W0, H0, X0 / 2, Y0 / 2, g.sc[1], gplane(1), S);
-        }
-        if (ns > 2) {
-            __syncthreads();
-            down_level<16, true, NT>(fs + kFOff1, fs + kFOff2, g.sc[1].w, g.sc[1].h, X0 / 4, Y0 / 4, g.sc[2], gplane(2), S);
-        }
-        if (ns > 3) {
-            __syncthreads();
-            down_level<8, true, NT>(fs + kFOff2, fs + kFOff3, g.sc[2].w, g.sc[2].h, X0 / 8, Y0 / 8, g.sc[3], gplane(3), S);
-        }
-        if (ns > 4) {
-            __syncthreads();
-            down_level<4, true, NT>(fs + kFOff3, fs + kFOff4, g.sc[3].w, g.sc[3].h, X0 / 16, Y0 / 16, g.sc[4], gplane(4), S);
-        }
-        if (ns > 5) {
-            __syncthreads();
-            down_level<2, false, NT>(fs + kFOff4, nullptr, g.sc[4].w, g.sc[4].h, X0 / 32, Y0 / 32, g.sc[5], gplane(5), S);
-        }
-        __syncthreads();  // the tile is reused by the next image
-    }
-}
-
-template <int FMT>
-__global__ void __launch_bounds__(kFThreads, KF_MINB) k_frontend(const __grid_constant__ Geo g, const __grid_constant__ BatchIn in,
-                                                                 float* __restrict__ xyb_base)
-{
-    extern __shared__ __align__(16) char fsm[];
-    frontend_tile<FMT, kFThreads>(g, in, xyb_base, blockIdx.x, blockIdx.y, blockIdx.z, fsm);
-}
 
 // ------------------------------------------------------------------------------------------
 // k_frontend2: the same front-end (colour conversion, linear-RGB pyramid, XYB of every scale), organised so that a
@@ -663,8 +523,8 @@ __device__ __forceinline__ void frontend_region(const Geo& g, const FrameIn& f, 
 
 // grid: (ceil(regions_x / (8 * kF2RegionsPerWarp)), regions_y, frames); warp w of a CTA owns kF2RegionsPerWarp regions along x
 template <int FMT>
-__global__ void __launch_bounds__(kF2Threads, KF2_MINB) k_frontend2(const __grid_constant__ Geo g, const __grid_constant__ BatchIn in,
-                                                             float* __restrict__ xyb_base)
+__global__ void __launch_bounds__(kF2Threads, KF2_MINB) k_frontend2(const __grid_constant__ Geo g, const FramePair* __restrict__ in,
+                                                             float* __restrict__ xyb_base, int frame0)
 {
     __shared__ exact_math::PowfTables T;
     __shared__ exact_math::CbrtScale S;
@@ -676,8 +536,9 @@ __global__ void __launch_bounds__(kF2Threads, KF2_MINB) k_frontend2(const __grid
         S.tab[threadIdx.x] = exact_math::cbrt_scale_entry(threadIdx.x);
     }
     __syncthreads();
-    const int frame = blockIdx.z, warp = threadIdx.x >> 5;
+    const int frame = frame0 + blockIdx.z, warp = threadIdx.x >> 5;
     const int rx_n = (g.sc[0].w + kF2Region - 1) / kF2Region;
+    const FramePair fp = in[frame];
     float* xyb_slot = xyb_base + (size_t)frame * g.xyb_stride;
 #pragma unroll 1
     for (int i = 0; i < kF2RegionsPerWarp; i++) {
@@ -685,46 +546,8 @@ __global__ void __launch_bounds__(kF2Threads, KF2_MINB) k_frontend2(const __grid
         if (rx >= rx_n) break;
 #pragma unroll 1
         for (int img = 0; img < 2; img++)
-            frontend_region<FMT>(g, img ? in.dis[frame] : in.ref[frame], xyb_slot, img, rx * kF2Region, blockIdx.y * kF2Region, T, S,
+            frontend_region<FMT>(g, img ? fp.dis : fp.ref, xyb_slot, img, rx * kF2Region, blockIdx.y * kF2Region, T, S,
                                  scratch + threadIdx.x, kF2Threads);
-    }
-}
-
-// Persistent form of the same front-end: one 512-thread CTA per SM, every warp pulls 32x32 regions from an atomic
-// counter.  It is sized (64 registers x 512 threads, 3 KB of shared memory) to share each SM with one k_hv CTA of the
-// PREVIOUS batch: the front-end is bound by the FP64 / conversion / integer pipes and the issue rate, k_hv by the
-// FP32 pipe, so the two kernels run side by side on two streams instead of one after the other.
-constexpr int kF2PThreads = 512;
-template <int FMT>
-__global__ void __launch_bounds__(kF2PThreads, 2) k_frontend2p(const __grid_constant__ Geo g, const __grid_constant__ BatchIn in,
-                                                               float* __restrict__ xyb_base, uint32_t* __restrict__ counter, int nframes)
-{
-    __shared__ exact_math::PowfTables T;
-    __shared__ exact_math::CbrtScale S;
-    __shared__ float scratch[15 * kF2PThreads];
-    {
-        const uint64_t* src = reinterpret_cast<const uint64_t*>(&kPowfTablesInit);
-        uint64_t* dst = reinterpret_cast<uint64_t*>(&T);
-        for (int i = threadIdx.x; i < (int)(sizeof(exact_math::PowfTables) / 8); i += kF2PThreads) dst[i] = src[i];
-        if (threadIdx.x < 256) S.tab[threadIdx.x] = exact_math::cbrt_scale_entry(threadIdx.x);
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int rx_n = (g.sc[0].w + kF2Region - 1) / kF2Region, ry_n = (g.sc[0].h + kF2Region - 1) / kF2Region;
-    const uint32_t per_frame = (uint32_t)(rx_n * ry_n), total = per_frame * (uint32_t)nframes;
-    for (;;) {
-        uint32_t id = 0;
-        if (lane == 0) id = atomicAdd(counter, 1u);
-        id = __shfl_sync(0xffffffffu, id, 0);
-        if (id >= total) break;
-        const int frame = (int)(id / per_frame);
-        const int rem = (int)(id - (uint32_t)frame * per_frame);
-        const int ry = rem / rx_n, rx = rem - ry * rx_n;
-        float* xyb_slot = xyb_base + (size_t)frame * g.xyb_stride;
-#pragma unroll 1
-        for (int img = 0; img < 2; img++)
-            frontend_region<FMT>(g, img ? in.dis[frame] : in.ref[frame], xyb_slot, img, rx * kF2Region, ry * kF2Region, T, S,
-                                 scratch + threadIdx.x, kF2PThreads);
     }
 }
 
@@ -977,39 +800,6 @@ __global__ void __launch_bounds__(kHThreads, 2) k_hpass(const __grid_constant__ 
 {
     extern __shared__ __align__(1024) char hsm[];
     hpass_band(g, maps, blockIdx.x, blockIdx.y, hsm);
-}
-
-// Horizontal fusion of two INDEPENDENT pieces of work in one launch so that they share the SMs: the H pass of
-// batch p (streams 0.93 GB per pair through HBM, leaves ~60 % of the issue slots idle) and the front-end of
-// the NEXT batch k (FP64 / integer bound, almost no HBM traffic).  Roles are interleaved over blockIdx with a
-// Bresenham split, so every SM holds a mix of the two and the memory-bound CTAs hide behind the compute-bound
-// ones.  Either side may be empty (n_h_blocks == 0 or n_f_blocks == 0).
-struct FuseArgs {
-    int n_h_blocks;   // items_h * frames_h
-    int frames_h;
-    int n_f_blocks;   // tiles_x * tiles_y * frames_f
-    int tiles_x, tiles_y;
-};
-
-template <int FMT>
-__global__ void __launch_bounds__(kHThreads, 2) k_fused_fh(const __grid_constant__ Geo g, const __grid_constant__ TmaMapsH maps_h,
-                                                           const __grid_constant__ BatchIn in_f, float* __restrict__ xyb_f,
-                                                           const FuseArgs fa)
-{
-    extern __shared__ __align__(1024) char sm[];
-    const long long total = (long long)fa.n_h_blocks + fa.n_f_blocks;
-    const long long b = blockIdx.x;
-    const int ih = (int)((b * fa.n_h_blocks) / total);
-    const bool is_h = (int)(((b + 1) * fa.n_h_blocks) / total) > ih;
-    if (is_h) {
-        // item-major order: all frames' largest bands first
-        hpass_band(g, maps_h, ih / fa.frames_h, ih % fa.frames_h, sm);
-    } else {
-        const int jf = (int)(b - ih);
-        const int per_frame = fa.tiles_x * fa.tiles_y;
-        const int frame = jf / per_frame, t = jf - frame * per_frame;
-        frontend_tile<FMT, kHThreads>(g, in_f, xyb_f, t % fa.tiles_x, t / fa.tiles_x, frame, sm);
-    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1274,50 +1064,6 @@ __device__ __forceinline__ void edge_maps2(f2 mu1, f2 mu2, f2 ref, f2 dis, f2 (&
     part[3] = f2_fma(det2, det2, part[3]);
 }
 
-// error_maps2 with the tails on the FP64 pipe (-DKX_F64_TAILS; measured SLOWER in k_hv: 2.60 ms against 2.19 ms per 8 4K pairs,
-// the extra issue slots and the longer dependency chains cost more than the FP32-pipe cycles they free -- kept as an experiment).
-// The SSIM quotient q is formed exactly as in error_maps2 (f32, cpu.rs:604-626); from there on everything is f64 like
-// the reference (cpu.rs:627-631, 658-674): d = max(1 - q, 0); d1 = (1 + |dis - mu2|) / (1 + |ref - mu1|) - 1, evaluated
-// as (a - b) / (1 + b) with a Newton-refined reciprocal (relative error ~2^-45); sums of x and x^4 straight into the
-// f64 accumulators of both columns.
-__device__ __forceinline__ void dp_tail(float q, float a, float b, double (&acc)[6])
-{
-    const double d = fmax(1.0 - (double)q, 0.0);
-    acc[0] += d;
-    const double dd = d * d;
-    acc[1] = fma(dd, dd, acc[1]);
-    const double ad = (double)a, bd = (double)b;
-    const double den = 1.0 + bd;
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
-    y = fma(y, fma(-den, y, 1.0), y);
-    const double d1 = (ad - bd) * y;
-    const double art = fmax(d1, 0.0), det = fmax(-d1, 0.0);
-    const double a2 = art * art, t2 = det * det;
-    acc[2] += art;
-    acc[3] = fma(a2, a2, acc[3]);
-    acc[4] += det;
-    acc[5] = fma(t2, t2, acc[5]);
-}
-__device__ __forceinline__ void error_maps_dp(const f2 (&o)[5], f2 ref, f2 dis, double (&acc)[6])
-{
-    const f2 C2 = f2_splat(0.0009f), one = f2_splat(1.0f);
-    const f2 s11 = o[0], s22 = o[1], s12 = o[2], mu1 = o[3], mu2 = o[4];
-    const f2 mu11 = f2_mul(mu1, mu1), mu22 = f2_mul(mu2, mu2), mu12 = f2_mul(mu1, mu2);
-    const f2 mu_diff = f2_sub(mu1, mu2);
-    const f2 num_m = f2_fma(mu_diff, f2_neg(mu_diff), one);
-    const f2 num_s = f2_fma(f2_splat(2.0f), f2_sub_prod(s12, mu12), C2);
-    const f2 denom_s = f2_add(f2_add(f2_sub_prod(s11, mu11), f2_sub_prod(s22, mu22)), C2);
-    const f2 q = div_rn_normal2(f2_mul(num_m, num_s), denom_s);
-    const f2 a = f2_abs(f2_sub(dis, mu2)), b = f2_abs(f2_sub(ref, mu1));
-    float q0, q1, a0, a1, b0, b1;
-    f2_unpack(q, q0, q1);
-    f2_unpack(a, a0, a1);
-    f2_unpack(b, b0, b1);
-    dp_tail(q0, a0, b0, acc);
-    dp_tail(q1, a1, b1, acc);
-}
-
 // k_vpass, TMA-fed.  CTA = one 64-column strip of one scale of one frame; 3 consumer warps (warp = channel, lane =
 // a PAIR of adjacent columns, all arithmetic packed f32x2) + 1 producer warp.  The producer streams
 // {hb rows t, t+1 ; xyb rows t-4, t-3} boxes into a 5-stage shared-memory ring with cp.async.bulk.tensor (out-of-range
@@ -1458,9 +1204,6 @@ __global__ void __launch_bounds__(kVTmaThreads, 2) k_vpass(const __grid_constant
 // handed out by an atomic ticket in dependency order (strip-major), so a CTA only ever waits for CTAs that are
 // already running: no deadlock regardless of how many CTAs are resident.
 // ------------------------------------------------------------------------------------------
-#ifndef KX_HSETS
-#define KX_HSETS 2     // H warps per channel taking alternate bands (1: 12-warp CTA, measured 9 % slower)
-#endif
 constexpr int kXR = 12;                                  // rows per band
 constexpr int kXC = kVCols;                              // columns per strip (the strip list is the V pass's)
 constexpr int kXInLead = 8;                              // tile starts at column x0 - 8
@@ -1473,7 +1216,7 @@ constexpr int kXHbPlane = kXR * kXHbPitch + 8;           // 824 floats
 constexpr int kXHbFloats = 15 * kXHbPlane;
 constexpr uint32_t kXHbBytes = kXHbFloats * 4;           // 49440
 constexpr int kXHThreads = 96;
-constexpr int kXWarps = KX_HSETS == 1 ? 12 : 16;         // roles by warp id, see k_hv
+constexpr int kXWarps = 16;                              // roles by warp id, see k_hv
 constexpr int kXNIn = 3;                                 // depth of the XYB tile ring
 constexpr int kXThreads = kXWarps * 32;
 constexpr int kXHsF2 = 6 * kXHThreads;                   // hand-off record: [6 state words][96 H threads] f2
@@ -1495,31 +1238,9 @@ static_assert(kXSmemBytes <= 232448, "k_hv shared memory");
 static_assert(kXR % kXSub == 0, "k_hv sub-bands");
 
 // mbarrier wait with a watchdog: a protocol bug must end in a trap, not in a hung GPU
-#ifndef KX_SPIN
-#define KX_SPIN 0
-#endif
-#ifndef KX_WAIT_NS
-#define KX_WAIT_NS 0   // extra back-off between failed mbarrier try_waits (the hardware suspend hint returns early)
-#endif
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity)
 {
     const uint32_t a = smem_u32(bar);
-#if KX_SPIN
-    for (uint32_t it = 0;; it++) {
-        uint32_t ok;
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(a), "r"(parity)
-            : "memory");
-        if (ok) return;
-        if (it > 400000000u) __trap();
-    }
-#else
     for (uint32_t it = 0;; it++) {
         uint32_t ok;
         asm volatile(
@@ -1532,10 +1253,8 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity)
             : "r"(a), "r"(parity), "r"(20000u)
             : "memory");
         if (ok) return;
-        if (KX_WAIT_NS > 0) __nanosleep(KX_WAIT_NS);
         if (it > 400000u) __trap();
     }
-#endif
 }
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p)
 {
@@ -1620,32 +1339,8 @@ __device__ __forceinline__ void h_products(const HGroupLoad& L, f2 (&w)[16], int
     w[(at + 3) & 15] = f2_pack(L.xa.w * L.ya.w, L.xb.w * L.yb.w);
 }
 
-#ifndef KX_MAXNREG
-#define KX_MAXNREG 128   // 16 warps x 128 registers = the whole register file
-#endif
-// timing experiments only (results are wrong unless all are at their defaults)
-#ifndef KX_PF
-#define KX_PF 0   // bands of L2 prefetch ahead of the shared-memory ring (0 = off; 6 and 12 measured no faster)
-#endif
-#ifndef KX_EXP_NOSTATE
-#define KX_EXP_NOSTATE 0
-#endif
-#ifndef KX_EXP_NOTMA
-#define KX_EXP_NOTMA 0
-#endif
-#ifndef KX_HUNROLL
-#define KX_HUNROLL 2   // unroll of the 16-column body of the H scan: 2 halves the loop-carried register moves (-1.3 %); 4 overflows the instruction cache (+1.7 %)
-#endif
-constexpr int kXHUnroll = KX_HUNROLL;
-#ifndef KX_EXP_HITERS
-#define KX_EXP_HITERS 4
-#endif
-#ifndef KX_EXP_VROWS
-#define KX_EXP_VROWS kXSub
-#endif
-#ifndef KX_EXP_NODEP
-#define KX_EXP_NODEP 0
-#endif
+constexpr int kXMaxNReg = 128;   // 16 warps x 128 registers = the whole register file
+constexpr int kXHUnroll = 2;     // unroll of the 16-column body of the H scan: 2 halves the loop-carried register moves (-1.3 %); 4 overflows the instruction cache (+1.7 %)
 // Warp roles (16 warps).  The scheduler sub-partition of a warp is (warp id % 4).  Per 12-row band an H warp needs
 // ~1660 FP32-pipe cycles, a Va warp ~1150, a Vb warp ~750.  Every channel has TWO H warps that take alternate bands,
 // so the waits / state fetch / first loads of band j+1 overlap the scan of band j:
@@ -1657,13 +1352,6 @@ __device__ __forceinline__ int hv_role(int warp, int& ch, int& par)
     // 0 = H, 1 = Va, 2 = Vb, 3 = P_tma, 4 = P_out, 5 = idle, 6 = P_state
     const int sp = warp & 3, row = warp >> 2;
     ch = sp; par = row;
-#if KX_HSETS == 1
-    //   SP0: H0 Va0 P_out    SP1: H1 Va1 P_state    SP2: H2 Va2 P_tma    SP3: Vb0 Vb1 Vb2
-    par = 0;
-    if (sp < 3) return row == 0 ? 0 : (row == 1 ? 1 : (sp == 0 ? 4 : (sp == 1 ? 6 : 3)));
-    ch = row;
-    return 2;
-#else
     if (sp < 3) {
         if (row < 2) return 0;
         if (row == 2) return 1;
@@ -1671,10 +1359,9 @@ __device__ __forceinline__ int hv_role(int warp, int& ch, int& par)
     }
     ch = row;
     return row < 3 ? 2 : 3;
-#endif
 }
 
-__global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, const __grid_constant__ TmaMapsX maps,
+__global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const __grid_constant__ TmaMapsX maps,
                                                      const HvArgs a)
 {
     extern __shared__ __align__(1024) char xs[];
@@ -1741,21 +1428,17 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
         // ===== P_tma: tile loads =====
         if (lane != 0) return;
         const CUtensorMap* map = &maps.xyb_in[s];
-        if (KX_PF > kXNIn)
-            for (int j = kXNIn; j < KX_PF && j < nb; j++) tma_prefetch_4d(map, x0 - kXInLead, j * kXR, 0, frame);
         for (int j = 0; j < nb; j++) {
             const int si = j % kXNIn;
             if (j >= kXNIn) mbar_wait_wd(&in_free[si], (uint32_t)((j / kXNIn - 1) & 1));
-            if (KX_EXP_NOTMA) { mbar_arrive(&in_full[si]); continue; }
             mbar_expect_tx(&in_full[si], kXInBytes);
             tma_load_4d(xs + kXOffIn + si * kXInBytes, map, &in_full[si], x0 - kXInLead, j * kXR, 0, frame);
-            if (KX_PF > 0 && j + KX_PF < nb) tma_prefetch_4d(map, x0 - kXInLead, (j + KX_PF) * kXR, 0, frame);
         }
         return;
     }
     if (role == 6) {
         // ===== P_state: watches the flags of the strip to the left; the H warps then read the record from L2 =====
-        if (k == 0 || KX_EXP_NODEP || lane != 0) return;
+        if (k == 0 || lane != 0) return;
         for (int j = 0; j < nb; j++) {
             if (j >= 2) mbar_wait_wd(&hs_free[j & 1], (uint32_t)(((j >> 1) - 1) & 1));
             const uint32_t* fl = a.flags + rec_base + (size_t)(k - 1) * nb + j;
@@ -1806,11 +1489,11 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             // every H warp walks ALL the phases of the ring barriers in order (a parity wait must never skip a phase),
             // but only scans the bands of its own parity
             const int si = j % 3, sin = j % kXNIn;
-            const bool mine = (KX_HSETS == 1) || ((j & 1) == hpar);
+            const bool mine = (j & 1) == hpar;
             mbar_wait_wd(&in_full[sin], (uint32_t)((j / kXNIn) & 1));
             HState2 st;
             if (mine) {
-                if (k > 0 && !KX_EXP_NODEP) {
+                if (k > 0) {
                     mbar_wait_wd(&hs_ready[j & 1], (uint32_t)((j >> 1) & 1));
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&hs_free[j & 1]);   // P_state may go on to band j + 2
@@ -1849,7 +1532,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             if (j >= 2) mbar_wait_wd(&hb_free[si], (uint32_t)(((j - 2) / 3) & 1));
             uint32_t axI = axA, ayI = ayA, ayIB = ayB;
 #pragma unroll kXHUnroll
-            for (int it = 0; it < KX_EXP_HITERS; it++, axI += 64, ayI += 64, ayIB += 64) {
+            for (int it = 0; it < 4; it++, axI += 64, ayI += 64, ayIB += 64) {
 #pragma unroll
                 for (int gg = 0; gg < 4; gg++) {
                     const HGroupLoad cur = nxt;
@@ -1874,7 +1557,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
                 float* t0 = reinterpret_cast<float*>(xs + kXOffHb + si * kXHbBytes) + (hv_slot(q) * 3 + ch) * kXHbPlane + rp * kXHbPitch;
                 for (int cc = W - x0; cc < kXC; cc++) { t0[cc] = 0.0f; t0[6 * kXHbPitch + cc] = 0.0f; }
             }
-            if (!last_strip && !KX_EXP_NOSTATE) {
+            if (!last_strip) {
                 // the state at the right edge of the band goes straight to the record of (strip, band): 256 B per store
                 unsigned long long* rec = reinterpret_cast<unsigned long long*>(a.hstate + (rec_base + (size_t)k * nb + j) * kXHsF2) + hidx;
                 __stcg(rec, st.p1.v); __stcg(rec + 96, st.p3.v); __stcg(rec + 2 * 96, st.p5.v);
@@ -1928,7 +1611,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
                 // common path has no branch per row, so the four rows' map chains interleave
                 auto rows = [&](auto checked) {
 #pragma unroll
-                    for (int r = 0; r < KX_EXP_VROWS; r++) {
+                    for (int r = 0; r < kXSub; r++) {
                         const int i = i4 + r, t = j * kXR + i;
                         const uint32_t a_t = cur_i4 + (uint32_t)(r * kXHbPitch * 4);
                         const uint32_t a_d = (r < 2 ? d_lo : d_hi) + (uint32_t)(r * kXHbPitch * 4);
@@ -1987,7 +1670,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             const uint32_t d_lo = prv + (uint32_t)((i4 + 2) * kXHbPitch * 4);
             const uint32_t d_hi = i4 == 8 ? cur - (uint32_t)(2 * kXHbPitch * 4) : d_lo;
 #pragma unroll
-            for (int r = 0; r < KX_EXP_VROWS; r++) {
+            for (int r = 0; r < kXSub; r++) {
                 const uint32_t a_t = cur_i4 + (uint32_t)(r * kXHbPitch * 4);
                 const uint32_t a_d = (r < 2 ? d_lo : d_hi) + (uint32_t)(r * kXHbPitch * 4);
 #pragma unroll
@@ -2004,7 +1687,7 @@ __global__ void __maxnreg__(KX_MAXNREG) k_hv(const __grid_constant__ Geo g, cons
             const uint32_t mus = mub + (uint32_t)p * kXMuSlotBytes;
             auto maps = [&](auto checked) {
 #pragma unroll
-                for (int r = 0; r < KX_EXP_VROWS; r++) {
+                for (int r = 0; r < kXSub; r++) {
                     const int t = j * kXR + i4 + r;
                     const f2 m1 = lds64(mus + (uint32_t)(r * 2 * kXC * 4)), m2 = lds64(mus + (uint32_t)((r * 2 + 1) * kXC * 4));
                     if (!decltype(checked)::value || (t >= 4 && t < H + 4)) ssim_map2(o[r][0], o[r][1], o[r][2], m1, m2, part);
@@ -2058,7 +1741,7 @@ __global__ void __launch_bounds__(128) k_finalize(const __grid_constant__ Geo g,
                                                   unsigned long long first_ticket, unsigned long long ring_cap,
                                                   double* __restrict__ scores_out, uint32_t* __restrict__ hv_ticket)
 {
-    if (hv_ticket != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { hv_ticket[0] = 0u; hv_ticket[1] = 0u; }  // work counters of k_hv / k_frontend2p, for the next batch
+    if (hv_ticket != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { hv_ticket[0] = 0u; hv_ticket[1] = 0u; }  // work counter of k_hv, for the next batch
     __shared__ double norms[108];
     const int frame = blockIdx.x, tid = threadIdx.x;
     if (tid < 108) norms[tid] = 0.0;

@@ -19,11 +19,23 @@ from .ssimulacra2 import ColorMatrix, DeviceFrame, PixelFormat, Ssimulacra2
 
 @dataclass
 class FrameScores:
-    """turbo-metrics/src/lib.rs:114-123 (only the metric of this path is ever populated)."""
-    psnr: Optional[float] = None
-    ssim: Optional[float] = None
-    msssim: Optional[float] = None
+    """turbo-metrics/src/lib.rs:114-123 restricted to the metric of this path (serde skips the `None` metrics, so a
+    reference run with only --ssimulacra2 serialises exactly this)."""
     ssimulacra2: Optional[float] = None
+
+
+@dataclass
+class MetricAggregate:
+    """turbo-metrics/src/lib.rs:56-70."""
+    scores: List[float]
+    stats: "Stats"
+
+
+@dataclass
+class MetricsResults:
+    """turbo-metrics/src/lib.rs:72-84 restricted to ssimulacra2."""
+    frame_count: int
+    ssimulacra2: Optional[MetricAggregate]
 
 
 @dataclass
@@ -99,14 +111,37 @@ class TurboMetrics:
         """lib.rs:268-360."""
         return FrameScores(ssimulacra2=self.ssimulacra2.compute_sync(fref, fdis, stream))
 
-    def compute_all(self, pairs: Iterable[Tuple[DeviceFrame, DeviceFrame]], stream=None) -> List[float]:
-        """lib.rs:362-433 with submit-ahead: at most batch x ring pairs in flight; scores in submission order."""
+    def compute_all(self, frames_ref: Iterable[DeviceFrame], frames_dis: Iterable[DeviceFrame], opts: Optional[Options] = None,
+                    stream=None) -> MetricsResults:
+        """The frame loop of lib.rs:362-433 with the same `Options` semantics (lib.rs:385-400): skip `skip + skip_ref` /
+        `skip + skip_dis` frames of the two sources, then walk them in lockstep; with `decode_count` counting the pairs seen,
+        score a pair unless `every > 1 and decode_count != 0 and decode_count % every != 0`, stop at the first candidate
+        with `decode_count >= frames` (frames > 0), or when either source ends.  Re-done for throughput: up to
+        batch x ring pairs are in flight, scores are collected in submission order.
+
+        LIFETIME: a yielded frame is read when its batch is launched, not when it is submitted -- every frame must own
+        its memory until its score has been collected (this loop keeps the DeviceFrame objects alive for that long);
+        a source that recycles a small buffer pool has to order the reuse with `Ssimulacra2.wait_input(ticket, stream)`."""
+        opts = opts or Options()
+        it_ref, it_dis = iter(frames_ref), iter(frames_dis)
+        for _ in range(opts.skip_ref + opts.skip):       # FrameSource::skip_frames
+            next(it_ref, None)
+        for _ in range(opts.skip_dis + opts.skip):
+            next(it_dis, None)
         scores: List[float] = []
         pending: List[int] = []
-        for fref, fdis in pairs:
+        decode_count = 0
+        for fref, fdis in zip(it_ref, it_dis):
+            if opts.every > 1 and decode_count != 0 and decode_count % opts.every != 0:
+                decode_count += 1
+                continue
+            if opts.frames > 0 and decode_count >= opts.frames:
+                break
+            decode_count += 1
             pending.append(self.ssimulacra2.compute(fref, fdis, stream))
             if len(pending) >= self.window:
                 scores.append(self.ssimulacra2.get_score(pending.pop(0)))
         self.ssimulacra2.flush()
         scores.extend(self.ssimulacra2.get_score(t) for t in pending)
-        return scores
+        from .stats import Stats
+        return MetricsResults(len(scores), MetricAggregate(scores, Stats.compute(scores)) if scores else None)

@@ -77,32 +77,36 @@ class DeviceFrame:
         return DeviceFrame(base, 0, pitch, img, nbytes)
 
 
+def make_config(width, height, fmt, matrix=ColorMatrix.BT709, full_range=False, device=0, batch=0, ring=0,
+                pipeline=_lib.PIPELINE_DEFAULT, flags=0, input_group=0) -> Config:
+    cfg = Config()
+    cfg.width, cfg.height, cfg.format, cfg.matrix = width, height, int(fmt), int(matrix)
+    cfg.full_range, cfg.device, cfg.batch, cfg.ring = int(full_range), device, batch, ring
+    cfg.pipeline, cfg.flags, cfg.input_group = pipeline, flags, input_group
+    return cfg
+
+
 class Ssimulacra2:
     """`Ssimulacra2::new` (lib.rs:48-107): an instance is valid for one width x height x format."""
 
     def __init__(self, width: int, height: int, fmt: PixelFormat = PixelFormat.LINEARF32,
                  matrix: ColorMatrix = ColorMatrix.BT709, full_range: bool = False, device: int = 0,
-                 batch: int = 0, ring: int = 0, pipeline: Optional[str] = None):
-        """pipeline (development / tests): None = the library default ("hv": front-end, fused H+V kernel,
-        finalize); "split" = four kernels with the H-pass planes in HBM (debug_read(what=1));
-        "fh" = front-end fused with the previous batch's H pass + separate V pass.  Passed to the library
-        through the SSIMU2_PIPELINE environment variable it reads in ssimu2_create."""
+                 batch: int = 0, ring: int = 0, pipeline: Optional[str] = None, score_only: bool = False,
+                 input_group: int = 0, timing: bool = True):
+        """pipeline: None / "hv" = the product pipeline (front-end, fused H+V kernel, finalize); "split" = development
+        pipeline with the H-pass planes in HBM (debug_read(what=1)).
+        score_only: SSIMU2_FLAG_SCORE_ONLY -- skip the work whose weights are zero (scores identical, no norms).
+        input_group: pairs per front-end launch (0 = whole batch): input frames are consumed sooner, see wait_input()."""
         self._h = C.c_void_p()
-        cfg = Config(width, height, int(fmt), int(matrix), int(full_range), device, batch, ring)
-        import os
-        old = os.environ.get("SSIMU2_PIPELINE")
-        if pipeline is not None:
-            os.environ["SSIMU2_PIPELINE"] = pipeline
-        try:
-            check(_lib.lib().ssimu2_create(C.byref(self._h), C.byref(cfg)), "ssimu2_create")
-        finally:
-            if pipeline is not None:
-                if old is None:
-                    os.environ.pop("SSIMU2_PIPELINE", None)
-                else:
-                    os.environ["SSIMU2_PIPELINE"] = old
+        if pipeline not in (None, "hv", "split"):
+            raise ValueError(f"unknown pipeline {pipeline!r}")
+        flags = (_lib.FLAG_SCORE_ONLY if score_only else 0) | (0 if timing else _lib.FLAG_NO_TIMING)
+        cfg = make_config(width, height, fmt, matrix, full_range, device, batch, ring,
+                          _lib.PIPELINE_SPLIT if pipeline == "split" else _lib.PIPELINE_DEFAULT, flags, input_group)
+        check(_lib.lib().ssimu2_create(C.byref(self._h), C.byref(cfg)), "ssimu2_create")
         self.width, self.height, self.format = width, height, PixelFormat(fmt)
         self._keep = {}
+        self._last = None
 
     # -- lifetime -------------------------------------------------------------------------
     def close(self):
@@ -150,6 +154,7 @@ class Ssimulacra2:
         check(_lib.lib().ssimu2_submit(self._h, C.byref(a), C.byref(b), C.c_void_p(self._stream_handle(stream)),
                                        C.byref(t)), "ssimu2_submit")
         self._keep[t.value] = (ref, dis)
+        self._last = t.value
         return t.value
 
     def compute_batch(self, refs: Sequence[DeviceFrame], diss: Sequence[DeviceFrame], stream=None) -> range:
@@ -162,6 +167,8 @@ class Ssimulacra2:
               "ssimu2_submit_batch")
         for i in range(n):
             self._keep[t.value + i] = (refs[i], diss[i])
+        if n:
+            self._last = t.value + n - 1
         return range(t.value, t.value + n)
 
     def compute_from_cpu(self, ref: DeviceFrame, dis: DeviceFrame) -> int:
@@ -173,6 +180,7 @@ class Ssimulacra2:
         check(_lib.lib().ssimu2_submit_host(self._h, C.byref(a), C.byref(b), ref.nbytes, C.byref(t)),
               "ssimu2_submit_host")
         self._keep[t.value] = (ref, dis)
+        self._last = t.value
         return t.value
 
     def compute_from_cpu_batch(self, refs: Sequence[DeviceFrame], diss: Sequence[DeviceFrame]) -> range:
@@ -185,6 +193,7 @@ class Ssimulacra2:
         check(_lib.lib().ssimu2_submit_host_batch(self._h, n, A, B, refs[0].nbytes, C.byref(t)), "ssimu2_submit_host_batch")
         for i in range(n):
             self._keep[t.value + i] = (refs[i], diss[i])
+        self._last = t.value + n - 1
         return range(t.value, t.value + n)
 
     def flush(self):
@@ -193,10 +202,12 @@ class Ssimulacra2:
     def get_score(self, ticket: Optional[int] = None) -> float:
         """`Ssimulacra2::get_score` (lib.rs:289-291); defaults to the last submitted pair."""
         if ticket is None:
-            ticket = max(self._keep) if self._keep else 0
+            if self._last is None:
+                raise ValueError("get_score() before any compute()")
+            ticket = self._last
         s = C.c_double()
         check(_lib.lib().ssimu2_get_score(self._h, ticket, C.byref(s)), "ssimu2_get_score")
-        self._release(ticket)
+        self._release()
         return s.value
 
     def get_scores(self, tickets: range) -> np.ndarray:
@@ -206,7 +217,7 @@ class Ssimulacra2:
         if n:
             assert tickets.step == 1
             check(_lib.lib().ssimu2_get_scores(self._h, tickets.start, n, out.ctypes.data_as(C.POINTER(C.c_double))), "ssimu2_get_scores")
-            self._release(tickets[-1])
+            self._release()
         return out
 
     def get_norms(self, ticket: int) -> np.ndarray:
@@ -222,9 +233,27 @@ class Ssimulacra2:
     def compute_from_cpu_sync(self, ref: DeviceFrame, dis: DeviceFrame) -> float:
         return self.get_score(self.compute_from_cpu(ref, dis))
 
-    def _release(self, upto: int):
-        for k in [k for k in self._keep if k <= upto]:
+    def completed(self) -> int:
+        """`ssimu2_completed`: every ticket below the returned watermark is done and its frames are no longer read."""
+        w = C.c_uint64()
+        check(_lib.lib().ssimu2_completed(self._h, C.byref(w)), "ssimu2_completed")
+        return w.value
+
+    def _release(self):
+        # batches complete out of order across ring slots: only the in-order watermark says which inputs are free
+        w = self.completed()
+        for k in [k for k in self._keep if k < w]:
             del self._keep[k]
+
+    def stream_wait(self, ticket: int, stream=None):
+        """`ssimu2_stream_wait`: make `stream` wait (on the device) for the ticket's batch."""
+        check(_lib.lib().ssimu2_stream_wait(self._h, ticket, C.c_void_p(self._stream_handle(stream))), "ssimu2_stream_wait")
+
+    def wait_input(self, ticket: int, stream=None):
+        """`ssimu2_stream_wait_input`: make `stream` wait until the ticket's input frames have been consumed -- what a
+        decoder needs before it reuses a surface (cudarse-video/src/dec.rs:277-287)."""
+        check(_lib.lib().ssimu2_stream_wait_input(self._h, ticket, C.c_void_p(self._stream_handle(stream))),
+              "ssimu2_stream_wait_input")
 
     # -- device-side results / introspection ---------------------------------------------------
     def scores_device(self):
@@ -252,3 +281,82 @@ class Ssimulacra2:
         ms = (C.c_float * 4)()
         check(_lib.lib().ssimu2_last_batch_ms(self._h, ms), "ssimu2_last_batch_ms")
         return list(ms)
+
+
+class ShardedSsimulacra2:
+    """`ssimu2_shard_*`: one scorer per GPU of the box, each driven by its own host thread inside the library; the caller
+    sees one ordered score stream (global tickets).  No torch.distributed, no NCCL: pairs are independent
+    (ssimulacra2-cuda/README.md:26-27), the reference's single-GPU frame loop is turbo-metrics/src/lib.rs:362-433."""
+
+    def __init__(self, width: int, height: int, fmt: PixelFormat, devices: Sequence[int], matrix: ColorMatrix = ColorMatrix.BT709,
+                 full_range: bool = False, batch: int = 0, ring: int = 0, score_only: bool = False):
+        self._s = C.c_void_p()
+        flags = _lib.FLAG_SCORE_ONLY if score_only else 0
+        cfg = make_config(width, height, fmt, matrix, full_range, 0, batch, ring, _lib.PIPELINE_DEFAULT, flags, 0)
+        devs = (C.c_int32 * len(devices))(*devices)
+        check(_lib.lib().ssimu2_shard_create(C.byref(self._s), C.byref(cfg), devs, len(devices)), "ssimu2_shard_create")
+        self.devices = list(devices)
+        self._keep = []
+        self._done_upto = 0
+
+    def close(self):
+        if getattr(self, "_s", None) is not None and self._s:
+            _lib.lib().ssimu2_shard_destroy(self._s)
+            self._s = None
+            self._keep = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device_of(self, ticket: int) -> int:
+        d = C.c_int32()
+        check(_lib.lib().ssimu2_shard_device_of(self._s, ticket, C.byref(d)), "ssimu2_shard_device_of")
+        return d.value
+
+    def submit_host(self, refs: Sequence[DeviceFrame], diss: Sequence[DeviceFrame]) -> range:
+        n = len(refs)
+        assert n == len(diss) and n > 0
+        A = (Frame * n)(*[f.c() for f in refs])
+        B = (Frame * n)(*[f.c() for f in diss])
+        t = C.c_uint64()
+        check(_lib.lib().ssimu2_shard_submit_host(self._s, n, A, B, refs[0].nbytes, C.byref(t)), "ssimu2_shard_submit_host")
+        self._keep.append((t.value + n, refs, diss))
+        return range(t.value, t.value + n)
+
+    def submit_device(self, refs: Sequence[DeviceFrame], diss: Sequence[DeviceFrame], streams: Optional[Sequence[int]] = None) -> range:
+        """Frames must live on the device `device_of(ticket)` names for their ticket."""
+        n = len(refs)
+        assert n == len(diss) and n > 0
+        A = (Frame * n)(*[f.c() for f in refs])
+        B = (Frame * n)(*[f.c() for f in diss])
+        S = None
+        if streams is not None:
+            S = (C.c_void_p * len(self.devices))(*[C.c_void_p(x) for x in streams])
+        t = C.c_uint64()
+        check(_lib.lib().ssimu2_shard_submit_device(self._s, n, A, B, S, C.byref(t)), "ssimu2_shard_submit_device")
+        self._keep.append((t.value + n, refs, diss))
+        return range(t.value, t.value + n)
+
+    def flush(self):
+        check(_lib.lib().ssimu2_shard_flush(self._s), "ssimu2_shard_flush")
+
+    def get_scores(self, tickets: range) -> np.ndarray:
+        n = len(tickets)
+        out = np.zeros(n, np.float64)
+        if n:
+            check(_lib.lib().ssimu2_shard_get_scores(self._s, tickets.start, n, out.ctypes.data_as(C.POINTER(C.c_double))),
+                  "ssimu2_shard_get_scores")
+            # a submission's frames are free once every ticket up to its end has been fetched (contiguous watermark)
+            if tickets.start <= self._done_upto:
+                self._done_upto = max(self._done_upto, tickets.stop)
+            self._keep = [k for k in self._keep if k[0] > self._done_upto]
+        return out

@@ -107,6 +107,30 @@ EM_HD double u2d(uint64_t u)
 #endif
 }
 
+// ---- f32 -> f64 widening on the integer pipe ------------------------------------------------------------
+// Measured on B200 (tools/ubench/xu.cu): F2F.F64.F32 and I2F.F64 issue at 7.5 lanes/clk/SM -- a QUARTER of the
+// MUFU rate and 1/8 of DFMA -- and the two routines below need four of them per cube root / power: the conversion unit,
+// not the FP64 pipe, bounded the colour front-end.  For a positive NORMAL float the widening is three integer
+// instructions (exponent re-bias + mantissa shift), exact by construction, on a pipe that is otherwise idle here.
+EM_HD double widen_pos_normal(uint32_t ix)
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double((int)((ix >> 3) + 0x38000000u), (int)(ix << 29));
+#else
+    return (double)u2f(ix);
+#endif
+}
+// (double)k for a small integer k: 2^52 + 2^31 + k is exactly representable with k in the low word; subtracting the
+// constant is exact.  One LOP3 + one DADD instead of I2F.F64.
+EM_HD double small_int_to_double(int k)
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(0x43300000, (int)((uint32_t)k ^ 0x80000000u)) - 4503601774854144.0;   // 2^52 + 2^31
+#else
+    return (double)k;
+#endif
+}
+
 // ---- exactly rounded divisions without the library's special-case paths ----------------------------
 // Operands must be normal and the quotient far from over/underflow (true for every use below).
 // Device: reciprocal seed (MUFU) + Newton + Markstein's residual correction; host: the IEEE operator.
@@ -202,7 +226,8 @@ EM_HD float cbrtf_glibc(float x, const Consts& K, const CbrtScale* S = nullptr)
     // frexpf: |x| = xm * 2^e, xm in [0.5, 1); the double of xm is built directly from the mantissa bits
     // (on the device: one LOP3 + one exact F2F instead of assembling the double from the mantissa bits)
 #if defined(__CUDA_ARCH__)
-    const double xm = (double)u2f((ix & 0x007fffffu) | 0x3f000000u);
+    // hi = 0x3fe00000 | (m >> 3), lo = m << 29: the double of xm straight from the mantissa bits (no F2F, see widen_pos_normal)
+    const double xm = __hiloint2double((int)(((ix >> 3) & 0x000fffffu) | 0x3fe00000u), (int)(ix << 29));
 #else
     const uint32_t m = ix & 0x007fffffu;
     const double xm = u2d(((uint64_t)(0x3fe00000u | (m >> 3)) << 32) | (uint64_t)(m << 29));
@@ -214,7 +239,8 @@ EM_HD float cbrtf_glibc(float x, const Consts& K, const CbrtScale* S = nullptr)
     t = t + K.cb0;
     const float u = (float)t;
     const float t2 = (u * u) * u;
-    const double t2d = (double)t2, ud = (double)u;
+    // u is in (0.5, 1], t2 = u^3 in (0.1, 1]: positive normal floats
+    const double t2d = widen_pos_normal(f2u(t2)), ud = widen_pos_normal(f2u(u));
     // ym = u * (t2 + 2.0 * xm) / (2.0 * t2 + xm) * factor[2 + e % 3], then ldexpf(ym, e / 3): the power of
     // two commutes with the rounding to float, so both scalings are one multiplication by an exact double
     // (xm + xm) + t2 and (t2 + t2) + xm: the doublings are exact, so each sum is one fused operation
@@ -249,9 +275,9 @@ EM_HD float powf_glibc(float x, float y, const Consts& K, const PowfTables& T)
     const int k = (int32_t)top >> 23;
     const Log2Entry le = T.log2_tab[i];
     const double invc = le.invc, logc = le.logc;
-    const double z = (double)u2f(iz);
+    const double z = widen_pos_normal(iz);   // z in [0.7, 1.4)
     const double r = fma(z, invc, K.minus_one);
-    const double y0 = logc + (double)k;
+    const double y0 = logc + small_int_to_double(k);
     const double r2 = r * r;
     double yy = fma(K.A0, r, K.A1);
     const double p = fma(K.A2, r, K.A3);
@@ -276,5 +302,126 @@ EM_HD float powf_glibc(float x, float y, const Consts& K, const PowfTables& T)
     w = w * s;
     return (float)w;
 }
+
+#if defined(__CUDACC__)
+// ---- N evaluations in lock-step (device hot path) -----------------------------------------------------------
+// Measured on B200 (tools/ubench/fp64.cu): DFMA / DMUL / DADD have a dependent-issue latency of 23 cycles, a warp keeps
+// about seven of them in flight, and the pipe issues one per 2 cycles per scheduler -- so the pipe only fills when every
+// warp carries six or more INDEPENDENT chains.  Written one evaluation at a time, the compiler interleaves two chains and
+// the front-end ran at a third of the FP64 rate.  These forms advance N evaluations step by step; the arithmetic of each
+// lane is cbrtf_glibc<false> / powf_glibc<false>, operation for operation.
+template <int N>
+__device__ __forceinline__ void cbrtf_glibc_n(float (&x)[N], const Consts& K, const CbrtScale* S)
+{
+    uint32_t ix[N];
+    double xm[N], t[N], t2d[N], ud[N], num[N], den[N], y[N], e[N], q[N], f[N];
+    float u[N], t2[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        ix[i] = f2u(x[i]);
+        xm[i] = __hiloint2double((int)(((ix[i] >> 3) & 0x000fffffu) | 0x3fe00000u), (int)(ix[i] << 29));
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = K.cb2 * xm[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = K.cb1 - t[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = t[i] * xm[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = t[i] + K.cb0;
+#pragma unroll
+    for (int i = 0; i < N; i++) u[i] = (float)t[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) t2[i] = (u[i] * u[i]) * u[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        t2d[i] = widen_pos_normal(f2u(t2[i]));
+        ud[i] = widen_pos_normal(f2u(u[i]));
+        f[i] = S->tab[ix[i] >> 23];
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) den[i] = fma(2.0, t2d[i], xm[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) num[i] = fma(2.0, xm[i], t2d[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(den[i]));
+#pragma unroll
+    for (int i = 0; i < N; i++) num[i] = num[i] * ud[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) e[i] = fma(-den[i], y[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; i++) y[i] = fma(y[i], e[i], y[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) q[i] = num[i] * y[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) e[i] = fma(-den[i], q[i], num[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) q[i] = fma(e[i], y[i], q[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = (float)(q[i] * f[i]);
+}
+
+template <int N>
+__device__ __forceinline__ void powf_glibc_n(float (&x)[N], float yexp, const Consts& K, const PowfTables& T)
+{
+    double z[N], r[N], y0[N], r2[N], yy[N], p[N], r4[N], q[N], kd[N], rr[N], s[N], zz[N], w[N];
+    uint64_t ki[N];
+    const double yd = (double)yexp;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const uint32_t ixx = f2u(x[i]);
+        const uint32_t tmp = ixx - 0x3f330000u;
+        const int idx = (int)((tmp >> 19) & 15u);
+        const uint32_t top = tmp & 0xff800000u;
+        const Log2Entry le = T.log2_tab[idx];
+        z[i] = widen_pos_normal(ixx - top);
+        r[i] = le.invc;
+        y0[i] = le.logc + small_int_to_double((int32_t)top >> 23);
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(z[i], r[i], K.minus_one);
+#pragma unroll
+    for (int i = 0; i < N; i++) r2[i] = r[i] * r[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) yy[i] = fma(K.A0, r[i], K.A1);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = fma(K.A2, r[i], K.A3);
+#pragma unroll
+    for (int i = 0; i < N; i++) q[i] = fma(K.A4, r[i], y0[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) r4[i] = r2[i] * r2[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) q[i] = fma(p[i], r2[i], q[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) yy[i] = fma(yy[i], r4[i], q[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) yy[i] = yd * yy[i];          // ylogx
+#pragma unroll
+    for (int i = 0; i < N; i++) kd[i] = yy[i] + K.shift;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        ki[i] = d2u(kd[i]);
+        kd[i] = kd[i] - K.shift;
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) rr[i] = yy[i] - kd[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        uint64_t tt = T.exp2_tab[ki[i] & 31u];
+        tt += ki[i] << 47;
+        s[i] = u2d(tt);
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) zz[i] = fma(K.C0, rr[i], K.C1);
+#pragma unroll
+    for (int i = 0; i < N; i++) r2[i] = rr[i] * rr[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) w[i] = fma(K.C2, rr[i], K.one);
+#pragma unroll
+    for (int i = 0; i < N; i++) w[i] = fma(zz[i], r2[i], w[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = (float)(w[i] * s[i]);
+}
+#endif
 
 }  // namespace exact_math

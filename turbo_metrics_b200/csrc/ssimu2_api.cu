@@ -548,6 +548,11 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
     CR(cudaFuncSetAttribute((const void*)k_hpass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBytes));
     CR(cudaFuncSetAttribute((const void*)k_vpass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVSmemBytes));
     CR(cudaFuncSetAttribute((const void*)k_hv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXSmemBytes));
+    {
+        exact_math::CbrtScale cs;
+        for (int i = 0; i < 256; i++) cs.tab[i] = exact_math::cbrt_scale_entry(i);
+        CR(cudaMemcpyToSymbol(kCbrtC, &cs, sizeof(cs)));
+    }
     if (cfg->format == kNV12 || cfg->format == kP016) {
         const int n = cfg->format == kNV12 ? 256 : 1024, shift = cfg->format == kNV12 ? 0 : 6;
         const size_t bytes = (size_t)2 * n * n * sizeof(float);

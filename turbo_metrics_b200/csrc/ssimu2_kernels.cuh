@@ -91,11 +91,99 @@ __device__ const float kSrgb8Lut[256] = {
 #define RG_PREV_3 1.1755705f
 #define RG_PREV_5 0.00000000000000012246469f
 
+// ---- packed f32x2 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2) ----------------------------------------
+// One instruction = two independent IEEE round-to-nearest f32 operations on a 64-bit register pair, so the
+// results are bit-identical to the scalar forms while the filter costs half the issue slots.  Negations are
+// written as unpack / negate / pack: ptxas folds them into the source modifiers of the consuming instruction.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+struct f2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ f2 f2_pack(float lo, float hi)
+{
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(f2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ f2 f2_splat(float c) { return f2_pack(c, c); }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b)
+{
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 f2_sub(f2 a, f2 b)
+{
+    f2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b)
+{
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c)
+{
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+// a - m and a + m where m is the result of f2_mul: ptxas contracts mul.rn.f32x2 + add/sub.rn.f32x2 into one FFMA2
+// (even with --fmad=false), which would change the rounding; fma(m, -+1, a) is the same single-rounded a -+ m and
+// cannot be contracted.
+__device__ __forceinline__ f2 f2_sub_prod(f2 a, f2 m) { return f2_fma(m, f2_pack(-1.0f, -1.0f), a); }
+__device__ __forceinline__ f2 f2_add_prod(f2 a, f2 m) { return f2_fma(m, f2_pack(1.0f, 1.0f), a); }
+__device__ __forceinline__ f2 f2_neg(f2 a)
+{
+    float lo, hi;
+    f2_unpack(a, lo, hi);
+    return f2_pack(-lo, -hi);
+}
+__device__ __forceinline__ f2 f2_abs(f2 a)
+{
+    float lo, hi;
+    f2_unpack(a, lo, hi);
+    return f2_pack(fabsf(lo), fabsf(hi));
+}
+__device__ __forceinline__ f2 f2_max0(f2 a)
+{
+    float lo, hi;
+    f2_unpack(a, lo, hi);
+    return f2_pack(fmaxf(lo, 0.0f), fmaxf(hi, 0.0f));
+}
+__device__ __forceinline__ f2 f2_rcp_approx(f2 a)
+{
+    float lo, hi, rl, rh;
+    f2_unpack(a, lo, hi);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rl) : "f"(lo));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rh) : "f"(hi));
+    return f2_pack(rl, rh);
+}
+__device__ __forceinline__ float f2_hsum(f2 a)
+{
+    float lo, hi;
+    f2_unpack(a, lo, hi);
+    return lo + hi;
+}
+__device__ __forceinline__ f2 lds64(uint32_t addr)
+{
+    f2 r;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r.v) : "r"(addr));
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------
 // colour front-end
 // ------------------------------------------------------------------------------------------
 __device__ const exact_math::PowfTables kPowfTablesInit = {{EM_POWF_LOG2_TAB}, {EM_EXP2F_TAB}};
 __constant__ exact_math::Consts kEM = EM_CONSTS_INIT;
+// cbrt scale table in the constant bank (filled once per device by ssimu2_create): neighbouring pixels have similar
+// magnitudes, so the per-lane indexed LDC sees 1-3 distinct addresses per warp and the look-up stays off the LSU pipe,
+// which the front-end's table gathers keep busy
+__constant__ exact_math::CbrtScale kCbrtC;
 
 // BT709::eotf, cuda-colorspace-kernel/src/lib.rs:220-236 (same body for the BT601 variants).
 // The reference uses __nv_fast_powf (not reproducible on a CPU); the oracle and this kernel both use
@@ -322,11 +410,369 @@ __device__ __forceinline__ Rgb shfl_rgb(Rgb v, int src)
 }
 
 #ifndef KF2_MINB
-#define KF2_MINB 4
+#define KF2_MINB 4     // x 128 threads = 16 warps per SM at 128 registers: the lock-step FP64 chains need the registers (no spills)
 #endif
 constexpr int kF2Region = 32;
-constexpr int kF2Threads = 256;
+#ifndef KF2_THREADS
+#define KF2_THREADS 128
+#endif
+
+constexpr int kF2Threads = KF2_THREADS;
 constexpr int kF2RegionsPerWarp = 2;    // consecutive regions along x
+
+// ---- fast path of the front-end: regions that lie completely inside the frame (all but the last row / column of
+// regions), NV12 / P016 / sRGB8.  Same arithmetic as frontend_region below, operation for operation; what changes is the
+// schedule:
+//   lane = a 4 (wide) x 8 (tall) pixel patch of the 32x32 region, walked one ROW of four pixels at a time, so every XYB row
+//   leaves as one 128-bit store per plane (a warp instruction writes whole 128-byte lines) and every level-1 row as one
+//   64-bit store; the pyramid needs no parking: the 2x2 box of level 1 is accumulated in the reference's order while the
+//   two rows go by ((0,0)+(1,0) from the first row, then +(0,1), +(1,1)), level 2 likewise over two row pairs, levels 3-5
+//   by shuffles at the end of the region;
+//   integer -> float conversions and the per-pixel luma arithmetic come from two small shared-memory tables
+//   (exact: built with the same expressions), the divisions by the transfer-function constants use a compile-time
+//   reciprocal + Markstein's correction (IEEE-exact quotient, tests/test_gpu_parity.py::test_device_divisions_are_ieee),
+//   the transfer function is evaluated branch-free (both segments, select), XYB runs on pixel PAIRS in packed f32x2.
+struct FeTables {
+    exact_math::PowfTables T;
+    exact_math::CbrtScale S;
+    float luma[1024];     // YUV: (float)(max(Y, luma_min) - luma_min) * k.y by code (Y >> lut_shift); sRGB8: the 256-entry table
+    float chroma[1024];   // YUV: (float)(C - neutral) by code
+};
+
+// n / d for a compile-time d: r = RN(1 / d); q = RN(n r); the residual n - d q is exact in one FMA and the correction
+// lands on the correctly rounded quotient (Markstein).  n = 0 gives 0; n must not be so small that the quotient is subnormal.
+__device__ __forceinline__ float fdiv_rcp(float n, float d, float r)
+{
+    const float q = n * r;
+    const float rem = fmaf(-d, q, n);
+    return fmaf(rem, r, q);
+}
+
+// bt709_eotf + clamp01, branch-free (the power segment is evaluated for every argument and discarded below the threshold;
+// powf_glibc<false> is straight-line code with masked table indices, so a non-positive argument costs nothing but garbage)
+__device__ __forceinline__ float bt709_eotf_clamped(float v, const exact_math::PowfTables& T)
+{
+    const float BETA = 0.018053968510807f;
+    const float ALPHA = 1.0f + 5.5f * BETA;
+    const float THRESHOLD = 0.08124285829863521110029445797874f;
+    const float p = exact_math::powf_glibc<false>(fdiv_rcp(v + (ALPHA - 1.0f), ALPHA, 1.0f / ALPHA), 1.0f / 0.45f, kEM, T);
+    const float l = fdiv_rcp(v, 4.5f, 1.0f / 4.5f);
+    return clamp01(v >= THRESHOLD ? p : l);
+}
+
+// bt709_eotf_clamped on N values with the power segments advanced in lock-step
+template <int N>
+__device__ __forceinline__ void bt709_eotf_clamped_n(float (&v)[N], const exact_math::PowfTables& T)
+{
+    const float BETA = 0.018053968510807f;
+    const float ALPHA = 1.0f + 5.5f * BETA;
+    const float THRESHOLD = 0.08124285829863521110029445797874f;
+    float p[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = fdiv_rcp(v[i] + (ALPHA - 1.0f), ALPHA, 1.0f / ALPHA);
+    exact_math::powf_glibc_n<N>(p, 1.0f / 0.45f, kEM, T);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const float l = fdiv_rcp(v[i], 4.5f, 1.0f / 4.5f);
+        v[i] = clamp01(v[i] >= THRESHOLD ? p[i] : l);
+    }
+}
+
+// XYB of two pixels whose linear values are in [0, 1] (the integer formats): xyb_of on both lanes of a packed pair.
+// The fmaxf(mixed, 0) of the reference is dropped: mixed >= bias > 0 for non-negative inputs, so it never changes a bit.
+__device__ __forceinline__ void xyb_pair(f2 r, f2 g, f2 b, const exact_math::CbrtScale& S, f2& X, f2& Y, f2& B)
+{
+    const float K_M02 = 0.078f, K_M00 = 0.30f, K_M01 = 1.0f - K_M02 - K_M00;
+    const float K_M12 = 0.078f, K_M10 = 0.23f, K_M11 = 1.0f - K_M12 - K_M10;
+    const float K_M20 = 0.24342269f, K_M21 = 0.20476745f, K_M22 = 1.0f - K_M20 - K_M21;
+    const float K_B0 = 0.0037930734f;
+    const float K_B0_ROOT = 0.1559542025327239180319220163705f;
+    const f2 bias = f2_splat(K_B0);
+    const f2 mrg = f2_fma(f2_splat(K_M00), r, f2_fma(f2_splat(K_M01), g, f2_fma(f2_splat(K_M02), b, bias)));
+    const f2 mgr = f2_fma(f2_splat(K_M10), r, f2_fma(f2_splat(K_M11), g, f2_fma(f2_splat(K_M12), b, bias)));
+    const f2 mbb = f2_fma(f2_splat(K_M20), r, f2_fma(f2_splat(K_M21), g, f2_fma(f2_splat(K_M22), b, bias)));
+    float a0, a1, b0, b1, c0, c1;
+    f2_unpack(mrg, a0, a1);
+    f2_unpack(mgr, b0, b1);
+    f2_unpack(mbb, c0, c1);
+    {
+        float v[6] = {a0, a1, b0, b1, c0, c1};
+        exact_math::cbrtf_glibc_n<6>(v, kEM, &kCbrtC);   // six chains in lock-step: see exact_math.cuh
+        a0 = v[0]; a1 = v[1]; b0 = v[2]; b1 = v[3]; c0 = v[4]; c1 = v[5];
+    }
+    const f2 nroot = f2_splat(-K_B0_ROOT);
+    const f2 rg = f2_add(f2_pack(a0, a1), nroot), gr = f2_add(f2_pack(b0, b1), nroot), bb = f2_add(f2_pack(c0, c1), nroot);
+    const f2 half = f2_splat(0.5f);
+    const f2 x = f2_mul(half, f2_sub(rg, gr)), y = f2_mul(half, f2_add(rg, gr));   // 0.5 * s is exact: a later contraction into an FMA cannot change the result
+    X = f2_fma(x, f2_splat(14.0f), f2_splat(0.42f));
+    Y = f2_add(y, f2_splat(0.01f));
+    B = f2_add(f2_sub(bb, y), f2_splat(0.55f));
+}
+
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+template <int FMT>
+struct FastFmt {
+    static constexpr bool ok = (FMT == kNV12 || FMT == kP016 || FMT == kSRGB8);
+};
+
+// the raw words of one row of four pixels (P016: 2 words, NV12: 1, sRGB8: 3) / of the two chroma samples under them
+struct RowWords {
+    uint32_t w0, w1, w2;
+};
+// `asm volatile` on purpose: the compiler sinks an ordinary load to just above its first use, which puts the whole DRAM
+// latency in front of the warp; a volatile asm keeps its place among the stores of the rows, i.e. where it was written --
+// half an iteration ahead of the consumer.
+template <int FMT>
+__device__ __forceinline__ RowWords load_row_words(const uint8_t* p)
+{
+    RowWords r{0, 0, 0};
+    if constexpr (FMT == kP016) {
+        asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.w0), "=r"(r.w1) : "l"(p));
+    } else if constexpr (FMT == kNV12) {
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r.w0) : "l"(p));
+    } else {
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r.w0) : "l"(p));
+        asm volatile("ld.global.nc.u32 %0, [%1+4];" : "=r"(r.w1) : "l"(p));
+        asm volatile("ld.global.nc.u32 %0, [%1+8];" : "=r"(r.w2) : "l"(p));
+    }
+    return r;
+}
+
+// L2 prefetch of the raw samples of one interior region (this lane's 8 luma rows + 4 chroma rows).  A prefetch has no
+// destination register, so unlike a load it cannot be sunk to its consumer: issued one work item ahead, it turns the DRAM
+// latency in front of every first use into an L2 hit.
+template <int FMT>
+__device__ __forceinline__ void prefetch_region(const FrameIn& f, int X0, int Y0)
+{
+    const int lane = threadIdx.x & 31;
+    const int x = X0 + 4 * (lane & 7), y0 = Y0 + 8 * (lane >> 3);
+    constexpr int kBpp = FMT == kP016 ? 2 : (FMT == kNV12 ? 1 : 3);
+    const uint8_t* pY = f.p0 + (size_t)y0 * f.pitch + (size_t)(x * kBpp);
+#pragma unroll
+    for (int r = 0; r < 8; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pY + (size_t)r * f.pitch));
+    if constexpr (FMT != kSRGB8) {
+        const uint8_t* pC = f.p1 + (size_t)(y0 >> 1) * f.pitch + (size_t)(x * kBpp);
+#pragma unroll
+        for (int r = 0; r < 4; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pC + (size_t)r * f.pitch));
+    }
+}
+
+// One interior 32x32 region of one image; executed by a full warp.  Returns false (warp-uniform) if the region holds P016
+// samples with non-zero low bits (not 10-bit content): the caller then redoes the region with the general path.
+// Register budget: the six cube roots of a pixel pair advance in lock-step (exact_math::cbrtf_glibc_n: the FP64 pipe has a
+// 23-cycle dependent-issue latency, so a warp must carry several independent chains) and want ~60 registers; the kernel
+// runs at 128 registers x 16 warps per SM.  The state carried across rows is kept small -- 32-bit lane offsets against
+// warp-uniform base pointers, the first of the lane's two level-2 pixels parked in shared memory (`park`, three floats per
+// thread) -- and the two pixel pairs of a row are evaluated one after the other (an empty asm ties the second pair's inputs
+// to the first pair's results): a value spilled to local memory comes back through an L1 that the table gathers keep
+// evicting, and every spill reload showed up as a long-scoreboard stall (profiles/r2_frontend_notes.md).
+template <int FMT>
+__device__ __forceinline__ bool frontend_region_fast(const Geo& g, const FrameIn& f, float* __restrict__ ximg, int img, int X0, int Y0,
+                                                     const FeTables& tb, float* __restrict__ park, int park_stride)
+{
+    const int lane = threadIdx.x & 31;
+    const int pxi = lane & 7, pyi = lane >> 3;
+    const int x = X0 + 4 * pxi, y0 = Y0 + 8 * pyi;
+    const uint32_t s_luma = smem_u32(tb.luma), s_chroma = smem_u32(tb.chroma);
+    const uint32_t pitch0 = (uint32_t)g.sc[0].pitch, pitch1 = (uint32_t)g.sc[1].pitch, pitch2 = (uint32_t)g.sc[2].pitch;
+    const size_t plane0 = (size_t)g.sc[0].h * pitch0, plane1 = (size_t)g.sc[1].h * pitch1, plane2 = (size_t)g.sc[2].h * pitch2;
+    // warp-uniform plane bases of levels 0-2, per-lane element offsets
+    float* const b0 = ximg + g.sc[0].xyb_off + (size_t)img * 3 * plane0;
+    float* const b1 = ximg + g.sc[1].xyb_off + (size_t)img * 3 * plane1;
+    float* const b2 = ximg + g.sc[2].xyb_off + (size_t)img * 3 * plane2;
+    uint32_t o0 = (uint32_t)y0 * pitch0 + (uint32_t)x;
+    uint32_t o1 = (uint32_t)(y0 >> 1) * pitch1 + (uint32_t)(x >> 1);
+    const uint32_t o2 = (uint32_t)(y0 >> 2) * pitch2 + (uint32_t)(x >> 2);
+    constexpr int kBpp = FMT == kP016 ? 2 : (FMT == kNV12 ? 1 : 3);
+    uint32_t oY = (uint32_t)y0 * f.pitch + (uint32_t)(x * kBpp);
+    uint32_t oC = (uint32_t)(y0 >> 1) * f.pitch + (uint32_t)(x * kBpp);
+    const char* lut = reinterpret_cast<const char*>(g.eotf_lut);
+    const uint32_t lut_b = (uint32_t)g.lut_n * (uint32_t)g.lut_n * 4u;   // byte offset of the B table
+    uint32_t bad = 0;
+    float s1[2][3];
+    float s2[3] = {0.f, 0.f, 0.f};
+    Rgb l2b = Rgb{0.f, 0.f, 0.f};
+
+    // The raw samples are fetched one step ahead (the second row of a pair at the top of the pair, the next pair's chroma
+    // and first row in its middle): a load that is consumed right away exposes the full DRAM latency to the warp.
+    RowWords wy_next = load_row_words<FMT>(f.p0 + oY), wc_next{0, 0, 0};
+    oY += f.pitch;
+    if constexpr (FMT != kSRGB8) {
+        wc_next = load_row_words<FMT>(f.p1 + oC);
+        oC += f.pitch;
+    }
+#pragma unroll 1
+    for (int rp = 0; rp < 4; rp++) {
+        const RowWords wc = wc_next, wy0 = wy_next;
+        const RowWords wy1 = load_row_words<FMT>(f.p0 + oY);
+        oY += f.pitch;
+        // ---- chroma of the row pair: two samples, each shared by a 2x2 block
+        float g_[2] = {0.f, 0.f};
+        uint32_t roff[2] = {0, 0}, boff[2] = {0, 0};
+        if constexpr (FMT == kP016) {
+            bad |= wc.w0 | wc.w1;
+            const uint32_t w[2] = {wc.w0, wc.w1};
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const float cb = lds_f32(s_chroma + ((w[j] >> 4) & 0xFFCu)), cr = lds_f32(s_chroma + ((w[j] >> 20) & 0xFFCu));
+                g_[j] = fmaf(g.coef.g1, cb, g.coef.g2 * cr);
+                boff[j] = lut_b + ((w[j] << 6) & 0x3FF000u);
+                roff[j] = (w[j] >> 10) & 0x3FF000u;
+            }
+        } else if constexpr (FMT == kNV12) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const uint32_t cbi = (wc.w0 >> (16 * j)) & 0xFFu, cri = (wc.w0 >> (16 * j + 8)) & 0xFFu;
+                const float cb = lds_f32(s_chroma + cbi * 4u), cr = lds_f32(s_chroma + cri * 4u);
+                g_[j] = fmaf(g.coef.g1, cb, g.coef.g2 * cr);
+                boff[j] = lut_b + (cbi << 10);
+                roff[j] = cri << 10;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const RowWords wy = r == 0 ? wy0 : wy1;
+            if (r == 1 && rp < 3) {
+                // next pair: chroma + first row
+                wy_next = load_row_words<FMT>(f.p0 + oY);
+                oY += f.pitch;
+                if constexpr (FMT != kSRGB8) {
+                    wc_next = load_row_words<FMT>(f.p1 + oC);
+                    oC += f.pitch;
+                }
+            }
+            // ---- one row of four pixels -> linear RGB -> XYB, as two pixel pairs
+            float lr[4], lb[4], lg[4];
+            uint32_t yc[4] = {0, 0, 0, 0};
+            if constexpr (FMT == kP016) {
+                bad |= wy.w0 | wy.w1;
+                yc[0] = (wy.w0 >> 4) & 0xFFCu; yc[1] = (wy.w0 >> 20) & 0xFFCu; yc[2] = (wy.w1 >> 4) & 0xFFCu; yc[3] = (wy.w1 >> 20) & 0xFFCu;
+            } else if constexpr (FMT == kNV12) {
+                yc[0] = (wy.w0 << 2) & 0x3FCu; yc[1] = (wy.w0 >> 6) & 0x3FCu; yc[2] = (wy.w0 >> 14) & 0x3FCu; yc[3] = (wy.w0 >> 22) & 0x3FCu;
+            }
+            if constexpr (FMT != kSRGB8) {
+                // the exact R / B memo: all eight gathers of the row are issued before the first transfer-function chain
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    lr[i] = __ldg(reinterpret_cast<const float*>(lut + (roff[i >> 1] + yc[i])));
+                    lb[i] = __ldg(reinterpret_cast<const float*>(lut + (boff[i >> 1] + yc[i])));
+                }
+            } else {
+                // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+                auto tab = [&](uint32_t w, int k) { return lds_f32(s_luma + (k == 0 ? (w << 2) & 0x3FCu : (w >> (8 * k - 2)) & 0x3FCu)); };
+                lr[0] = tab(wy.w0, 0); lg[0] = tab(wy.w0, 1); lb[0] = tab(wy.w0, 2);
+                lr[1] = tab(wy.w0, 3); lg[1] = tab(wy.w1, 0); lb[1] = tab(wy.w1, 1);
+                lr[2] = tab(wy.w1, 2); lg[2] = tab(wy.w1, 3); lb[2] = tab(wy.w2, 0);
+                lr[3] = tab(wy.w2, 1); lg[3] = tab(wy.w2, 2); lb[3] = tab(wy.w2, 3);
+            }
+            if constexpr (FMT != kSRGB8) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) lg[i] = lds_f32(s_luma + yc[i]) + g_[i >> 1];
+                bt709_eotf_clamped_n<4>(lg, tb.T);
+            }
+            f2 Xp[2], Yp[2], Bp[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                // level 1: box sums in the reference's order (0,0), (1,0), (0,1), (1,1); every value is >= +0, so the leading
+                // "0 +" of box4 is the identity
+                if (r == 0) {
+                    s1[j][0] = lr[2 * j] + lr[2 * j + 1];
+                    s1[j][1] = lg[2 * j] + lg[2 * j + 1];
+                    s1[j][2] = lb[2 * j] + lb[2 * j + 1];
+                } else {
+                    s1[j][0] = (s1[j][0] + lr[2 * j]) + lr[2 * j + 1];
+                    s1[j][1] = (s1[j][1] + lg[2 * j]) + lg[2 * j + 1];
+                    s1[j][2] = (s1[j][2] + lb[2 * j]) + lb[2 * j + 1];
+                }
+                xyb_pair(f2_pack(lr[2 * j], lr[2 * j + 1]), f2_pack(lg[2 * j], lg[2 * j + 1]), f2_pack(lb[2 * j], lb[2 * j + 1]), tb.S, Xp[j],
+                         Yp[j], Bp[j]);
+                // evaluate the second pair AFTER the first (see the header comment)
+                if (j == 0) asm volatile("" : "+f"(lr[2]), "+f"(lr[3]) : "l"(Bp[0].v));
+            }
+            {
+                float e0, e1, e2, e3;
+                f2_unpack(Xp[0], e0, e1); f2_unpack(Xp[1], e2, e3);
+                *reinterpret_cast<float4*>(b0 + o0) = make_float4(e0, e1, e2, e3);
+                f2_unpack(Yp[0], e0, e1); f2_unpack(Yp[1], e2, e3);
+                *reinterpret_cast<float4*>(b0 + plane0 + o0) = make_float4(e0, e1, e2, e3);
+                f2_unpack(Bp[0], e0, e1); f2_unpack(Bp[1], e2, e3);
+                *reinterpret_cast<float4*>(b0 + 2 * plane0 + o0) = make_float4(e0, e1, e2, e3);
+            }
+            o0 += pitch0;
+        }
+        // ---- level 1: two pixels, one 64-bit store per plane
+        const Rgb v10 = Rgb{s1[0][0] * 0.25f, s1[0][1] * 0.25f, s1[0][2] * 0.25f};
+        const Rgb v11 = Rgb{s1[1][0] * 0.25f, s1[1][1] * 0.25f, s1[1][2] * 0.25f};
+        {
+            f2 X, Y, B;
+            xyb_pair(f2_pack(v10.r, v11.r), f2_pack(v10.g, v11.g), f2_pack(v10.b, v11.b), tb.S, X, Y, B);
+            float e0, e1;
+            f2_unpack(X, e0, e1); *reinterpret_cast<float2*>(b1 + o1) = make_float2(e0, e1);
+            f2_unpack(Y, e0, e1); *reinterpret_cast<float2*>(b1 + plane1 + o1) = make_float2(e0, e1);
+            f2_unpack(B, e0, e1); *reinterpret_cast<float2*>(b1 + 2 * plane1 + o1) = make_float2(e0, e1);
+            o1 += pitch1;
+        }
+        // ---- level 2: box of the 2x2 level-1 pixels of two consecutive row pairs
+        if ((rp & 1) == 0) {
+            s2[0] = v10.r + v11.r; s2[1] = v10.g + v11.g; s2[2] = v10.b + v11.b;
+        } else {
+            const Rgb v2 = Rgb{((s2[0] + v10.r) + v11.r) * 0.25f, ((s2[1] + v10.g) + v11.g) * 0.25f, ((s2[2] + v10.b) + v11.b) * 0.25f};
+            if (rp == 1) {
+                park[0] = v2.r; park[park_stride] = v2.g; park[2 * park_stride] = v2.b;
+            } else {
+                l2b = v2;
+            }
+        }
+    }
+    const Rgb l2a = Rgb{park[0], park[park_stride], park[2 * park_stride]};
+    {
+        // the lane's two level-2 pixels (one above the other)
+        f2 X, Y, B;
+        xyb_pair(f2_pack(l2a.r, l2b.r), f2_pack(l2a.g, l2b.g), f2_pack(l2a.b, l2b.b), tb.S, X, Y, B);
+        float e0, e1;
+        float* q2 = b2 + o2;
+        f2_unpack(X, e0, e1); q2[0] = e0; q2[pitch2] = e1;
+        f2_unpack(Y, e0, e1); q2[plane2] = e0; q2[plane2 + pitch2] = e1;
+        f2_unpack(B, e0, e1); q2[2 * plane2] = e0; q2[2 * plane2 + pitch2] = e1;
+    }
+    // ---- levels 3, 4, 5: 16 + 4 + 1 pixels per region
+    //   level 3: lanes with even pxi (with the lane to the right); level 4: lanes 0, 4, 16, 20; level 5: lane 0
+    const Rgb p0 = shfl_rgb_xor(l2a, 1), p1 = shfl_rgb_xor(l2b, 1);
+    const Rgb v3 = Rgb{box4(l2a.r, p0.r, l2b.r, p1.r), box4(l2a.g, p0.g, l2b.g, p1.g), box4(l2a.b, p0.b, l2b.b, p1.b)};
+    const Rgb a3 = shfl_rgb_xor(v3, 2), b3 = shfl_rgb_xor(v3, 8), c3 = shfl_rgb_xor(v3, 10);
+    const Rgb v4 = Rgb{box4(v3.r, a3.r, b3.r, c3.r), box4(v3.g, a3.g, b3.g, c3.g), box4(v3.b, a3.b, b3.b, c3.b)};
+    const Rgb a4 = shfl_rgb_xor(v4, 4), b4 = shfl_rgb_xor(v4, 16), c4 = shfl_rgb_xor(v4, 20);
+    const Rgb v5 = Rgb{box4(v4.r, a4.r, b4.r, c4.r), box4(v4.g, a4.g, b4.g, c4.g), box4(v4.b, a4.b, b4.b, c4.b)};
+    // one XYB evaluation for all of them: level 3 stays on its lanes, level 4 moves one lane to the right (1, 5, 17, 21),
+    // level 5 to lane 3
+    const Rgb m4 = shfl_rgb(v4, (lane - 1) & 31), m5 = shfl_rgb(v5, 0);
+    Rgb v = v3;
+    int s = 3, ox = (X0 >> 3) + (pxi >> 1), oy = (Y0 >> 3) + pyi;
+    if (pxi & 1) {
+        s = -1;
+        if ((lane & 0x0B) == 1) {   // lanes 1, 5, 17, 21
+            v = m4; s = 4; ox = (X0 >> 4) + (pxi >> 2); oy = (Y0 >> 4) + (pyi >> 1);
+        } else if (lane == 3) {
+            v = m5; s = 5; ox = X0 >> 5; oy = Y0 >> 5;
+        }
+    }
+    float X, Yv, B;
+    xyb_of<FMT>(v.r, v.g, v.b, tb.S, X, Yv, B);
+    if (s >= 3 && s < g.nscales) {
+        const ScaleDesc& sd = g.sc[s];
+        const size_t plane = (size_t)sd.h * sd.pitch;
+        float* q = ximg + sd.xyb_off + (size_t)img * 3 * plane + (size_t)oy * sd.pitch + ox;
+        q[0] = X; q[plane] = Yv; q[2 * plane] = B;
+    }
+    if constexpr (FMT == kP016) return !__any_sync(0xffffffffu, (bad & 0x003F003Fu) != 0);
+    return true;
+}
 
 // One 32x32 region of one image of one frame; executed by a full warp.
 template <int FMT>
@@ -526,28 +972,60 @@ template <int FMT>
 __global__ void __launch_bounds__(kF2Threads, KF2_MINB) k_frontend2(const __grid_constant__ Geo g, const FramePair* __restrict__ in,
                                                              float* __restrict__ xyb_base, int frame0)
 {
-    __shared__ exact_math::PowfTables T;
-    __shared__ exact_math::CbrtScale S;
+    __shared__ FeTables tb;
     __shared__ float scratch[15 * kF2Threads];
     {
         const uint64_t* src = reinterpret_cast<const uint64_t*>(&kPowfTablesInit);
-        uint64_t* dst = reinterpret_cast<uint64_t*>(&T);
+        uint64_t* dst = reinterpret_cast<uint64_t*>(&tb.T);
         for (int i = threadIdx.x; i < (int)(sizeof(exact_math::PowfTables) / 8); i += kF2Threads) dst[i] = src[i];
-        S.tab[threadIdx.x] = exact_math::cbrt_scale_entry(threadIdx.x);
+        for (int i = threadIdx.x; i < 256; i += kF2Threads) tb.S.tab[i] = exact_math::cbrt_scale_entry(i);
+        if constexpr (FMT == kNV12 || FMT == kP016) {
+            // the per-sample integer -> float work of yuv_px / yuv_chroma, once per code (same expressions => same bits)
+            for (int c = threadIdx.x; c < g.lut_n; c += kF2Threads) {
+                const int v = c << g.lut_shift;
+                tb.luma[c] = (float)(max(v, g.coef.luma_min) - g.coef.luma_min) * g.coef.y;
+                tb.chroma[c] = (float)(v - g.coef.neutral);
+            }
+        } else if constexpr (FMT == kSRGB8) {
+            for (int i = threadIdx.x; i < 256; i += kF2Threads) tb.luma[i] = kSrgb8Lut[i];
+        }
     }
     __syncthreads();
     const int frame = frame0 + blockIdx.z, warp = threadIdx.x >> 5;
     const int rx_n = (g.sc[0].w + kF2Region - 1) / kF2Region;
     const FramePair fp = in[frame];
     float* xyb_slot = xyb_base + (size_t)frame * g.xyb_stride;
+    const int Y0 = blockIdx.y * kF2Region;
+    const int rx0 = (blockIdx.x * (kF2Threads / 32) + warp) * kF2RegionsPerWarp;
+    const bool rows_inside = Y0 + kF2Region <= g.sc[0].h;
+    if constexpr (FastFmt<FMT>::ok) {
+        if (rows_inside && (rx0 + 1) * kF2Region <= g.sc[0].w) prefetch_region<FMT>(fp.ref, rx0 * kF2Region, Y0);
+    }
 #pragma unroll 1
     for (int i = 0; i < kF2RegionsPerWarp; i++) {
-        const int rx = (blockIdx.x * (kF2Threads / 32) + warp) * kF2RegionsPerWarp + i;
+        const int rx = rx0 + i;
         if (rx >= rx_n) break;
+        const int X0 = rx * kF2Region;
 #pragma unroll 1
-        for (int img = 0; img < 2; img++)
-            frontend_region<FMT>(g, img ? fp.dis : fp.ref, xyb_slot, img, rx * kF2Region, blockIdx.y * kF2Region, T, S,
-                                 scratch + threadIdx.x, kF2Threads);
+        for (int img = 0; img < 2; img++) {
+            const FrameIn& f = img ? fp.dis : fp.ref;
+            bool done = false;
+            if constexpr (FastFmt<FMT>::ok) {
+                // the next work item of this warp (the other image of this region, then the next region) one step ahead
+                if (img == 0) {
+                    if (rows_inside && X0 + kF2Region <= g.sc[0].w) prefetch_region<FMT>(fp.dis, X0, Y0);
+                } else if (i + 1 < kF2RegionsPerWarp && rows_inside && X0 + 2 * kF2Region <= g.sc[0].w) {
+                    prefetch_region<FMT>(fp.ref, X0 + kF2Region, Y0);
+                }
+                // interior region, aligned rows, (YUV) the exact R / B memo present
+                const uint32_t align = FMT == kP016 ? 7u : 3u;
+                const bool fast = X0 + kF2Region <= g.sc[0].w && Y0 + kF2Region <= g.sc[0].h &&
+                                  ((((uintptr_t)f.p0 | (uintptr_t)f.p1 | (uintptr_t)f.pitch) & align) == 0) &&
+                                  (FMT == kSRGB8 || g.eotf_lut != nullptr);
+                if (fast) done = frontend_region_fast<FMT>(g, f, xyb_slot, img, X0, Y0, tb, scratch + threadIdx.x, kF2Threads);
+            }
+            if (!done) frontend_region<FMT>(g, f, xyb_slot, img, X0, Y0, tb.T, tb.S, scratch + threadIdx.x, kF2Threads);
+        }
     }
 }
 
@@ -565,7 +1043,6 @@ struct alignas(64) TmaMapsH {
     CUtensorMap hb_out[kMaxScales];  // H pass store: 15 planes, box {32, 32, 15, 1}, 128B swizzle
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -603,11 +1080,6 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3)
-{
-    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-                 : "memory");
-}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3)
 {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
@@ -816,27 +1288,7 @@ __global__ void __launch_bounds__(kHThreads, 2) k_hpass(const __grid_constant__ 
 // of each filter is a per-thread ring in shared memory (no barriers in the main loop).
 // ------------------------------------------------------------------------------------------
 constexpr int kVCols = 64;
-constexpr int kVThreads = 3 * kVCols;
 constexpr int kVRing = 10;
-constexpr int kVSub = 5;  // rows per load batch (7 * kVSub independent loads in flight per thread)
-
-struct VState {
-    float p1, p3, p5, pp1, pp3, pp5;
-};
-
-__device__ __forceinline__ float vstep(VState& s, float top, float bottom)
-{
-    float sum = top + bottom;
-    float a1 = fmaf(s.p1, -RG_PREV_1, s.pp1);
-    float a3 = fmaf(s.p3, -RG_PREV_3, s.pp3);
-    float a5 = fmaf(s.p5, -RG_PREV_5, s.pp5);
-    float o1 = fmaf(sum, RG_IN_1, -a1);
-    float o3 = fmaf(sum, RG_IN_3, -a3);
-    float o5 = fmaf(sum, RG_IN_5, -a5);
-    s.pp1 = s.p1; s.pp3 = s.p3; s.pp5 = s.p5;
-    s.p1 = o1; s.p3 = o3; s.p5 = o5;
-    return (o1 + o3) + o5;
-}
 
 // Correctly rounded f32 quotient for operands in the normal range (no zero / inf / nan / subnormal
 // handling): reciprocal seed + one Newton step + Markstein's residual correction.  Checked against
@@ -850,125 +1302,6 @@ __device__ __forceinline__ float div_rn_normal(float n, float d)
     float q = n * r;
     float rem = fmaf(-d, q, n);
     return fmaf(rem, r, q);
-}
-
-// The three error maps of one (pixel, channel) and their contributions to the six sums.
-// SSIM' term: cpu.rs:604-631 -- identical f32 arithmetic up to the quotient q; d = 1 - q is then
-// formed in f32 (exact whenever q is in [0.5, 2], i.e. wherever d is small) instead of f64.
-// Edge terms: cpu.rs:658-674 computes (1+|dis-mu2|)/(1+|ref-mu1|) - 1 in f64; here the algebraically
-// equal (a-b)/(1+b) in f32, which keeps a RELATIVE error of ~2e-7 on every term (the f32 form of the
-// original expression would not).  Nothing downstream amplifies these errors: they enter the sums
-// directly, 3 orders of magnitude under the 1e-4 bar.
-__device__ __forceinline__ void error_maps(const float (&o)[5], float ref, float dis, float (&part)[6])
-{
-    const float C2 = 0.0009f;
-    const float s11 = o[0], s22 = o[1], s12 = o[2], mu1 = o[3], mu2 = o[4];
-    const float mu11 = mu1 * mu1, mu22 = mu2 * mu2, mu12 = mu1 * mu2;
-    const float mu_diff = mu1 - mu2;
-    const float num_m = fmaf(mu_diff, -mu_diff, 1.0f);
-    const float num_s = fmaf(2.0f, s12 - mu12, C2);
-    const float denom_s = ((s11 - mu11) + (s22 - mu22)) + C2;
-    const float q = div_rn_normal(num_m * num_s, denom_s);
-    const float d = fmaxf(1.0f - q, 0.0f);
-    part[0] += d;
-    const float d2 = d * d;
-    part[1] = fmaf(d2, d2, part[1]);
-
-    const float a = fabsf(dis - mu2), b = fabsf(ref - mu1);
-    const float den = 1.0f + b;
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
-    r = fmaf(r, fmaf(-den, r, 1.0f), r);
-    const float d1 = (a - b) * r;
-    const float e2 = d1 * d1, e4 = e2 * e2;
-    const bool pos = d1 > 0.0f;
-    part[2] += pos ? d1 : 0.0f;      // artifact
-    part[3] += pos ? e4 : 0.0f;
-    part[4] += pos ? 0.0f : -d1;     // detail lost
-    part[5] += pos ? 0.0f : e4;
-}
-
-// ---- packed f32x2 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2) ----------------------------------------
-// One instruction = two independent IEEE round-to-nearest f32 operations on a 64-bit register pair, so the
-// results are bit-identical to the scalar forms while the filter costs half the issue slots.  Negations are
-// written as unpack / negate / pack: ptxas folds them into the source modifiers of the consuming instruction.
-struct f2 {
-    unsigned long long v;
-};
-__device__ __forceinline__ f2 f2_pack(float lo, float hi)
-{
-    f2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void f2_unpack(f2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
-__device__ __forceinline__ f2 f2_splat(float c) { return f2_pack(c, c); }
-__device__ __forceinline__ f2 f2_add(f2 a, f2 b)
-{
-    f2 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
-    return r;
-}
-__device__ __forceinline__ f2 f2_sub(f2 a, f2 b)
-{
-    f2 r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
-    return r;
-}
-__device__ __forceinline__ f2 f2_mul(f2 a, f2 b)
-{
-    f2 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
-    return r;
-}
-__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c)
-{
-    f2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
-    return r;
-}
-// a - m and a + m where m is the result of f2_mul: ptxas contracts mul.rn.f32x2 + add/sub.rn.f32x2 into one FFMA2
-// (even with --fmad=false), which would change the rounding; fma(m, -+1, a) is the same single-rounded a -+ m and
-// cannot be contracted.
-__device__ __forceinline__ f2 f2_sub_prod(f2 a, f2 m) { return f2_fma(m, f2_pack(-1.0f, -1.0f), a); }
-__device__ __forceinline__ f2 f2_add_prod(f2 a, f2 m) { return f2_fma(m, f2_pack(1.0f, 1.0f), a); }
-__device__ __forceinline__ f2 f2_neg(f2 a)
-{
-    float lo, hi;
-    f2_unpack(a, lo, hi);
-    return f2_pack(-lo, -hi);
-}
-__device__ __forceinline__ f2 f2_abs(f2 a)
-{
-    float lo, hi;
-    f2_unpack(a, lo, hi);
-    return f2_pack(fabsf(lo), fabsf(hi));
-}
-__device__ __forceinline__ f2 f2_max0(f2 a)
-{
-    float lo, hi;
-    f2_unpack(a, lo, hi);
-    return f2_pack(fmaxf(lo, 0.0f), fmaxf(hi, 0.0f));
-}
-__device__ __forceinline__ f2 f2_rcp_approx(f2 a)
-{
-    float lo, hi, rl, rh;
-    f2_unpack(a, lo, hi);
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rl) : "f"(lo));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rh) : "f"(hi));
-    return f2_pack(rl, rh);
-}
-__device__ __forceinline__ float f2_hsum(f2 a)
-{
-    float lo, hi;
-    f2_unpack(a, lo, hi);
-    return lo + hi;
-}
-__device__ __forceinline__ f2 lds64(uint32_t addr)
-{
-    f2 r;
-    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r.v) : "r"(addr));
-    return r;
 }
 
 // vstep / div_rn_normal / error_maps on two adjacent columns at once (same operations, same order).
@@ -1002,6 +1335,13 @@ __device__ __forceinline__ f2 div_rn_normal2(f2 n, f2 d)
     return f2_fma(rem, r, q);
 }
 
+// The three error maps of two adjacent pixels of one channel and their contributions to the six sums.
+// SSIM' term: cpu.rs:604-631 -- identical f32 arithmetic up to the quotient q; d = 1 - q is then
+// formed in f32 (exact whenever q is in [0.5, 2], i.e. wherever d is small) instead of f64.
+// Edge terms: cpu.rs:658-674 computes (1+|dis-mu2|)/(1+|ref-mu1|) - 1 in f64; here the algebraically
+// equal (a-b)/(1+b) in f32, which keeps a RELATIVE error of ~2e-7 on every term (the f32 form of the
+// original expression would not).  Nothing downstream amplifies these errors: they enter the sums
+// directly, 3 orders of magnitude under the 1e-4 bar.
 // art = max(d1, 0), detail = max(-d1, 0); their 4th powers are formed from the clamped values (identical to
 // selecting d1^4 by the sign of d1: one of the two is exactly zero).
 __device__ __forceinline__ void error_maps2(const f2 (&o)[5], f2 ref, f2 dis, f2 (&part)[6])

@@ -595,3 +595,46 @@ def test_shard_api_device_frames(oracle):
         got = sh.get_scores(sh.submit_device(refs, diss))
     for g in range(n):
         assert abs(got[g] - expect[g % nd]) <= SCORE_ATOL and got[g] == got[g % nd]
+
+
+# ------------------------------------------------------------------------------------------ score-only mode
+@pytest.mark.parametrize("kind,w,h", CASES + [("p016", 1920, 1080)])
+def test_score_only_mode_gives_the_same_bits(oracle, kind, w, h):
+    """SSIMU2_FLAG_SCORE_ONLY skips the filters and the SSIM' map of every (scale, channel) whose two SSIM' weights are zero
+    (X and B at scale 0 -- 30 % of the FP32 work of the 4K path; the reference computes them and multiplies by 0.0,
+    ssimulacra2-cuda/src/lib.rs:586-603).  What remains is computed by the same instructions in the same order, so the score
+    must be BIT-equal to the full mode; the norms are not available."""
+    tm = _tm()
+    fmt, mk, r, d, (so, no, nso) = _make(kind, w, h, frame=1, seed=3, oracle=oracle) if (w, h) != (1920, 1080) or kind != "p016" else \
+        _make(kind, w, h, frame=1, seed=3, oracle=oracle)
+    rg, dg = r.cuda(), d.cuda()
+    n = 9
+    with tm.Ssimulacra2(w, h, fmt, batch=4, ring=2) as m:
+        full = m.get_scores(m.compute_batch([mk(rg)] * n, [mk(dg)] * n))
+    with tm.Ssimulacra2(w, h, fmt, batch=4, ring=2, score_only=True) as m:
+        ts = m.compute_batch([mk(rg)] * n, [mk(dg)] * n)
+        lite = m.get_scores(ts)
+        with pytest.raises(tm.Ssimu2Error) as e:
+            m.get_norms(ts[0])
+        assert e.value.status == -2          # SSIMU2_E_UNSUPPORTED
+        assert m.info().flags & 1
+    assert np.array_equal(full, lite), (full[0], lite[0])
+    assert abs(lite[0] - so) <= SCORE_ATOL
+
+
+def test_score_only_strip_handoff_under_load():
+    """The lite strips have their own warp-role map and barrier counts: many 1080p pairs through full batches of all ring
+    slots, every repetition bit-equal to the full mode's score."""
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    w, h, nd, n = 1920, 1080, 4, 96
+    fr = [synth.make_pair_yuv420(w, h, 8, frame=i, seed=5, device="cuda") for i in range(nd)]
+    pitch, ch = fr[0][2], fr[0][3]
+    F = lambda t: tm.DeviceFrame.yuv420(t, pitch, ch)
+    refs, diss = [F(fr[i % nd][0]) for i in range(n)], [F(fr[i % nd][1]) for i in range(n)]
+    with tm.Ssimulacra2(w, h, tm.PixelFormat.NV12, batch=16, ring=3) as m:
+        full = m.get_scores(m.compute_batch(refs[:nd], diss[:nd]))
+    with tm.Ssimulacra2(w, h, tm.PixelFormat.NV12, batch=16, ring=3, score_only=True) as m:
+        s = m.get_scores(m.compute_batch(refs, diss))
+    for i in range(n):
+        assert s[i] == full[i % nd], (i, s[i], full[i % nd])

@@ -104,6 +104,7 @@ struct ssimu2_handle {
     double total_ms[4] = {0, 0, 0, 0};  // per-kernel device time summed over harvested batches
     uint64_t timed_batches = 0, timed_pairs = 0;
     uint64_t alg_bytes = 0, io_bytes = 0;
+    unsigned char lite[kMaxScales] = {};   // score-only: channels without SSIM' per scale (HvArgs::lite)
 };
 
 namespace {
@@ -329,6 +330,7 @@ static int launch_batch(ssimu2_handle* h, int si)
         a.partials = sl.partials;
         a.epoch = ++sl.epoch;
         a.nframes = (int)n;
+        memcpy(a.lite, h->lite, sizeof(a.lite));
         if (timed) cudaEventRecord(sl.ev_k[2], st);
         k_hv<<<(unsigned)(g.items_v * n), kXThreads, kXSmemBytes, st>>>(g, sl.maps_x, a);
         if (timed) cudaEventRecord(sl.ev_k[3], st);
@@ -521,6 +523,17 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
     h->pipeline = (int)cfg->pipeline;
     h->score_only = (cfg->flags & SSIMU2_FLAG_SCORE_ONLY) != 0;
     build_geo(h);
+    if (h->score_only) {
+        // a channel of a scale is "lite" when both of its SSIM' weights are zero; the weight cursor is dense over the scales
+        // that exist (k_finalize, cpu.rs:842-854): weight index ((c * nscales + s) * 2 + n) * 3 + map
+        static const double w108[108] = {SSIMU2_WEIGHTS108};
+        const int ns = h->geo.nscales;
+        for (int s = 0; s < ns; s++)
+            for (int c = 0; c < 3; c++) {
+                const int base = (c * ns + s) * 6;
+                if (w108[base + 0] == 0.0 && w108[base + 3] == 0.0) h->lite[s] |= (unsigned char)(1u << c);
+            }
+    }
     DeviceGuard guard(cfg->device);
     int rc = 0;
 #define CR(expr)                                  \

@@ -1659,6 +1659,10 @@ struct HvArgs {
     double* partials;
     uint32_t epoch;
     int nframes;
+    // SSIMU2_FLAG_SCORE_ONLY: per scale, the channels whose two SSIM' weights are both zero (bit c).  Their s11 / s22 /
+    // s12 filters and SSIM' map cannot change the score.  The mask 0b101 (X and B: what the weights give at scale 0, 75 % of
+    // all pixels) has its own warp-role map ("lite" strips, hv_role); any other mask runs the full kernel.
+    unsigned char lite[kMaxScales];
 };
 
 // the four column groups (16 tile columns) of one H-scan iteration: products of both rows, 16 filter steps, stores
@@ -1687,11 +1691,24 @@ constexpr int kXHUnroll = 2;     // unroll of the 16-column body of the H scan: 
 //   SP0: H0a H0b Va0 P_out    SP1: H1a H1b Va1 (idle)    SP2: H2a H2b Va2 P_state    SP3: Vb0 Vb1 Vb2 P_tma
 // plane slot of quantity q (s11, s22, s12, mu1, mu2) in the H-pass tile: planes [slot * 3 + channel]
 __host__ __device__ constexpr int hv_slot(int q) { return q == 1 ? 3 : (q == 3 ? 1 : q); }
-__device__ __forceinline__ int hv_role(int warp, int& ch, int& par)
+// Lite strips (score-only mode, X and B without SSIM'): 9 instead of 15 filtered quantities.  The H work is re-dealt over two
+// warp sets -- HA = the five quantities of Y (as in the full map), HB = mu1 / mu2 of X and of B (24 lanes) -- and the V warps
+// are placed so that no sub-partition carries more than ~1900 FP32-pipe cycles per band (full map: 2800 on three of them):
+//   SP0: HAa HAb (idle) P_out    SP1: HBa HBb (idle) (idle)    SP2: Va_Y Vb_Y (idle) P_state    SP3: Vb_X Vb_B (idle) P_tma
+__device__ __forceinline__ int hv_role(int warp, bool lite, int& ch, int& par)
 {
-    // 0 = H, 1 = Va, 2 = Vb, 3 = P_tma, 4 = P_out, 5 = idle, 6 = P_state
+    // 0 = H, 1 = Va, 2 = Vb, 3 = P_tma, 4 = P_out, 5 = idle, 6 = P_state, 7 = HB (lite strips)
     const int sp = warp & 3, row = warp >> 2;
     ch = sp; par = row;
+    if (lite) {
+        if (row == 2) return 5;
+        if (row == 3) return sp == 0 ? 4 : (sp == 1 ? 5 : (sp == 2 ? 6 : 3));
+        if (sp == 0) { ch = 1; return 0; }
+        if (sp == 1) { ch = 0; return 7; }
+        if (sp == 2) { ch = 1; par = 0; return row == 0 ? 1 : 2; }
+        ch = row == 0 ? 0 : 2; par = 0;
+        return 2;
+    }
     if (sp < 3) {
         if (row < 2) return 0;
         if (row == 2) return 1;
@@ -1721,16 +1738,21 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        s_item = (int)atomicAdd(a.ticket, 1u);
+        const int it = (int)atomicAdd(a.ticket, 1u);
+        s_item = it;
+        int sc = 0;
+        while (sc + 1 < g.nscales && it >= (g.sc[sc].item0 + g.sc[sc].n_strips) * a.nframes) sc++;
+        const bool lt = a.lite[sc] == 5;
+        // arrivals per phase: the H warps that write a tile (one per channel / per set), the V warps that read it
         for (int i = 0; i < 3; i++) {
             mbar_init(&in_full[i], 1);
             mbar_init(&in_free[i], 3);
-            mbar_init(&hb_full[i], 3);
-            mbar_init(&hb_free[i], 6);
+            mbar_init(&hb_full[i], lt ? 2 : 3);
+            mbar_init(&hb_free[i], lt ? 4 : 6);
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&hs_ready[i], 1);
-            mbar_init(&hs_free[i], 3);
+            mbar_init(&hs_free[i], lt ? 2 : 3);
         }
         bars[29] = bars[30] = bars[31] = 0;
         for (int i = 0; i < 6; i++) {
@@ -1761,8 +1783,9 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
     const int x0 = k * kXC;
     const size_t rec_base = (size_t)frame * g.total_recs + sd.rec0;   // + strip * nb + band
     const bool last_strip = (k == sd.n_strips - 1);
+    const bool lite = a.lite[s] == 5;
     int c, hpar;
-    const int role = hv_role(warp, c, hpar);
+    const int role = hv_role(warp, lite, c, hpar);
 
     if (role == 3) {
         // ===== P_tma: tile loads =====
@@ -1808,23 +1831,33 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
     }
     if (role == 5) return;
 
-    if (role == 0) {
+    if (role == 0 || role == 7) {
         // ===== H: warp = channel, lane = (quantity, row pair); lanes 30, 31 shadow lane 29 =====
+        // (HB of a lite strip: lanes 0-11 = mu1 / mu2 of X, 12-23 = mu1 / mu2 of B, lanes 24-31 shadow lane 23)
         // Lane -> (quantity q, row pair rp), chosen with the tile layouts so that every 128-bit shared-memory access of
         // the scan is conflict-free (4 wavefronts; tools/banksim.py): lanes are grouped by quantity in the order
         // s11, s12, mu1, s22, mu2; s12 and mu1 walk their row pairs in a rotated order; the planes of the output tile are
         // stored in the order s11, mu1, s12, s22, mu2 (kXSlot); the rows of ones sit at a per-channel offset.
-        const int ch = c, l = lane < 30 ? lane : 29;
-        const int qidx = l / 6, jj = l - 6 * qidx;
-        const int q = (0x41320 >> (4 * qidx)) & 7;
-        const int rp = q == 2 ? ((0x541032 >> (4 * jj)) & 7) : (q == 3 ? ((0x325410 >> (4 * jj)) & 7) : jj);
+        int ch = c, q, rp;
+        if (role == 0) {
+            const int l = lane < 30 ? lane : 29;
+            const int qidx = l / 6, jj = l - 6 * qidx;
+            q = (0x41320 >> (4 * qidx)) & 7;
+            rp = q == 2 ? ((0x541032 >> (4 * jj)) & 7) : (q == 3 ? ((0x325410 >> (4 * jj)) & 7) : jj);
+        } else {
+            const int l = lane < 24 ? lane : 23;
+            ch = l < 12 ? 0 : 2;
+            const int l12 = l < 12 ? l : l - 12;
+            q = 3 + l12 / 6;
+            rp = l12 % 6;
+        }
         const int px = (q == 1 || q == 4) ? 3 + ch : ch;
         const int py = (q == 0) ? ch : ((q == 1 || q == 2) ? 3 + ch : -1);
         const uint32_t offxA = (uint32_t)((px * kXInPlane + rp * kXInW) * 4), offxB = offxA + 6 * kXInW * 4;
         const uint32_t offyA = py < 0 ? 0u : (uint32_t)((py * kXInPlane + rp * kXInW) * 4), offyB = offyA + 6 * kXInW * 4;
         const uint32_t onesA = sbase + kXOffOnes + (ch == 1 ? 32u : 16u), onesB = sbase + kXOffOnes + (ch == 1 ? 64u : 0u);
         const uint32_t offo = (uint32_t)(((hv_slot(q) * 3 + ch) * kXHbPlane + rp * kXHbPitch) * 4);
-        const int hidx = ch * 32 + lane;
+        const int hidx = role == 0 ? ch * 32 + lane : lane;   // slot of this lane in the hand-off record (HB: 0-31, the X slots)
         for (int j = 0; j < nb; j++) {
             // every H warp walks ALL the phases of the ring barriers in order (a parity wait must never skip a phase),
             // but only scans the bands of its own parity
@@ -1906,7 +1939,16 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&hb_full[si]);
-                if (!last_strip) st_release_cta_shared(hso_done + (uint32_t)((j & 1) * 3 + ch) * 4u, (uint32_t)(j >> 1) + 1u);
+                if (!last_strip) {
+                    // progress words of the publisher: one per channel; HB stands for X and B
+                    const uint32_t w0 = hso_done + (uint32_t)((j & 1) * 3) * 4u, done = (uint32_t)(j >> 1) + 1u;
+                    if (role == 0) {
+                        st_release_cta_shared(w0 + (uint32_t)c * 4u, done);
+                    } else {
+                        st_release_cta_shared(w0, done);
+                        st_release_cta_shared(w0 + 8u, done);
+                    }
+                }
             }
         }
         return;
@@ -1939,7 +1981,8 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
 #pragma unroll 1
             for (int i4 = 0; i4 < kXR; i4 += kXSub, n++) {
                 const int p = n & 1;
-                if (n >= 2) nbar_sync(7 + 2 * c + p, 64);   // Va has read this slot's previous rows
+                const bool hand = !(lite && c != 1);        // lite strips: nobody consumes the blurred mu rows of X and B
+                if (hand && n >= 2) nbar_sync(7 + 2 * c + p, 64);   // Va has read this slot's previous rows
                 const uint32_t mus = mub + (uint32_t)p * kXMuSlotBytes;
                 // delayed-tap rows of the sub-band: previous tile rows i4 + 2 .. i4 + 5, except that for i4 = 8 the last two
                 // (band rows 10, 11) are rows 0, 1 of this band's tile.  Formed once per sub-band: the V warps are the
@@ -1957,8 +2000,10 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
                         const uint32_t a_d = (r < 2 ? d_lo : d_hi) + (uint32_t)(r * kXHbPitch * 4);
                         const f2 m1 = vstep2(stq[0], lds64(a_d), lds64(a_t));
                         const f2 m2 = vstep2(stq[1], lds64(a_d + kXMu2Off), lds64(a_t + kXMu2Off));
-                        sts64(mus + (uint32_t)(r * 2 * kXC * 4), m1);
-                        sts64(mus + (uint32_t)((r * 2 + 1) * kXC * 4), m2);
+                        if (hand) {
+                            sts64(mus + (uint32_t)(r * 2 * kXC * 4), m1);
+                            sts64(mus + (uint32_t)((r * 2 + 1) * kXC * 4), m2);
+                        }
                         const f2 fr = fifo_r[r], fd = fifo_d[r];   // XYB of output row t - 4
                         fifo_r[r] = lds64(inb + (uint32_t)(i * kXInW * 4));
                         fifo_d[r] = lds64(inb + (uint32_t)((3 * kXInPlane + i * kXInW) * 4));
@@ -1967,7 +2012,7 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
                 };
                 const int t0 = j * kXR + i4;
                 if (t0 >= 4 && t0 + kXSub <= H + 4) rows(std::false_type{}); else rows(std::true_type{});
-                nbar_arrive(1 + 2 * c + p, 64);             // rows ready for Va
+                if (hand) nbar_arrive(1 + 2 * c + p, 64);   // rows ready for Va
             }
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) acc[kk] += (double)f2_hsum(part[kk]);
@@ -2055,26 +2100,26 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
 // Msssim::score cpu.rs:728-871 (weight order [channel][scale][L1,L4][ssim,artifact,detail]).
 // One CTA per frame.
 // ------------------------------------------------------------------------------------------
-__device__ const double kWeight[108] = {
-    0.0, 0.0007376606707406586, 0.0, 0.0, 0.0007793481682867309, 0.0,
-    0.0, 0.0004371155730107379, 0.0, 1.1041726426657346, 0.00066284834129271, 0.00015231632783718752,
-    0.0, 0.0016406437456599754, 0.0, 1.8422455520539298, 11.441172603757666, 0.0,
-    0.0007989109436015163, 0.000176816438078653, 0.0, 1.8787594979546387, 10.94906990605142, 0.0,
-    0.0007289346991508072, 0.9677937080626833, 0.0, 0.00014003424285435884, 0.9981766977854967, 0.00031949755934435053,
-    0.0004550992113792063, 0.0, 0.0, 0.0013648766163243398, 0.0, 0.0,
-    0.0, 0.0, 0.0, 7.466890328078848, 0.0, 17.445833984131262,
-    0.0006235601634041466, 0.0, 0.0, 6.683678146179332, 0.00037724407979611296, 1.027889937768264,
-    225.20515300849274, 0.0, 0.0, 19.213238186143016, 0.0011401524586618361, 0.001237755635509985,
-    176.39317598450694, 0.0, 0.0, 24.43300999870476, 0.28520802612117757, 0.0004485436923833408,
-    0.0, 0.0, 0.0, 34.77906344483772, 44.835625328877896, 0.0,
-    0.0, 0.0, 0.0, 0.0, 0.0, 0.0,
-    0.0, 0.0008680556573291698, 0.0, 0.0, 0.0, 0.0,
-    0.0, 0.0005313191874358747, 0.0, 0.00016533814161379112, 0.0, 0.0,
-    0.0, 0.0, 0.0, 0.0004179171803251336, 0.0017290828234722833, 0.0,
-    0.0020827005846636437, 0.0, 0.0, 8.826982764996862, 23.19243343998926, 0.0,
-    95.1080498811086, 0.9863978034400682, 0.9834382792465353, 0.0012286405048278493, 171.2667255897307, 0.9807858872435379,
+#define SSIMU2_WEIGHTS108     0.0, 0.0007376606707406586, 0.0, 0.0, 0.0007793481682867309, 0.0, \
+    0.0, 0.0004371155730107379, 0.0, 1.1041726426657346, 0.00066284834129271, 0.00015231632783718752, \
+    0.0, 0.0016406437456599754, 0.0, 1.8422455520539298, 11.441172603757666, 0.0, \
+    0.0007989109436015163, 0.000176816438078653, 0.0, 1.8787594979546387, 10.94906990605142, 0.0, \
+    0.0007289346991508072, 0.9677937080626833, 0.0, 0.00014003424285435884, 0.9981766977854967, 0.00031949755934435053, \
+    0.0004550992113792063, 0.0, 0.0, 0.0013648766163243398, 0.0, 0.0, \
+    0.0, 0.0, 0.0, 7.466890328078848, 0.0, 17.445833984131262, \
+    0.0006235601634041466, 0.0, 0.0, 6.683678146179332, 0.00037724407979611296, 1.027889937768264, \
+    225.20515300849274, 0.0, 0.0, 19.213238186143016, 0.0011401524586618361, 0.001237755635509985, \
+    176.39317598450694, 0.0, 0.0, 24.43300999870476, 0.28520802612117757, 0.0004485436923833408, \
+    0.0, 0.0, 0.0, 34.77906344483772, 44.835625328877896, 0.0, \
+    0.0, 0.0, 0.0, 0.0, 0.0, 0.0, \
+    0.0, 0.0008680556573291698, 0.0, 0.0, 0.0, 0.0, \
+    0.0, 0.0005313191874358747, 0.0, 0.00016533814161379112, 0.0, 0.0, \
+    0.0, 0.0, 0.0, 0.0004179171803251336, 0.0017290828234722833, 0.0, \
+    0.0020827005846636437, 0.0, 0.0, 8.826982764996862, 23.19243343998926, 0.0, \
+    95.1080498811086, 0.9863978034400682, 0.9834382792465353, 0.0012286405048278493, 171.2667255897307, 0.9807858872435379, \
     0.0, 0.0, 0.0, 0.0005130064588990679, 0.0, 0.00010854057858411537,
-};
+__device__ const double kWeight[108] = {SSIMU2_WEIGHTS108};
+
 
 __global__ void __launch_bounds__(128) k_finalize(const __grid_constant__ Geo g, const double* __restrict__ partials,
                                                   double* __restrict__ norms_out, double* __restrict__ scores_ring,

@@ -434,9 +434,11 @@ def run_shard_api(args):
     assert torch.cuda.device_count() >= n, f"--shard-api needs {n} visible GPUs"
     workload = args.workload
     w, h, kind, bits, desc = WORKLOADS[workload]
-    n_pairs, n_distinct = PAIRS_PER_STEP[workload] * n, DISTINCT[workload]
     fmt = {("yuv", 8): tm.PixelFormat.NV12, ("yuv", 16): tm.PixelFormat.P016, ("srgb8", 8): tm.PixelFormat.SRGB8}[(kind, bits)]
     batch = args.batch or BATCH[workload]
+    # device frames must live on the GPU their ticket is routed to ((ticket / batch) % n): a step of a whole number of
+    # batch x n rounds keeps that routing identical from step to step
+    n_pairs, n_distinct = -(-PAIRS_PER_STEP[workload] * n // (batch * n)) * batch * n, DISTINCT[workload]
     devs = list(range(n))
     frames = {}
     pitch = ch = None

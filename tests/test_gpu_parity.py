@@ -6,6 +6,7 @@ bit (exact_math.cuh) the intermediate planes are additionally required to be IDE
 oracle's, which is what keeps the norms far inside the bar.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -638,3 +639,27 @@ def test_score_only_strip_handoff_under_load():
         s = m.get_scores(m.compute_batch(refs, diss))
     for i in range(n):
         assert s[i] == full[i % nd], (i, s[i], full[i % nd])
+
+
+def test_small_frames_follow_the_cpu_reference_scale_rule(oracle):
+    """with min(width, height) < 113 the pyramid stops early (cpu.rs:359 tests the size BEFORE each downscale) and the
+    108 weights are consumed densely over the scales that exist (cpu.rs:842-854).  The reference's GPU op always runs six
+    scales with fixed weight offsets (ssimulacra2-cuda/src/lib.rs:61-65, 586-603) and scores such frames differently; the
+    contract of this library is the CPU implementation (BASELINE.json north_star).  This pins the choice."""
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    w, h = 160, 96
+    r, d = synth.make_pair_srgb8(w, h, frame=2, seed=12)
+    so, no, nso = oracle.ssimu2_srgb8(r.numpy(), d.numpy())
+    with tm.Ssimulacra2(w, h, tm.PixelFormat.SRGB8) as m:
+        rg, dg = r.cuda(), d.cuda()
+        t = m.compute(tm.DeviceFrame.packed(rg), tm.DeviceFrame.packed(dg))
+        score, norms, info = m.get_score(t), m.get_norms(t), m.info()
+    assert info.nscales == nso == 5 and (info.width[4], info.height[4]) == (10, 6)
+    _assert_norms(norms, no, score, so)
+    # the same norms under the GPU op's fixed indexing WEIGHT[c*36 + s*6 + k] give a clearly different score
+    wts = np.load(os.path.join(os.path.dirname(__file__), "golden", "weights108.npy"))
+    v = float(np.dot(wts, np.abs(norms))) * 0.9562382616834844
+    v = 6.248496625763138e-5 * v ** 3 + 2.326765642916932 * v - 0.020884521182843837 * v * v
+    fixed = 100.0 - 10.0 * v ** 0.6276336467831387
+    assert abs(fixed - score) > 1.0, (fixed, score)

@@ -485,8 +485,13 @@ __device__ __forceinline__ void bt709_eotf_clamped_n(float (&v)[N], const exact_
 #endif
 // XYB of two pixels whose linear values are in [0, 1] (the integer formats): xyb_of on both lanes of a packed pair.
 // The fmaxf(mixed, 0) of the reference is dropped: mixed >= bias > 0 for non-negative inputs, so it never changes a bit.
-__device__ XYB_PAIR_INLINE void xyb_pair(f2 r, f2 g, f2 b, const exact_math::CbrtScale& S, f2& X, f2& Y, f2& B)
+struct Xyb2 {
+    f2 X, Y, B;
+};
+// (arguments and results by value: references would travel through local memory at the call)
+__device__ XYB_PAIR_INLINE Xyb2 xyb_pair_v(f2 r, f2 g, f2 b)
 {
+    f2 X, Y, B;
     const float K_M02 = 0.078f, K_M00 = 0.30f, K_M01 = 1.0f - K_M02 - K_M00;
     const float K_M12 = 0.078f, K_M10 = 0.23f, K_M11 = 1.0f - K_M12 - K_M10;
     const float K_M20 = 0.24342269f, K_M21 = 0.20476745f, K_M22 = 1.0f - K_M20 - K_M21;
@@ -512,7 +517,14 @@ __device__ XYB_PAIR_INLINE void xyb_pair(f2 r, f2 g, f2 b, const exact_math::Cbr
     X = f2_fma(x, f2_splat(14.0f), f2_splat(0.42f));
     Y = f2_add(y, f2_splat(0.01f));
     B = f2_add(f2_sub(bb, y), f2_splat(0.55f));
+    return Xyb2{X, Y, B};
 }
+__device__ __forceinline__ void xyb_pair(f2 r, f2 g, f2 b, const exact_math::CbrtScale&, f2& X, f2& Y, f2& B)
+{
+    const Xyb2 o = xyb_pair_v(r, g, b);
+    X = o.X; Y = o.Y; B = o.B;
+}
+
 
 __device__ __forceinline__ float lds_f32(uint32_t addr)
 {

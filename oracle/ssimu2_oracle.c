@@ -13,6 +13,13 @@
  * equal cpu.rs:20-277), the recursive-Gaussian constants (cpu.rs:931-948, re-derived from
  * ssimulacra2-cuda-kernel/build.rs:28-145), the opsin constants, WEIGHT[108], the final
  * polynomial, and "identical images -> 100.0".
+ * Independent witnesses (tests/test_oracle_independent.py, no shared code): an exact-FIR float64 model agrees
+ * on the score to <= 0.07 on the small golden cases and 0.25 at 1080p; a float32 model with the recursive
+ * filter written from the published recurrences is BIT-equal on the filter and within 0.02 on the score at
+ * every size, i.e. the gap to the f64 model is the algorithm's own f32 round-off, not a port defect.
+ * "Bit-exact" claims of the CUDA path are relative to THIS oracle built with gcc against the libm of this
+ * image (glibc 2.39, x86-64, FMA ifunc variants of powf / cbrtf): Rust's f32::cbrt / powf call the platform
+ * libm, so another platform's reference run may differ from both in the last bit of those two functions.
  *
  * What it follows (paths relative to /root/reference/crates):
  *   ssimulacra2-cuda/examples/cpu.rs                 the repository's CPU SSIMULACRA2

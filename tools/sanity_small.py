@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import turbo_metrics_b200 as tm
 from turbo_metrics_b200 import synth
-for (w, h, kind) in [(203, 131, "srgb8"), (320, 180, "nv12"), (130, 70, "p016")]:
+lite = len(sys.argv) > 1 and sys.argv[1] == "lite"     # score-only mode (its own warp-role map in k_hv)
+for (w, h, kind) in [(203, 131, "srgb8"), (320, 180, "nv12"), (130, 70, "p016"), (256, 160, "p016")]:
     if kind == "srgb8":
         r, d = synth.make_pair_srgb8(w, h, frame=1, seed=3)
         mk, fmt = tm.DeviceFrame.packed, tm.PixelFormat.SRGB8
@@ -14,6 +15,6 @@ for (w, h, kind) in [(203, 131, "srgb8"), (320, 180, "nv12"), (130, 70, "p016")]
         mk = lambda t: tm.DeviceFrame.yuv420(t, pitch, ch)
         fmt = tm.PixelFormat.NV12 if bits == 8 else tm.PixelFormat.P016
     rg, dg = r.cuda(), d.cuda()
-    with tm.Ssimulacra2(w, h, fmt, batch=3, ring=2) as m:
+    with tm.Ssimulacra2(w, h, fmt, batch=3, ring=2, score_only=lite, input_group=2) as m:
         ts = [m.compute(mk(rg), mk(dg)) for _ in range(5)]
         print(w, h, kind, [round(m.get_score(t), 6) for t in ts])

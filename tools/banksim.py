@@ -35,8 +35,8 @@ def kernel_params(path):
     kXInW = int(const("kXInW"))
     pitch = int(const("kXHbPitch"))
     plane = eval(const("kXHbPlane"), {"kXR": kXR, "kXHbPitch": pitch})
-    order = nibbles(int(re.search(r"const int q = \((0x[0-9a-fA-F]+) >> \(4 \* qidx\)\) & 7;", s).group(1), 16), 5)
-    m = re.search(r"const int rp = q == 2 \? \(\((0x[0-9a-fA-F]+) >> \(4 \* jj\)\) & 7\) : \(q == 3 \? \(\((0x[0-9a-fA-F]+) >>", s)
+    order = nibbles(int(re.search(r"(?:const int )?q = \((0x[0-9a-fA-F]+) >> \(4 \* qidx\)\) & 7;", s).group(1), 16), 5)
+    m = re.search(r"(?:const int )?rp = q == 2 \? \(\((0x[0-9a-fA-F]+) >> \(4 \* jj\)\) & 7\) : \(q == 3 \? \(\((0x[0-9a-fA-F]+) >>", s)
     rowmap = {q: list(range(6)) for q in range(5)}
     rowmap[2] = nibbles(int(m.group(1), 16), 6)
     rowmap[3] = nibbles(int(m.group(2), 16), 6)

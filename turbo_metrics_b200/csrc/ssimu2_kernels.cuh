@@ -313,15 +313,14 @@ __device__ __forceinline__ void linear_to_xyb(float r, float g, float b, const e
 __device__ __forceinline__ float box4(float a, float b, float c, float d) { return ((((0.0f + a) + b) + c) + d) * 0.25f; }
 
 // ------------------------------------------------------------------------------------------
-// k_frontend2: the same front-end (colour conversion, linear-RGB pyramid, XYB of every scale), organised so that a
-// WARP owns a 32x32 source region and needs no shared-memory pyramid:
-//   lane = a 4x4 pixel patch (8 x 4 patches per pass, two passes): levels 0, 1 and 2 of the pyramid are formed in
-//   registers; levels 3 and 4 by warp shuffles; level 5 from the two passes.  XYB of levels 0-2 is evaluated at full
-//   lane occupancy; the 16 + 4 + 1 pixels of levels 3-5 of a region share ONE evaluation.
-// YUV 4:2:0 patches are read with 64/32-bit loads (4 luma samples, 2 chroma pairs); the chroma work (g', the row
-// pointers of the exact R / B memo tables) is done once per 2x2 block; XYB rows leave as 128-bit stores.
-// Arithmetic is that of k_frontend, operation for operation (box sum order (0,0),(1,0),(0,1),(1,1), edge clamp at
-// every level, cpu.rs:545-579).
+// k_frontend2: colour conversion, linear-RGB pyramid and XYB of every scale; a WARP owns a 32x32 source region and needs no
+// shared-memory pyramid.  Two region routines:
+//   frontend_region_fast (further down): interior regions of NV12 / P016 / sRGB8 -- the hot path, see its header;
+//   frontend_region (general): every format, frame edges (clamped coordinates), P016 samples with non-zero low bits.
+//     lane = a 4x4 pixel patch (8 x 4 patches per pass, two passes): levels 0, 1 and 2 of the pyramid are formed in
+//     registers; levels 3 and 4 by warp shuffles; level 5 from the two passes; the 16 + 4 + 1 pixels of levels 3-5 of a
+//     region share ONE XYB evaluation.
+// Both follow cpu.rs:545-579 operation for operation (box sum order (0,0),(1,0),(0,1),(1,1), edge clamp at every level).
 // ------------------------------------------------------------------------------------------
 struct YuvChroma {
     float g_, r_, b_;

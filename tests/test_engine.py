@@ -70,3 +70,35 @@ def test_select_frames_hand_checked():
     assert select_frames(10, 10, Options(every=3, frames=7)) == [(0, 0), (3, 3), (6, 6)]
     assert select_frames(10, 10, Options(skip=2, skip_ref=1, frames=3)) == [(3, 2), (4, 3), (5, 4)]
     assert tm.FrameScores(ssimulacra2=1.0).ssimulacra2 == 1.0
+
+
+class _FakeSharded:
+    def __init__(self):
+        self.pairs, self.fetched_upto, self.max_inflight = [], 0, 0
+
+    def submit_host(self, refs, diss):
+        t0 = len(self.pairs)
+        self.pairs.extend(zip(refs, diss))
+        self.max_inflight = max(self.max_inflight, len(self.pairs) - self.fetched_upto)
+        return range(t0, len(self.pairs))
+
+    def get_scores(self, tickets):
+        import numpy as np
+        assert tickets.start == self.fetched_upto, "ordered fetch"
+        self.fetched_upto = tickets.stop
+        return np.array([1000.0 * a + b for a, b in self.pairs[tickets.start:tickets.stop]])
+
+    def flush(self):
+        pass
+
+
+@pytest.mark.parametrize("opt", [Options(), Options(every=3, skip=2), Options(frames=17), Options(skip=100)])
+def test_sharded_frame_loop_follows_the_same_selection(opt):
+    from turbo_metrics_b200.engine import ShardedTurboMetrics
+    eng = ShardedTurboMetrics.__new__(ShardedTurboMetrics)
+    eng.sharded, eng.chunk, eng.window = _FakeSharded(), 8, 24
+    res = eng.compute_all(range(70), range(64), opt)
+    expect = select_frames(70, 64, opt)
+    assert res.frame_count == len(expect)
+    assert (res.ssimulacra2.scores if expect else []) == [1000.0 * a + b for a, b in expect]
+    assert eng.sharded.max_inflight <= 24 + 8

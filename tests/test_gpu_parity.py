@@ -663,3 +663,26 @@ def test_small_frames_follow_the_cpu_reference_scale_rule(oracle):
     v = 6.248496625763138e-5 * v ** 3 + 2.326765642916932 * v - 0.020884521182843837 * v * v
     fixed = 100.0 - 10.0 * v ** 0.6276336467831387
     assert abs(fixed - score) > 1.0, (fixed, score)
+
+
+def test_sharded_engine_frame_loop(oracle):
+    """ShardedTurboMetrics.compute_all: the reference's frame loop with `Options`, over all GPUs from one process, equals the
+    single-GPU engine's score stream."""
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    w, h, n = 192, 128, 45
+    pairs = [synth.make_pair_yuv420(w, h, 8, frame=i, seed=71) for i in range(n)]
+    pitch, ch = pairs[0][2], pairs[0][3]
+    F = lambda t: tm.DeviceFrame.yuv420(t, pitch, ch)
+    pinned = [(r.pin_memory(), d.pin_memory()) for r, d, _, _ in pairs]
+    dev = [(r.cuda(), d.cuda()) for r, d, _, _ in pairs]
+    opt = tm.Options(every=2, skip=1, frames=40)
+    eng = tm.TurboMetrics(w, h, tm.PixelFormat.NV12, batch=4, ring=2)
+    single = eng.compute_all((F(r) for r, _ in dev), (F(d) for _, d in dev), opt)
+    eng.close()
+    sh = tm.ShardedTurboMetrics(w, h, tm.PixelFormat.NV12, devices=_shard_devices(), batch=4, ring=2)
+    multi = sh.compute_all((F(r) for r, _ in pinned), (F(d) for _, d in pinned), opt)
+    sh.close()
+    assert multi.frame_count == single.frame_count == len(tm.select_frames(n, n, opt))
+    assert multi.ssimulacra2.scores == single.ssimulacra2.scores
+    assert multi.ssimulacra2.stats == single.ssimulacra2.stats

@@ -7,10 +7,10 @@ reference's operator interface.  (The directory is spelled with an underscore be
 `turbo-metrics_b200` is not an importable Python name.)
 """
 from ._lib import SO_PATH, Ssimu2Error  # noqa: F401
-from .engine import (FrameScores, MetricAggregate, MetricsResults, Options, TurboMetrics, gather_scores, select_frames,  # noqa: F401
-                     shard_range)
+from .engine import (FrameScores, MetricAggregate, MetricsResults, Options, ShardedTurboMetrics, TurboMetrics,  # noqa: F401
+                     gather_scores, select_frames, shard_range)
 from .stats import Stats  # noqa: F401
 from .ssimulacra2 import ColorMatrix, DeviceFrame, PixelFormat, ShardedSsimulacra2, Ssimulacra2  # noqa: F401
 
-__all__ = ["Ssimulacra2", "ShardedSsimulacra2", "MetricsResults", "MetricAggregate", "PixelFormat", "ColorMatrix", "DeviceFrame", "Ssimu2Error", "SO_PATH", "TurboMetrics",
+__all__ = ["Ssimulacra2", "ShardedSsimulacra2", "MetricsResults", "MetricAggregate", "PixelFormat", "ColorMatrix", "DeviceFrame", "Ssimu2Error", "SO_PATH", "TurboMetrics", "ShardedTurboMetrics",
            "FrameScores", "Options", "select_frames", "shard_range", "gather_scores", "Stats"]

@@ -6,15 +6,17 @@ sharding the reference does not have (it is single-GPU: device 0 is hard-coded, 
   host-synchronous (the score is fetched before returning).
 * `TurboMetrics.compute_all(pairs)`       -- the frame loop of lib.rs:362-433 re-done for throughput: pairs are
   submitted ahead (batch x ring in flight) and scores are collected in submission order.
-* `shard_range / gather_scores`           -- frame pairs are independent, so N GPUs = N processes, each scoring a
-  contiguous shard; only scalar scores are exchanged (ordered gather to rank 0).  No data-path collective.
+* `ShardedTurboMetrics.compute_all(...)`   -- the same loop over ALL GPUs of the box from one process (north_star 3): host frames
+  go through `ssimu2_shard_submit_host`, the library's per-device worker threads copy and score them, one ordered score stream.
+* `shard_range / gather_scores`           -- the one-process-per-GPU form (torchrun): each rank scores a contiguous shard; only
+  scalar scores are exchanged (ordered gather to rank 0).  No data-path collective.
 """
 from __future__ import annotations
 
 from dataclasses import dataclass
 from typing import Iterable, List, Optional, Sequence, Tuple
 
-from .ssimulacra2 import ColorMatrix, DeviceFrame, PixelFormat, Ssimulacra2
+from .ssimulacra2 import ColorMatrix, DeviceFrame, PixelFormat, ShardedSsimulacra2, Ssimulacra2
 
 
 @dataclass
@@ -143,5 +145,62 @@ class TurboMetrics:
                 scores.append(self.ssimulacra2.get_score(pending.pop(0)))
         self.ssimulacra2.flush()
         scores.extend(self.ssimulacra2.get_score(t) for t in pending)
+        from .stats import Stats
+        return MetricsResults(len(scores), MetricAggregate(scores, Stats.compute(scores)) if scores else None)
+
+
+class ShardedTurboMetrics:
+    """The frame loop over every GPU of the box, one process (the reference drives device 0 only, lib.rs:438-456).  Frames are
+    HOST frames (decoded / loaded on the CPU: turbo-metrics/src/input_image.rs:206-228 copies each frame itself)."""
+
+    def __init__(self, width: int, height: int, fmt: PixelFormat, devices: Sequence[int], matrix: ColorMatrix = ColorMatrix.BT709,
+                 full_range: bool = False, batch: int = 0, ring: int = 0, score_only: bool = False):
+        self.sharded = ShardedSsimulacra2(width, height, fmt, devices, matrix, full_range, batch, ring, score_only)
+        self.chunk = max(1, (batch or 8) * len(devices))
+        self.window = self.chunk * max(2, ring or 3)
+
+    def close(self):
+        self.sharded.close()
+
+    def compute_all(self, frames_ref: Iterable[DeviceFrame], frames_dis: Iterable[DeviceFrame], opts: Optional[Options] = None) -> MetricsResults:
+        """Same `Options` semantics as `TurboMetrics.compute_all`; pairs are submitted in chunks of one batch per GPU and at most
+        `window` pairs are in flight.  Every yielded frame must own its (host) memory until its score has been collected."""
+        opts = opts or Options()
+        it_ref, it_dis = iter(frames_ref), iter(frames_dis)
+        for _ in range(opts.skip_ref + opts.skip):
+            next(it_ref, None)
+        for _ in range(opts.skip_dis + opts.skip):
+            next(it_dis, None)
+        scores: List[float] = []
+        pending: List[range] = []
+        inflight = 0
+        cr: List[DeviceFrame] = []
+        cd: List[DeviceFrame] = []
+
+        def push():
+            nonlocal inflight
+            if cr:
+                pending.append(self.sharded.submit_host(list(cr), list(cd)))
+                inflight += len(cr)
+                cr.clear(); cd.clear()
+            while inflight > self.window and pending:
+                t = pending.pop(0)
+                scores.extend(self.sharded.get_scores(t).tolist())
+                inflight -= len(t)
+        decode_count = 0
+        for fref, fdis in zip(it_ref, it_dis):
+            if opts.every > 1 and decode_count != 0 and decode_count % opts.every != 0:
+                decode_count += 1
+                continue
+            if opts.frames > 0 and decode_count >= opts.frames:
+                break
+            decode_count += 1
+            cr.append(fref); cd.append(fdis)
+            if len(cr) >= self.chunk:
+                push()
+        push()
+        self.sharded.flush()
+        for t in pending:
+            scores.extend(self.sharded.get_scores(t).tolist())
         from .stats import Stats
         return MetricsResults(len(scores), MetricAggregate(scores, Stats.compute(scores)) if scores else None)

@@ -330,7 +330,8 @@ static int launch_batch(ssimu2_handle* h, int si)
         a.partials = sl.partials;
         a.epoch = ++sl.epoch;
         a.nframes = (int)n;
-        memcpy(a.lite, h->lite, sizeof(a.lite));
+        a.lite_bits = 0;
+        for (int s = 0; s < kMaxScales; s++) a.lite_bits |= (uint32_t)(h->lite[s] & 7u) << (4 * s);
         if (timed) cudaEventRecord(sl.ev_k[2], st);
         k_hv<<<(unsigned)(g.items_v * n), kXThreads, kXSmemBytes, st>>>(g, sl.maps_x, a);
         if (timed) cudaEventRecord(sl.ev_k[3], st);

@@ -1678,7 +1678,9 @@ struct HvArgs {
     // SSIMU2_FLAG_SCORE_ONLY: per scale, the channels whose two SSIM' weights are both zero (bit c).  Their s11 / s22 /
     // s12 filters and SSIM' map cannot change the score.  The mask 0b101 (X and B: what the weights give at scale 0, 75 % of
     // all pixels) has its own warp-role map ("lite" strips, hv_role); any other mask runs the full kernel.
-    unsigned char lite[kMaxScales];
+    // (packed 4 bits per scale: a dynamically indexed array in the parameter block would be copied to local memory)
+    uint32_t lite_bits;
+    __device__ __forceinline__ uint32_t lite(int s) const { return (lite_bits >> (4 * s)) & 7u; }
 };
 
 // the four column groups (16 tile columns) of one H-scan iteration: products of both rows, 16 filter steps, stores
@@ -1758,7 +1760,7 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
         s_item = it;
         int sc = 0;
         while (sc + 1 < g.nscales && it >= (g.sc[sc].item0 + g.sc[sc].n_strips) * a.nframes) sc++;
-        const bool lt = a.lite[sc] == 5;
+        const bool lt = a.lite(sc) == 5u;
         // arrivals per phase: the H warps that write a tile (one per channel / per set), the V warps that read it
         for (int i = 0; i < 3; i++) {
             mbar_init(&in_full[i], 1);
@@ -1799,7 +1801,7 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
     const int x0 = k * kXC;
     const size_t rec_base = (size_t)frame * g.total_recs + sd.rec0;   // + strip * nb + band
     const bool last_strip = (k == sd.n_strips - 1);
-    const bool lite = a.lite[s] == 5;
+    const bool lite = a.lite(s) == 5u;
     int c, hpar;
     const int role = hv_role(warp, lite, c, hpar);
 

@@ -106,7 +106,8 @@ typedef struct {
     int32_t matrix;       /* ssimu2_matrix */
     int32_t full_range;   /* 0 = limited (what the reference implements), 1 = full */
     int32_t device;       /* CUDA device ordinal */
-    uint32_t batch;       /* frame pairs per kernel launch group (0 = default 8, at most 1024) */
+    uint32_t batch;       /* frame pairs per kernel launch group, at most 1024.  0 = chosen from the frame size: 8 at 4K, 32 at
+                             1080p, 128 for 512x512 (enough strips for ~8 waves, workspace of all ring slots <= 8 GiB) */
     uint32_t ring;        /* batches in flight, one stream each (0 = default 3) */
     uint32_t pipeline;    /* ssimu2_pipeline */
     uint32_t flags;       /* SSIMU2_FLAG_* */

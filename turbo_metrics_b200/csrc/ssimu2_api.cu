@@ -516,14 +516,23 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
     ssimu2_handle* h = new (std::nothrow) ssimu2_handle();
     if (!h) return SSIMU2_E_NOMEM;
     h->cfg = *cfg;
-    h->batch = cfg->batch ? cfg->batch : kDefaultBatch;
-    if (h->batch > (uint32_t)kMaxBatch) h->batch = kMaxBatch;
     h->ring = cfg->ring ? cfg->ring : kDefaultRing;
     if (h->ring > 16) h->ring = 16;
+    h->batch = cfg->batch ? cfg->batch : kDefaultBatch;
+    if (h->batch > (uint32_t)kMaxBatch) h->batch = kMaxBatch;
     h->input_group = cfg->input_group >= h->batch ? 0 : cfg->input_group;
     h->pipeline = (int)cfg->pipeline;
     h->score_only = (cfg->flags & SSIMU2_FLAG_SCORE_ONLY) != 0;
     build_geo(h);
+    if (cfg->batch == 0) {
+        // default batch: enough k_hv work items (64-column strips over all scales) for ~8 waves of one CTA per SM, as a power
+        // of two, while the workspace of all ring slots stays under 8 GiB (4K: 8 pairs, 1080p: 32, 512x512: 128)
+        const uint64_t per_pair = (uint64_t)h->geo.xyb_stride * 4 + (uint64_t)h->geo.total_recs * kXHsBytes;
+        uint32_t b = kDefaultBatch;
+        while (b < 256 && (uint64_t)b * h->geo.items_v < 8u * 148u) b *= 2;
+        while (b > kDefaultBatch && (uint64_t)b * h->ring * per_pair > (8ull << 30)) b /= 2;
+        h->batch = b;
+    }
     if (h->score_only) {
         // a channel of a scale is "lite" when both of its SSIM' weights are zero; the weight cursor is dense over the scales
         // that exist (k_finalize, cpu.rs:842-854): weight index ((c * nscales + s) * 2 + n) * 3 + map

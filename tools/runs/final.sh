@@ -4,7 +4,7 @@ python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 python bench.py > gpurun_out/r2_bench_4k.json 2> gpurun_out/r2_bench.err; tail -c 300 gpurun_out/r2_bench.err
 python bench.py --score-only --no-refgpu > gpurun_out/r2_bench_4k_score_only.json 2>> gpurun_out/r2_bench.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_reference.json 2>> gpurun_out/r2_bench.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 1 --no-workloads --no-cpu-baseline --no-refgpu > gpurun_out/r2_ncu_bench.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_frontend2|k_hv|k_finalize|k_build_eotf_lut|k_hpass|k_vpass' -c 400 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 1 --no-workloads --no-cpu-baseline --no-refgpu > gpurun_out/r2_ncu_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_ -s 6 -c 3 -o gpurun_out/r2_final_4k -f python tools/quick_time.py 3840 2160 16 16 1 64 16 > gpurun_out/r2_pf1.log 2>&1
 ncu --set full --clock-control none -k regex:k_ -s 6 -c 3 -o gpurun_out/r2_final_1080p -f python tools/quick_time.py 1920 1080 8 32 1 128 32 > gpurun_out/r2_pf2.log 2>&1
 python - <<'PY'

@@ -83,3 +83,25 @@ def test_no_cpu_fallback():
     with pytest.raises(Ssimu2Error) as e:   # the worker threads fail to create their handles; create reports it and joins them
         ShardedSsimulacra2(64, 64, PixelFormat.SRGB8, devices=[0, 1])
     assert e.value.status == -4
+
+
+def _build_c_client(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "ssimu2_c_client")
+    from turbo_metrics_b200 import _lib
+    libdir = os.path.dirname(_lib.SO_PATH)
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "ssimu2_c_client.c"),
+                           "-L" + libdir, "-lssimu2_b200", "-Wl,-rpath," + libdir, "-o", exe])
+    return exe
+
+
+@pytest.mark.skipif(has_gpu(), reason="only meaningful on a box without a GPU")
+def test_plain_c_client_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """The header is plain C (compiled here with gcc -Wall -Werror) and the library is self-contained: a C program that includes
+    nothing but include/ssimu2_b200.h links against it; without a GPU it reports SSIMU2_E_NODEVICE instead of computing anything."""
+    import subprocess
+    exe = _build_c_client(tmp_path)
+    z = tmp_path / "z.rgb"
+    z.write_bytes(bytes(64 * 64 * 3))
+    r = subprocess.run([exe, "64", "64", str(z), str(z)], capture_output=True, text=True)
+    assert r.returncode == 1 and "no usable CUDA device" in r.stderr and r.stdout == ""

@@ -686,3 +686,28 @@ def test_sharded_engine_frame_loop(oracle):
     assert multi.frame_count == single.frame_count == len(tm.select_frames(n, n, opt))
     assert multi.ssimulacra2.scores == single.ssimulacra2.scores
     assert multi.ssimulacra2.stats == single.ssimulacra2.stats
+
+
+def test_plain_c_client_of_the_abi(oracle, tmp_path):
+    """examples/ssimu2_c_client.c: a C program with no CUDA or Python in it scores a pair from host memory through the C ABI
+    (and, with n_devices > 1, through ssimu2_shard_* on every GPU); same score as the oracle / the Python path."""
+    import subprocess
+    from test_abi import _build_c_client
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    w, h = 320, 200
+    r, d = synth.make_pair_srgb8(w, h, frame=4, seed=19)
+    (tmp_path / "r.rgb").write_bytes(r.numpy().tobytes())
+    (tmp_path / "d.rgb").write_bytes(d.numpy().tobytes())
+    so = oracle.ssimu2_srgb8(r.numpy(), d.numpy())[0]
+    exe = _build_c_client(tmp_path)
+    out = subprocess.run([exe, str(w), str(h), str(tmp_path / "r.rgb"), str(tmp_path / "d.rgb")], capture_output=True, text=True, check=True)
+    score = float(out.stdout.strip())
+    assert abs(score - so) <= SCORE_ATOL
+    with tm.Ssimulacra2(w, h, tm.PixelFormat.SRGB8) as m:
+        rg, dg = r.cuda(), d.cuda()
+        assert m.compute_sync(tm.DeviceFrame.packed(rg), tm.DeviceFrame.packed(dg)) == score
+    n = max(2, torch.cuda.device_count())
+    if torch.cuda.device_count() >= 2:
+        out = subprocess.run([exe, str(w), str(h), str(tmp_path / "r.rgb"), str(tmp_path / "d.rgb"), str(n)], capture_output=True, text=True, check=True)
+        assert [float(x) for x in out.stdout.split()] == [score] * n

@@ -711,3 +711,33 @@ def test_plain_c_client_of_the_abi(oracle, tmp_path):
     if torch.cuda.device_count() >= 2:
         out = subprocess.run([exe, str(w), str(h), str(tmp_path / "r.rgb"), str(tmp_path / "d.rgb"), str(n)], capture_output=True, text=True, check=True)
         assert [float(x) for x in out.stdout.split()] == [score] * n
+
+
+@pytest.mark.parametrize("kind", ["nv12_random", "p016_random10", "p016_random16"])
+def test_arbitrary_sample_values(oracle, kind):
+    """Every code value, in and out of the nominal range (super-black / super-white luma, saturated chroma), not only what the
+    synthetic generator produces; `p016_random16` has non-zero low bits in the 16-bit containers, which sends every region of
+    the fast front-end path back through the general path (frontend_region_fast returns false)."""
+    tm = _tm()
+    w, h = 256, 160
+    bits = 8 if kind.startswith("nv12") else 16
+    pitch, ch = (256, 160) if bits == 8 else (512, 160)
+    rng = np.random.default_rng(3)
+
+    def frame():
+        if bits == 8:
+            return torch.from_numpy(rng.integers(0, 256, pitch * ch * 3 // 2, dtype=np.uint8))
+        v = rng.integers(0, 1024, pitch // 2 * ch * 3 // 2, dtype=np.uint16) << 6
+        if kind == "p016_random16":
+            v = rng.integers(0, 65536, v.size, dtype=np.uint16)
+        return torch.from_numpy(v.view(np.uint8).copy())
+    r = frame()
+    d = r.clone()
+    d[::7] = frame()[::7]          # a distorted copy: every 7th byte replaced
+    so, no, _ = oracle.ssimu2_yuv420(r.numpy(), d.numpy(), pitch, ch, w, h, bits)
+    fmt = tm.PixelFormat.NV12 if bits == 8 else tm.PixelFormat.P016
+    F = lambda t: tm.DeviceFrame.yuv420(t, pitch, ch)
+    with tm.Ssimulacra2(w, h, fmt, batch=2, ring=1) as m:
+        rg, dg = r.cuda(), d.cuda()
+        t = m.compute(F(rg), F(dg))
+        _assert_norms(m.get_norms(t), no, m.get_score(t), so)

@@ -229,9 +229,11 @@ def parity_block(norms_gpu, score_gpu, o_score, o_norms, what):
     return p
 
 
-def measure(c, workload, steps, warmup, batch, ring, e2e_steps, with_clocks=True):
+def measure(c, workload, steps, warmup, batch, ring, e2e_steps, with_clocks=True, score_only=None):
     """One workload on this rank's GPU: device-resident throughput, e2e from pinned host buffers + the raw H2D rate, per-kernel
-    device times (ring = 1), the first pair's score + norms.  Returns a dict (times are max over ranks)."""
+    device times (ring = 1), the first pair's score + norms.  Returns a dict (times are max over ranks).
+    e2e_steps = 0 skips the host-buffer legs (used for the score-only sub-result, whose e2e is the same PCIe-bound figure)."""
+    score_only = c.args.score_only if score_only is None else score_only
     torch, tm, synth, dist = c.torch, c.tm, c.synth, c.dist
     w, h, kind, bits, desc = WORKLOADS[workload]
     n_pairs, n_distinct = PAIRS_PER_STEP[workload], DISTINCT[workload]
@@ -255,7 +257,7 @@ def measure(c, workload, steps, warmup, batch, ring, e2e_steps, with_clocks=True
     hrefs = [mk(host_frames[i % n_host][0]) for i in range(n_pairs)]
     hdiss = [mk(host_frames[i % n_host][1]) for i in range(n_pairs)]
 
-    m = tm.Ssimulacra2(w, h, fmt, device=c.local_rank, batch=batch, ring=ring, score_only=c.args.score_only)
+    m = tm.Ssimulacra2(w, h, fmt, device=c.local_rank, batch=batch, ring=ring, score_only=score_only)
     info = m.info()
     stream = torch.cuda.current_stream()
 
@@ -309,45 +311,48 @@ def measure(c, workload, steps, warmup, batch, ring, e2e_steps, with_clocks=True
     launches = m.info().kernel_launches - l0
     value = c.world * n_pairs * steps / (ms / 1000.0)
 
+    e2e = None
     # ---- e2e: host frames through the C ABI, and the raw H2D rate of the same buffers (no kernels) for comparison
-    for _ in range(max(1, warmup // 2)):
+    for _ in range(max(1, warmup // 2) if e2e_steps else 0):
         m.get_scores(submit_host())
-    ms_e2e = timed(submit_host, e2e_steps)
-    e2e_value = c.world * n_pairs * e2e_steps / (ms_e2e / 1000.0)
-    stage = [torch.empty_like(dev_frames[0][0]) for _ in range(4)]
-    n_raw = min(n_pairs, 128)
+    stage = None
+    if e2e_steps:
+        ms_e2e = timed(submit_host, e2e_steps)
+        e2e_value = c.world * n_pairs * e2e_steps / (ms_e2e / 1000.0)
+        stage = [torch.empty_like(dev_frames[0][0]) for _ in range(4)]
+        n_raw = min(n_pairs, 128)
 
-    def raw_h2d():
-        for i in range(n_raw):
-            stage[(2 * i) % 4].copy_(host_frames[i % n_host][0], non_blocking=True)
-            stage[(2 * i + 1) % 4].copy_(host_frames[i % n_host][1], non_blocking=True)
-    raw_h2d()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream); raw_h2d(); e1.record(stream)
-    torch.cuda.synchronize()
-    raw_ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([raw_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        raw_ms = float(t.item())
-    raw_gbs = c.world * 2 * frame_bytes * n_raw / (raw_ms / 1e3) / 1e9
-    e2e = {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 2 * frame_bytes * n_pairs,
-           "d2h_bytes_per_step": 8 * n_pairs * (1 if c.args.score_only else 109), "steps": e2e_steps,
-           "h2d_gbs": e2e_value * 2 * frame_bytes / 1e9, "h2d_gbs_raw": raw_gbs,
-           "note": "ssimu2_submit_host_batch from pinned host buffers (aggregate over all ranks); h2d_gbs_raw = the same buffers "
-                   "copied with no kernels running, all ranks at once: when the two agree the limiter is the host->device path"}
+        def raw_h2d():
+            for i in range(n_raw):
+                stage[(2 * i) % 4].copy_(host_frames[i % n_host][0], non_blocking=True)
+                stage[(2 * i + 1) % 4].copy_(host_frames[i % n_host][1], non_blocking=True)
+        raw_h2d()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); raw_h2d(); e1.record(stream)
+        torch.cuda.synchronize()
+        raw_ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([raw_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            raw_ms = float(t.item())
+        raw_gbs = c.world * 2 * frame_bytes * n_raw / (raw_ms / 1e3) / 1e9
+        e2e = {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 2 * frame_bytes * n_pairs,
+               "d2h_bytes_per_step": 8 * n_pairs * (1 if score_only else 109), "steps": e2e_steps,
+               "h2d_gbs": e2e_value * 2 * frame_bytes / 1e9, "h2d_gbs_raw": raw_gbs,
+               "note": "ssimu2_submit_host_batch from pinned host buffers (aggregate over all ranks); h2d_gbs_raw = the same buffers "
+                       "copied with no kernels running, all ranks at once: when the two agree the limiter is the host->device path"}
 
     # ---- score + norms of the first pair of the sequence (for the parity block)
     ts_chk = submit_device()
     sc = m.get_scores(ts_chk)
     s_first, s_last = float(sc[0]), float(sc[-1])
     assert 0.0 < s_first <= 100.0 and 0.0 < s_last <= 100.0, (s_first, s_last)
-    norms_first = None if c.args.score_only else m.get_norms(ts_chk[0])
+    norms_first = None if score_only else m.get_norms(ts_chk[0])
     m.close()
 
     # ---- per-kernel device time without cross-stream overlap: same batch size, ring = 1
-    m1 = tm.Ssimulacra2(w, h, fmt, device=c.local_rank, batch=batch, ring=1, score_only=c.args.score_only)
+    m1 = tm.Ssimulacra2(w, h, fmt, device=c.local_rank, batch=batch, ring=1, score_only=score_only)
     for _ in range(2):
         m1.get_scores(m1.compute_batch(refs[:2 * batch], diss[:2 * batch], stream))
     m1.kernel_ms(reset=True)
@@ -523,6 +528,12 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_workloads and workload == "4k":
         for wl in ("1080p", "512", "1080p_srgb8"):
             subs[wl] = measure(c, wl, 3, 3, BATCH[wl], args.ring, 2, with_clocks=True)
+    # ---- the same workload with SSIMU2_FLAG_SCORE_ONLY (the reference's API returns the score only; the flag drops the
+    # filters and maps whose weights are zero): device-resident throughput, and the score must have the same BITS
+    somode = None
+    if not args.score_only and not args.no_workloads:
+        somode = measure(c, workload, 3, 3, batch, args.ring, 0, with_clocks=False, score_only=True)
+        assert somode["s_first"] == r["s_first"] and somode["s_last"] == r["s_last"], "score-only mode changed a score"
     if rank != 0:
         return
 
@@ -610,6 +621,13 @@ def run_ours(args, rank, world, local_rank):
         "cpu_baseline": cpu,
         "parity": parity,
         "workloads": workloads,
+        "score_only_mode": None if somode is None else {
+            "value": somode["value"], "unit": "pairs/s", "ms_per_step": somode["ms"] / somode["steps"], "steps": somode["steps"], "warmup": somode["warmup"],
+            "roofline_frac": roofline_block(c, somode)["frac"],
+            "kernel_ms_per_launch": {k: v["ms_per_launch"] for k, v in roofline_block(c, somode)["kernels"].items()},
+            "scores_bit_equal_to_full_mode": True,
+            "note": "same workload and timed loop as `value` with ssimu2_config.flags = SSIMU2_FLAG_SCORE_ONLY: the 54 zero-weight norms "
+                    "are not computed (no ssimu2_get_norms); the run asserts the first and last score equal the full mode's bit for bit"},
         "gpu_reference_design": refdesign,
         "timing": r["timing"],
         "scores": {"first": r["s_first"], "last": r["s_last"]},

@@ -3,6 +3,9 @@ import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import turbo_metrics_b200 as tm
+if os.environ.get('SSIMU2_SO'):   # development aid: time another build of the library
+    import turbo_metrics_b200._lib as _l
+    _l.SO_PATH = os.path.abspath(os.environ['SSIMU2_SO'])
 from turbo_metrics_b200 import synth
 
 w, h, bits = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])

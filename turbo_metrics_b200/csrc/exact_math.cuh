@@ -67,12 +67,13 @@ struct Consts {
     double A0, A1, A2, A3, A4;     // powf log2 polynomial
     double C0, C1, C2;             // powf exp2 polynomial
     double shift, minus_one, one;
+    uint32_t mant20, pad;          // 0x000fffff: as a constant-bank operand, (a & mant20) | imm is ONE LOP3 (two immediates are two)
 };
 #define EM_CONSTS_INIT                                                                                        \
     {0x1.8832490c2feddp-3, 0x1.6527f4927f555p-1, 0x1.f87bc378ed415p-2,                                        \
      0x1.27616c9496e0bp-2, -0x1.71969a075c67ap-2, 0x1.ec70a6ca7baddp-2, -0x1.7154748bef6c8p-1,                \
      0x1.71547652ab82bp+0, 0x1.c6af84b912394p-5, 0x1.ebfce50fac4f3p-3, 0x1.62e42ff0c52d6p-1, 0x1.8p+47, -1.0, \
-     1.0}
+     1.0, 0x000fffffu, 0u}
 
 EM_HD uint32_t f2u(float f)
 {
@@ -227,7 +228,8 @@ EM_HD float cbrtf_glibc(float x, const Consts& K, const CbrtScale* S = nullptr)
     // (on the device: one LOP3 + one exact F2F instead of assembling the double from the mantissa bits)
 #if defined(__CUDA_ARCH__)
     // hi = 0x3fe00000 | (m >> 3), lo = m << 29: the double of xm straight from the mantissa bits (no F2F, see widen_pos_normal)
-    const double xm = __hiloint2double((int)(((ix >> 3) & 0x000fffffu) | 0x3fe00000u), (int)(ix << 29));
+    // (mask + one shift-add: the mantissa field and the exponent constant do not overlap, so + is |)
+    const double xm = __hiloint2double((int)(((ix & 0x007fffffu) >> 3) + 0x3fe00000u), (int)(ix << 29));
 #else
     const uint32_t m = ix & 0x007fffffu;
     const double xm = u2d(((uint64_t)(0x3fe00000u | (m >> 3)) << 32) | (uint64_t)(m << 29));
@@ -316,10 +318,11 @@ __device__ __forceinline__ void cbrtf_glibc_n(float (&x)[N], const Consts& K, co
     uint32_t ix[N];
     double xm[N], t[N], t2d[N], ud[N], num[N], den[N], y[N], e[N], q[N], f[N];
     float u[N], t2[N];
+    const uint32_t mant = K.mant20;
 #pragma unroll
     for (int i = 0; i < N; i++) {
         ix[i] = f2u(x[i]);
-        xm[i] = __hiloint2double((int)(((ix[i] >> 3) & 0x000fffffu) | 0x3fe00000u), (int)(ix[i] << 29));
+        xm[i] = __hiloint2double((int)(((ix[i] >> 3) & mant) | 0x3fe00000u), (int)(ix[i] << 29));
     }
 #pragma unroll
     for (int i = 0; i < N; i++) t[i] = K.cb2 * xm[i];

@@ -906,6 +906,12 @@ int ssimu2_debug_read(ssimu2_t* h, uint64_t ticket, int what, int scale, float* 
     return SSIMU2_OK;
 }
 
+#ifdef KX_TRACE
+extern "C" int ssimu2_debug_hv_trace(unsigned long long* out)
+{
+    return (int)cudaMemcpyFromSymbol(out, ssimu2::g_hv_trace, sizeof(ssimu2::g_hv_trace));
+}
+#endif
 int ssimu2_debug_math(int op, const float* in, float y, float* out, size_t n)
 {
     if (!in || !out || op < 0 || op > 6) return SSIMU2_E_INVALID;

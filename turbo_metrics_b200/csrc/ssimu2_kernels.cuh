@@ -1701,6 +1701,20 @@ __device__ __forceinline__ void h_products(const HGroupLoad& L, f2 (&w)[16], int
     w[(at + 3) & 15] = f2_pack(L.xa.w * L.ya.w, L.xb.w * L.yb.w);
 }
 
+#ifdef KX_TRACE
+// Timing trace of ONE work item (development aid, compiled out of the shipped build; results are unaffected):
+// [warp][band - KX_TRACE_J0][event] SM clocks, read back by tools/hv_trace.py through ssimu2_debug_hv_trace.
+#ifndef KX_TRACE_ITEM
+#define KX_TRACE_ITEM 485
+#endif
+#ifndef KX_TRACE_J0
+#define KX_TRACE_J0 60
+#endif
+__device__ unsigned long long g_hv_trace[16][32][12];
+#define KX_TR(ev) do { if (tr_on && lane == 0 && j >= KX_TRACE_J0 && j < KX_TRACE_J0 + 32) g_hv_trace[warp][j - KX_TRACE_J0][ev] = (unsigned long long)clock64(); } while (0)
+#else
+#define KX_TR(ev) do { } while (0)
+#endif
 constexpr int kXMaxNReg = 128;   // 16 warps x 128 registers = the whole register file
 constexpr int kXHUnroll = 2;     // unroll of the 16-column body of the H scan: 2 halves the loop-carried register moves (-1.3 %); 4 overflows the instruction cache (+1.7 %)
 // Warp roles (16 warps).  The scheduler sub-partition of a warp is (warp id % 4).  Per 12-row band an H warp needs
@@ -1796,6 +1810,9 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
         item -= g.sc[s].item0 * nf;
     }
     const int k = item / a.nframes, frame = item - k * a.nframes;
+#ifdef KX_TRACE
+    const bool tr_on = s_item == KX_TRACE_ITEM;
+#endif
     const ScaleDesc sd = g.sc[s];
     const int W = sd.w, H = sd.h, nb = sd.nb;
     const int x0 = k * kXC;
@@ -1814,6 +1831,7 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
             if (j >= kXNIn) mbar_wait_wd(&in_free[si], (uint32_t)((j / kXNIn - 1) & 1));
             mbar_expect_tx(&in_full[si], kXInBytes);
             tma_load_4d(xs + kXOffIn + si * kXInBytes, map, &in_full[si], x0 - kXInLead, j * kXR, 0, frame);
+            KX_TR(0);
         }
         return;
     }
@@ -1882,6 +1900,7 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
             const int si = j % 3, sin = j % kXNIn;
             const bool mine = (j & 1) == hpar;
             mbar_wait_wd(&in_full[sin], (uint32_t)((j / kXNIn) & 1));
+            if (mine) KX_TR(0);
             HState2 st;
             if (mine) {
                 if (k > 0) {
@@ -1920,7 +1939,9 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
                 }
             }
             HGroupLoad nxt = h_load(axA, axB, ayA, ayB, 48);
+            KX_TR(1);
             if (j >= 2) mbar_wait_wd(&hb_free[si], (uint32_t)(((j - 2) / 3) & 1));
+            KX_TR(2);
             uint32_t axI = axA, ayI = ayA, ayIB = ayB;
 #pragma unroll kXHUnroll
             for (int it = 0; it < 4; it++, axI += 64, ayI += 64, ayIB += 64) {
@@ -1955,6 +1976,7 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
                 __stcg(rec + 3 * 96, st.pp1.v); __stcg(rec + 4 * 96, st.pp3.v); __stcg(rec + 5 * 96, st.pp5.v);
             }
             __syncwarp();
+            KX_TR(3);
             if (lane == 0) {
                 mbar_arrive(&hb_full[si]);
                 if (!last_strip) {
@@ -1992,6 +2014,7 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
             const int si = j % 3, sp = (j + 2) % 3;
             mbar_wait_wd(&hb_full[si], (uint32_t)((j / 3) & 1));
             mbar_wait_wd(&in_full[si], (uint32_t)((j / 3) & 1));
+            KX_TR(0);
             const uint32_t cur = sbase + kXOffHb + si * kXHbBytes + lane8 + (uint32_t)((hv_slot(3) * 3 + c) * kXHbPlane * 4);
             const uint32_t prv = sbase + kXOffHb + sp * kXHbBytes + lane8 + (uint32_t)((hv_slot(3) * 3 + c) * kXHbPlane * 4);
             const uint32_t inb = sbase + kXOffIn + si * kXInBytes + kXInLead * 4 + lane8 + (uint32_t)(c * kXInPlane * 4);
@@ -2000,7 +2023,9 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
             for (int i4 = 0; i4 < kXR; i4 += kXSub, n++) {
                 const int p = n & 1;
                 const bool hand = !(lite && c != 1);        // lite strips: nobody consumes the blurred mu rows of X and B
+                KX_TR(2 + i4 / 4 * 3);
                 if (hand && n >= 2) nbar_sync(7 + 2 * c + p, 64);   // Va has read this slot's previous rows
+                KX_TR(3 + i4 / 4 * 3);
                 const uint32_t mus = mub + (uint32_t)p * kXMuSlotBytes;
                 // delayed-tap rows of the sub-band: previous tile rows i4 + 2 .. i4 + 5, except that for i4 = 8 the last two
                 // (band rows 10, 11) are rows 0, 1 of this band's tile.  Formed once per sub-band: the V warps are the
@@ -2030,11 +2055,13 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
                 };
                 const int t0 = j * kXR + i4;
                 if (t0 >= 4 && t0 + kXSub <= H + 4) rows(std::false_type{}); else rows(std::true_type{});
+                KX_TR(4 + i4 / 4 * 3);
                 if (hand) nbar_arrive(1 + 2 * c + p, 64);   // rows ready for Va
             }
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) acc[kk] += (double)f2_hsum(part[kk]);
             __syncwarp();
+            KX_TR(1);
             if (lane == 0) {
                 mbar_arrive(&in_free[si]);
                 mbar_arrive(&hb_free[sp]);   // the previous band's tile goes back to the H warps
@@ -2059,6 +2086,7 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
     for (int j = 0; j < nb; j++) {
         const int si = j % 3, sp = (j + 2) % 3;
         mbar_wait_wd(&hb_full[si], (uint32_t)((j / 3) & 1));
+        KX_TR(0);
         const uint32_t cur = sbase + kXOffHb + si * kXHbBytes + lane8 + (uint32_t)(c * kXHbPlane * 4);
         const uint32_t prv = sbase + kXOffHb + sp * kXHbBytes + lane8 + (uint32_t)(c * kXHbPlane * 4);
         f2 part[2] = {zero2, zero2};
@@ -2086,7 +2114,9 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&hb_free[sp]);
             }
+            KX_TR(2 + i4 / 4 * 3);
             nbar_sync(1 + 2 * c + p, 64);
+            KX_TR(3 + i4 / 4 * 3);
             const uint32_t mus = mub + (uint32_t)p * kXMuSlotBytes;
             auto maps = [&](auto checked) {
 #pragma unroll
@@ -2098,10 +2128,12 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
             };
             const int t0 = j * kXR + i4;
             if (t0 >= 4 && t0 + kXSub <= H + 4) maps(std::false_type{}); else maps(std::true_type{});
+            KX_TR(4 + i4 / 4 * 3);
             if (n + 2 < nsub) nbar_arrive(7 + 2 * c + p, 64);   // Vb waits for it before it reuses the slot (never after the last use)
         }
         acc[0] += (double)f2_hsum(part[0]);
         acc[1] += (double)f2_hsum(part[1]);
+        KX_TR(1);
     }
 #pragma unroll
     for (int kk = 0; kk < 2; kk++) {

@@ -81,7 +81,8 @@ typedef enum { SSIMU2_MATRIX_BT709 = 0, SSIMU2_MATRIX_BT601_525 = 1, SSIMU2_MATR
 
 /* One device frame.  YUV 4:2:0: plane[0] = Y, plane[1] = interleaved CbCr
  * (NVDEC: plane[1] = plane[0] + pitch * coded_height, cudarse-video/src/dec.rs:299-366),
- * both with the same pitch.  Packed RGB formats use plane[0] only.  pitch is in bytes. */
+ * both with the same pitch.  Packed RGB formats use plane[0] only.  pitch is in bytes and must hold one row
+ * (width x 1 / 2 bytes for NV12 / P016, width x 3 / 6 / 12 bytes for the packed formats): SSIMU2_E_INVALID otherwise. */
 typedef struct {
     uint64_t plane[2];
     uint32_t pitch;

@@ -423,6 +423,9 @@ static bool frame_ok(const ssimu2_handle* h, const ssimu2_frame* f)
 {
     if (!f || !f->plane[0] || f->pitch == 0) return false;
     if ((h->cfg.format == kNV12 || h->cfg.format == kP016) && !f->plane[1]) return false;
+    // a row must fit in the pitch (rows that overlap would be read as garbage, and past the end of the last one)
+    static const uint32_t bytes_per_px[] = {1, 2, 3, 6, 12, 12};   // NV12 / P016: per luma sample; packed RGB: per pixel
+    if ((uint64_t)f->pitch < (uint64_t)h->cfg.width * bytes_per_px[h->cfg.format]) return false;
     return true;
 }
 

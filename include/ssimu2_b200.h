@@ -163,7 +163,10 @@ int ssimu2_stream_wait_input(ssimu2_t *h, uint64_t ticket, void *stream);
  * HOST memory with the same layout an ssimu2_frame describes (plane[] are host addresses;
  * for YUV plane[1] must lie inside the same allocation as plane[0], after it).  The library
  * copies them to its own device staging ring (pinned memory is faster but not required) and
- * enqueues the pair.  frame_bytes = bytes to copy starting at plane[0]. */
+ * enqueues the pair.  frame_bytes = bytes to copy starting at plane[0].
+ * Lifetime: a PAGEABLE buffer has been read when the call returns (the CUDA runtime stages it) and may be reused at once,
+ * like the slices of the reference's call; a PINNED buffer is read asynchronously by the copy engine: keep it unmodified
+ * until the pair's score has been fetched or ssimu2_completed() has passed its ticket. */
 int ssimu2_submit_host(ssimu2_t *h, const ssimu2_frame *ref, const ssimu2_frame *dis, size_t frame_bytes,
                        uint64_t *ticket);
 /* n host pairs at once (all frames share frame_bytes); pair i has *first_ticket + i.  The frame loop of a caller that

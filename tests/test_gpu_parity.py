@@ -308,6 +308,27 @@ def test_host_frames_entry_point(oracle):
     assert all(s == scores[0] for s in scores)
 
 
+def test_host_frames_in_pageable_memory_can_be_reused_at_once(oracle):
+    """`compute_from_cpu_srgb_sync` takes ordinary slices (lib.rs:232-250): host frames need not be pinned, and a pageable buffer
+    has been consumed when submit returns -- the caller's frame loop may decode the next frame into the same buffer."""
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    w, h = 512, 288
+    pairs = [synth.make_pair_srgb8(w, h, frame=i, seed=9) for i in range(4)]
+    want = [oracle.ssimu2_srgb8(r.numpy(), d.numpy())[0] for r, d in pairs]
+    buf_r, buf_d = torch.empty_like(pairs[0][0]), torch.empty_like(pairs[0][1])
+    assert not buf_r.is_pinned() and not buf_d.is_pinned()
+    with tm.Ssimulacra2(w, h, tm.PixelFormat.SRGB8, batch=4, ring=2) as m:
+        ts = []
+        for r, d in pairs:
+            buf_r.copy_(r); buf_d.copy_(d)
+            ts.append(m.compute_from_cpu(tm.DeviceFrame.packed(buf_r), tm.DeviceFrame.packed(buf_d)))
+            buf_r.zero_(); buf_d.fill_(255)        # clobber the buffers right after submit
+        got = [m.get_score(t) for t in ts]
+    assert len(set(np.round(want, 3))) == 4          # four different pairs: a mixed-up or clobbered frame would show
+    np.testing.assert_allclose(got, want, rtol=0, atol=SCORE_ATOL)
+
+
 def test_caller_stream_ordering(oracle):
     """Frames produced on the caller's stream right before submit are seen by the scorer."""
     tm = _tm()

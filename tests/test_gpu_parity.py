@@ -143,6 +143,45 @@ def test_intermediate_planes_are_bit_identical_srgb8(oracle, w, h):
     _assert_norms(norms, no, score, so)
 
 
+@pytest.mark.parametrize("kind", ["linear", "linear_out_of_range", "linear_huge", "srgb16"])
+def test_intermediate_planes_are_bit_identical_packed16_and_float(oracle, kind):
+    """The fast front-end path of the linear-f32 (the reference's own `Ssimulacra2::new` input, lib.rs:48) and sRGB16 formats:
+    interior regions go through it, the frame edge through the general path, and both must give the oracle's bits.  The
+    out-of-range variants plant negative, -0, > 1, subnormal (and, `linear_huge`, > 1e30 and nan) samples: the regions the unchecked
+    cube root cannot take must fall back to the general path, everything must still be bit-identical (for `linear_huge` the
+    sums overflow in the oracle too, so only the planes are compared)."""
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    w, h = 200, 136
+    if kind == "srgb16":
+        r8, d8 = synth.make_pair_srgb8(w, h, frame=4, seed=6)
+        r = (r8.to(torch.int32) * 257 + 3).clamp(0, 65535).to(torch.int16)
+        d = (d8.to(torch.int32) * 257 + 40).clamp(0, 65535).to(torch.int16)
+        a = oracle.linear_from_srgb16(r.numpy().view(np.uint16))
+        b = oracle.linear_from_srgb16(d.numpy().view(np.uint16))
+        fmt = tm.PixelFormat.SRGB16
+    else:
+        r, d = synth.make_pair_linearf32(w, h, frame=4, seed=6)
+        if kind != "linear":
+            r, d = r.clone(), d.clone()
+            r[40, 50, 1] = -0.25; r[41, 90, 0] = 1.75; r[70, 10, 2] = -0.0; d[12, 150, 1] = 1.0e-42; d[90, 40, 2] = 7.5
+            if kind == "linear_huge":
+                d[100, 120, 0] = 3.0e30; r[100, 30, 1] = float("nan")
+        a, b = oracle.linear_from_linearf32(r.numpy()), oracle.linear_from_linearf32(d.numpy())
+        fmt = tm.PixelFormat.LINEARF32
+    with tm.Ssimulacra2(w, h, fmt, batch=1, ring=1, pipeline="split") as m:
+        rg, dg = r.cuda(), d.cuda()
+        t = m.compute(tm.DeviceFrame.packed(rg), tm.DeviceFrame.packed(dg))
+        score, norms, ns = m.get_score(t), m.get_norms(t), m.info().nscales
+        xyb_o, hb_o = _oracle_stages(oracle, a, b, ns)
+        for s in range(ns):
+            assert np.array_equal(_bits(m.debug_read(t, 0, s)), _bits(xyb_o[s])), f"XYB planes differ at scale {s}"
+            assert np.array_equal(_bits(m.debug_read(t, 1, s)), _bits(hb_o[s])), f"H-pass planes differ at scale {s}"
+    if kind != "linear_huge":
+        so, no, _ = oracle.ssimu2_linear_planar(a, b)
+        _assert_norms(norms, no, score, so)
+
+
 @pytest.mark.parametrize("bits", [8, 16])
 def test_intermediate_planes_are_bit_identical_yuv(oracle, bits):
     tm = _tm()

@@ -591,6 +591,18 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
         h->geo.lut_shift = shift;
         h->device_bytes += bytes;
     }
+    if (cfg->format == kSRGB16) {
+        // exact memo of the sRGB16 transfer function: one gather per sample instead of one powf
+        const size_t bytes = (size_t)65536 * sizeof(float);
+        CR(cudaMalloc(&h->eotf_lut, bytes));
+        k_build_srgb16_lut<<<65536 / 256, 256>>>(h->eotf_lut);
+        CR(cudaGetLastError());
+        CR(cudaDeviceSynchronize());
+        h->geo.eotf_lut = h->eotf_lut;
+        h->geo.lut_n = 65536;
+        h->geo.lut_shift = 0;
+        h->device_bytes += bytes;
+    }
     for (uint32_t i = 0; i < h->ring; i++) {
         Slot& sl = h->slots[i];
         const Geo& g = h->geo;

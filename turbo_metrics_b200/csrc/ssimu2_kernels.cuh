@@ -257,9 +257,14 @@ __device__ __forceinline__ void load_px(const FrameIn& f, int x, int y, const Yu
         b = kSrgb8Lut[__ldg(p + 2)];
     } else if constexpr (FMT == kSRGB16) {
         const uint16_t* p = reinterpret_cast<const uint16_t*>(f.p0 + (size_t)y * f.pitch) + 3 * x;
-        r = srgb_inverse_oetf<false>((float)__ldg(p) / 65535.0f, T);
-        g = srgb_inverse_oetf<false>((float)__ldg(p + 1) / 65535.0f, T);
-        b = srgb_inverse_oetf<false>((float)__ldg(p + 2) / 65535.0f, T);
+        if (lut != nullptr) {
+            // exact memo by code (k_build_srgb16_lut: the same expression, evaluated once per code at create time)
+            r = __ldg(lut + __ldg(p)); g = __ldg(lut + __ldg(p + 1)); b = __ldg(lut + __ldg(p + 2));
+        } else {
+            r = srgb_inverse_oetf<false>((float)__ldg(p) / 65535.0f, T);
+            g = srgb_inverse_oetf<false>((float)__ldg(p + 1) / 65535.0f, T);
+            b = srgb_inverse_oetf<false>((float)__ldg(p + 2) / 65535.0f, T);
+        }
     } else {
         const float* p = reinterpret_cast<const float*>(f.p0 + (size_t)y * f.pitch) + 3 * x;
         r = __ldg(p); g = __ldg(p + 1); b = __ldg(p + 2);
@@ -534,12 +539,17 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
 
 template <int FMT>
 struct FastFmt {
-    static constexpr bool ok = (FMT == kNV12 || FMT == kP016 || FMT == kSRGB8);
+    static constexpr bool ok = (FMT == kNV12 || FMT == kP016 || FMT == kSRGB8 || FMT == kSRGB16 || FMT == kLINEARF32);
+    static constexpr bool yuv = (FMT == kNV12 || FMT == kP016);
+    // bytes per sample of plane 0 (YUV: luma sample; packed formats: pixel), alignment the row loads need (mask)
+    static constexpr int bpp = FMT == kP016 ? 2 : (FMT == kNV12 ? 1 : (FMT == kSRGB8 ? 3 : (FMT == kSRGB16 ? 6 : 12)));
+    static constexpr uint32_t align = FMT == kP016 || FMT == kSRGB16 ? 7u : (FMT == kLINEARF32 ? 15u : 3u);
+    static constexpr bool needs_lut = yuv || FMT == kSRGB16;
 };
 
 // the raw words of one row of four pixels (P016: 2 words, NV12: 1, sRGB8: 3) / of the two chroma samples under them
 struct RowWords {
-    uint32_t w0, w1, w2;
+    uint32_t w0, w1, w2, w3, w4, w5, w6, w7, w8, w9, w10, w11;   // sRGB16 uses six, linear f32 all twelve
 };
 // `asm volatile` on purpose: the compiler sinks an ordinary load to just above its first use, which puts the whole DRAM
 // latency in front of the warp; a volatile asm keeps its place among the stores of the rows, i.e. where it was written --
@@ -547,8 +557,16 @@ struct RowWords {
 template <int FMT>
 __device__ __forceinline__ RowWords load_row_words(const uint8_t* p)
 {
-    RowWords r{0, 0, 0};
-    if constexpr (FMT == kP016) {
+    RowWords r{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if constexpr (FMT == kSRGB16) {
+        asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.w0), "=r"(r.w1) : "l"(p));
+        asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2+8];" : "=r"(r.w2), "=r"(r.w3) : "l"(p));
+        asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2+16];" : "=r"(r.w4), "=r"(r.w5) : "l"(p));
+    } else if constexpr (FMT == kLINEARF32) {
+        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.w0), "=r"(r.w1), "=r"(r.w2), "=r"(r.w3) : "l"(p));
+        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(r.w4), "=r"(r.w5), "=r"(r.w6), "=r"(r.w7) : "l"(p));
+        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4+32];" : "=r"(r.w8), "=r"(r.w9), "=r"(r.w10), "=r"(r.w11) : "l"(p));
+    } else if constexpr (FMT == kP016) {
         asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.w0), "=r"(r.w1) : "l"(p));
     } else if constexpr (FMT == kNV12) {
         asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r.w0) : "l"(p));
@@ -568,11 +586,11 @@ __device__ __forceinline__ void prefetch_region(const FrameIn& f, int X0, int Y0
 {
     const int lane = threadIdx.x & 31;
     const int x = X0 + 4 * (lane & 7), y0 = Y0 + 8 * (lane >> 3);
-    constexpr int kBpp = FMT == kP016 ? 2 : (FMT == kNV12 ? 1 : 3);
+    constexpr int kBpp = FastFmt<FMT>::bpp;
     const uint8_t* pY = f.p0 + (size_t)y0 * f.pitch + (size_t)(x * kBpp);
 #pragma unroll
     for (int r = 0; r < 8; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pY + (size_t)r * f.pitch));
-    if constexpr (FMT != kSRGB8) {
+    if constexpr (FastFmt<FMT>::yuv) {
         const uint8_t* pC = f.p1 + (size_t)(y0 >> 1) * f.pitch + (size_t)(x * kBpp);
 #pragma unroll
         for (int r = 0; r < 4; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pC + (size_t)r * f.pitch));
@@ -605,7 +623,8 @@ __device__ __forceinline__ bool frontend_region_fast(const Geo& g, const FrameIn
     uint32_t o0 = (uint32_t)y0 * pitch0 + (uint32_t)x;
     uint32_t o1 = (uint32_t)(y0 >> 1) * pitch1 + (uint32_t)(x >> 1);
     const uint32_t o2 = (uint32_t)(y0 >> 2) * pitch2 + (uint32_t)(x >> 2);
-    constexpr int kBpp = FMT == kP016 ? 2 : (FMT == kNV12 ? 1 : 3);
+    constexpr int kBpp = FastFmt<FMT>::bpp;
+    constexpr bool kYuv = FastFmt<FMT>::yuv;
     uint32_t oY = (uint32_t)y0 * f.pitch + (uint32_t)(x * kBpp);
     uint32_t oC = (uint32_t)(y0 >> 1) * f.pitch + (uint32_t)(x * kBpp);
     const char* lut = reinterpret_cast<const char*>(g.eotf_lut);
@@ -617,9 +636,9 @@ __device__ __forceinline__ bool frontend_region_fast(const Geo& g, const FrameIn
 
     // The raw samples are fetched one step ahead (the second row of a pair at the top of the pair, the next pair's chroma
     // and first row in its middle): a load that is consumed right away exposes the full DRAM latency to the warp.
-    RowWords wy_next = load_row_words<FMT>(f.p0 + oY), wc_next{0, 0, 0};
+    RowWords wy_next = load_row_words<FMT>(f.p0 + oY), wc_next{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     oY += f.pitch;
-    if constexpr (FMT != kSRGB8) {
+    if constexpr (kYuv) {
         wc_next = load_row_words<FMT>(f.p1 + oC);
         oC += f.pitch;
     }
@@ -658,7 +677,7 @@ __device__ __forceinline__ bool frontend_region_fast(const Geo& g, const FrameIn
                 // next pair: chroma + first row
                 wy_next = load_row_words<FMT>(f.p0 + oY);
                 oY += f.pitch;
-                if constexpr (FMT != kSRGB8) {
+                if constexpr (kYuv) {
                     wc_next = load_row_words<FMT>(f.p1 + oC);
                     oC += f.pitch;
                 }
@@ -672,12 +691,34 @@ __device__ __forceinline__ bool frontend_region_fast(const Geo& g, const FrameIn
             } else if constexpr (FMT == kNV12) {
                 yc[0] = (wy.w0 << 2) & 0x3FCu; yc[1] = (wy.w0 >> 6) & 0x3FCu; yc[2] = (wy.w0 >> 14) & 0x3FCu; yc[3] = (wy.w0 >> 22) & 0x3FCu;
             }
-            if constexpr (FMT != kSRGB8) {
+            if constexpr (kYuv) {
                 // the exact R / B memo: all eight gathers of the row are issued before the first transfer-function chain
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     lr[i] = __ldg(reinterpret_cast<const float*>(lut + (roff[i >> 1] + yc[i])));
                     lb[i] = __ldg(reinterpret_cast<const float*>(lut + (boff[i >> 1] + yc[i])));
+                }
+            } else if constexpr (FMT == kSRGB16) {
+                // u16 codes R0 G0 | B0 R1 | G1 B1 | R2 G2 | B2 R3 | G3 B3 -> the exact transfer memo (one gather per code)
+                const float* t16 = g.eotf_lut;
+                auto lo = [&](uint32_t w) { return __ldg(t16 + (w & 0xFFFFu)); };
+                auto hi = [&](uint32_t w) { return __ldg(t16 + (w >> 16)); };
+                lr[0] = lo(wy.w0); lg[0] = hi(wy.w0); lb[0] = lo(wy.w1);
+                lr[1] = hi(wy.w1); lg[1] = lo(wy.w2); lb[1] = hi(wy.w2);
+                lr[2] = lo(wy.w3); lg[2] = hi(wy.w3); lb[2] = lo(wy.w4);
+                lr[3] = hi(wy.w4); lg[3] = lo(wy.w5); lb[3] = hi(wy.w5);
+            } else if constexpr (FMT == kLINEARF32) {
+                // the values themselves.  The unchecked cube root wants non-negative, finite-sized arguments: the sign bit is
+                // dropped here (keeps every table index in range) and any value that was negative, -0, nan or above 1e30
+                // marks the region for the general path, which has the fully checked routines
+                const uint32_t ww[12] = {wy.w0, wy.w1, wy.w2, wy.w3, wy.w4, wy.w5, wy.w6, wy.w7, wy.w8, wy.w9, wy.w10, wy.w11};
+#pragma unroll
+                for (int i = 0; i < 12; i++) bad = max(bad, ww[i]);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    lr[i] = __uint_as_float(ww[3 * i] & 0x7fffffffu);
+                    lg[i] = __uint_as_float(ww[3 * i + 1] & 0x7fffffffu);
+                    lb[i] = __uint_as_float(ww[3 * i + 2] & 0x7fffffffu);
                 }
             } else {
                 // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
@@ -687,7 +728,7 @@ __device__ __forceinline__ bool frontend_region_fast(const Geo& g, const FrameIn
                 lr[2] = tab(wy.w1, 2); lg[2] = tab(wy.w1, 3); lb[2] = tab(wy.w2, 0);
                 lr[3] = tab(wy.w2, 1); lg[3] = tab(wy.w2, 2); lb[3] = tab(wy.w2, 3);
             }
-            if constexpr (FMT != kSRGB8) {
+            if constexpr (kYuv) {
 #pragma unroll
                 for (int i = 0; i < 4; i++) lg[i] = lds_f32(s_luma + yc[i]) + g_[i >> 1];
                 bt709_eotf_clamped_n<4>(lg, tb.T);
@@ -787,6 +828,7 @@ __device__ __forceinline__ bool frontend_region_fast(const Geo& g, const FrameIn
         q[0] = X; q[plane] = Yv; q[2 * plane] = B;
     }
     if constexpr (FMT == kP016) return !__any_sync(0xffffffffu, (bad & 0x003F003Fu) != 0);
+    if constexpr (FMT == kLINEARF32) return !__any_sync(0xffffffffu, bad > 0x7149f2cau);   // bits of 1e30f; negatives and nan are larger
     return true;
 }
 
@@ -1034,10 +1076,10 @@ __global__ void __launch_bounds__(kF2Threads, KF2_MINB) k_frontend2(const __grid
                     prefetch_region<FMT>(fp.ref, X0 + kF2Region, Y0);
                 }
                 // interior region, aligned rows, (YUV) the exact R / B memo present
-                const uint32_t align = FMT == kP016 ? 7u : 3u;
+                const uint32_t align = FastFmt<FMT>::align;
                 const bool fast = X0 + kF2Region <= g.sc[0].w && Y0 + kF2Region <= g.sc[0].h &&
                                   ((((uintptr_t)f.p0 | (uintptr_t)f.p1 | (uintptr_t)f.pitch) & align) == 0) &&
-                                  (FMT == kSRGB8 || g.eotf_lut != nullptr);
+                                  (!FastFmt<FMT>::needs_lut || g.eotf_lut != nullptr);
                 if (fast) done = frontend_region_fast<FMT>(g, f, xyb_slot, img, X0, Y0, tb, scratch + threadIdx.x, kF2Threads);
             }
             if (!done) frontend_region<FMT>(g, f, xyb_slot, img, X0, Y0, tb.T, tb.S, scratch + threadIdx.x, kF2Threads);
@@ -2240,6 +2282,21 @@ __global__ void k_build_eotf_lut(const YuvCoef k, int n, int shift, float* __res
     const float r_ = k.r * cc, b_ = k.b * cc;
     out[idx] = clamp01(bt709_eotf(luma + r_, T));
     out[(size_t)n * n + idx] = clamp01(bt709_eotf(luma + b_, T));
+}
+
+// Builds the 65536-entry memo of the sRGB16 transfer (Geo::eotf_lut of an SSIMU2_FMT_SRGB16 handle) with the arithmetic path of
+// load_px: same expression, same device routine, so a looked-up value has the bits of the computed one.
+__global__ void k_build_srgb16_lut(float* __restrict__ out)
+{
+    __shared__ exact_math::PowfTables T;
+    {
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(&kPowfTablesInit);
+        uint64_t* dst = reinterpret_cast<uint64_t*>(&T);
+        for (int i = threadIdx.x; i < (int)(sizeof(exact_math::PowfTables) / 8); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < 65536) out[c] = srgb_inverse_oetf<false>((float)c / 65535.0f, T);
 }
 
 // Test hook: the device build of exact_math.cuh over an array.

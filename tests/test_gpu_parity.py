@@ -143,7 +143,7 @@ def test_intermediate_planes_are_bit_identical_srgb8(oracle, w, h):
     _assert_norms(norms, no, score, so)
 
 
-@pytest.mark.parametrize("kind", ["linear", "linear_out_of_range", "linear_huge", "srgb16"])
+@pytest.mark.parametrize("kind", ["linear", "linear_out_of_range", "linear_huge", "srgb16", "srgbf32", "srgbf32_out_of_range"])
 def test_intermediate_planes_are_bit_identical_packed16_and_float(oracle, kind):
     """The fast front-end path of the linear-f32 (the reference's own `Ssimulacra2::new` input, lib.rs:48) and sRGB16 formats:
     interior regions go through it, the frame edge through the general path, and both must give the oracle's bits.  The
@@ -160,6 +160,15 @@ def test_intermediate_planes_are_bit_identical_packed16_and_float(oracle, kind):
         a = oracle.linear_from_srgb16(r.numpy().view(np.uint16))
         b = oracle.linear_from_srgb16(d.numpy().view(np.uint16))
         fmt = tm.PixelFormat.SRGB16
+    elif kind.startswith("srgbf32"):
+        r8, d8 = synth.make_pair_srgb8(w, h, frame=4, seed=6)
+        r, d = r8.to(torch.float32) / 255.0, (d8.to(torch.float32) / 255.0 * 0.97 + 0.013)
+        r[5, 7, :] = 0.0                              # exact zeros and the linear segment of the transfer function
+        d[5, 9, :] = torch.tensor([0.0392, 0.0393, 0.0394])
+        if kind == "srgbf32_out_of_range":             # negative, -0, tiny, above one, huge: the region goes to the checked path
+            r[40, 50, 1] = -0.25; r[70, 10, 2] = -0.0; d[12, 150, 1] = 1.0e-38; d[90, 40, 2] = 1.5; r[100, 100, 0] = 2.0e6
+        a, b = oracle.linear_from_srgbf32(r.numpy()), oracle.linear_from_srgbf32(d.numpy())
+        fmt = tm.PixelFormat.SRGBF32
     else:
         r, d = synth.make_pair_linearf32(w, h, frame=4, seed=6)
         if kind != "linear":
@@ -177,7 +186,7 @@ def test_intermediate_planes_are_bit_identical_packed16_and_float(oracle, kind):
         for s in range(ns):
             assert np.array_equal(_bits(m.debug_read(t, 0, s)), _bits(xyb_o[s])), f"XYB planes differ at scale {s}"
             assert np.array_equal(_bits(m.debug_read(t, 1, s)), _bits(hb_o[s])), f"H-pass planes differ at scale {s}"
-    if kind != "linear_huge":
+    if kind != "linear_huge" and np.all(np.isfinite(a)) and np.all(np.isfinite(b)):
         so, no, _ = oracle.ssimu2_linear_planar(a, b)
         _assert_norms(norms, no, score, so)
 

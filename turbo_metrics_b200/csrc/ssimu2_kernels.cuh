@@ -482,6 +482,24 @@ __device__ __forceinline__ void bt709_eotf_clamped_n(float (&v)[N], const exact_
     }
 }
 
+// srgb_inverse_oetf on N values that are 0 or in [1e-30, 1e6] (checked by the caller), branch-free with the power segments in
+// lock-step: the same quotients (fdiv_normal is the IEEE quotient on normal operands) and the same powf as the checked routine
+template <int N>
+__device__ __forceinline__ void srgb_inverse_oetf_n(float (&v)[N], const exact_math::PowfTables& T)
+{
+    const float SRGB_ALPHA = 1.0550107f;
+    const float SRGB_BETA = 0.0030412825f;
+    float p[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = exact_math::fdiv_normal(v[i] + (SRGB_ALPHA - 1.0f), SRGB_ALPHA);
+    exact_math::powf_glibc_n<N>(p, 2.4f, kEM, T);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const float l = exact_math::fdiv_normal(v[i], 12.92f);
+        v[i] = v[i] < 12.92f * SRGB_BETA ? l : p[i];
+    }
+}
+
 // not inlined: five call sites per row pair; as a function the hot loop is 0.7 k instead of 1.7 k instructions (11 KB instead of
 // 27 KB of code per format), which the instruction cache prefers (NV12 front-end 1.47 -> 1.37 ms per 32 1080p pairs)
 #ifndef XYB_PAIR_INLINE
@@ -539,11 +557,11 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
 
 template <int FMT>
 struct FastFmt {
-    static constexpr bool ok = (FMT == kNV12 || FMT == kP016 || FMT == kSRGB8 || FMT == kSRGB16 || FMT == kLINEARF32);
+    static constexpr bool ok = true;   // every format has the fast schedule (edge regions / odd alignments use the general path)
     static constexpr bool yuv = (FMT == kNV12 || FMT == kP016);
     // bytes per sample of plane 0 (YUV: luma sample; packed formats: pixel), alignment the row loads need (mask)
     static constexpr int bpp = FMT == kP016 ? 2 : (FMT == kNV12 ? 1 : (FMT == kSRGB8 ? 3 : (FMT == kSRGB16 ? 6 : 12)));
-    static constexpr uint32_t align = FMT == kP016 || FMT == kSRGB16 ? 7u : (FMT == kLINEARF32 ? 15u : 3u);
+    static constexpr uint32_t align = FMT == kP016 || FMT == kSRGB16 ? 7u : (FMT == kLINEARF32 || FMT == kSRGBF32 ? 15u : 3u);
     static constexpr bool needs_lut = yuv || FMT == kSRGB16;
 };
 
@@ -562,7 +580,7 @@ __device__ __forceinline__ RowWords load_row_words(const uint8_t* p)
         asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.w0), "=r"(r.w1) : "l"(p));
         asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2+8];" : "=r"(r.w2), "=r"(r.w3) : "l"(p));
         asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2+16];" : "=r"(r.w4), "=r"(r.w5) : "l"(p));
-    } else if constexpr (FMT == kLINEARF32) {
+    } else if constexpr (FMT == kLINEARF32 || FMT == kSRGBF32) {
         asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.w0), "=r"(r.w1), "=r"(r.w2), "=r"(r.w3) : "l"(p));
         asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(r.w4), "=r"(r.w5), "=r"(r.w6), "=r"(r.w7) : "l"(p));
         asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4+32];" : "=r"(r.w8), "=r"(r.w9), "=r"(r.w10), "=r"(r.w11) : "l"(p));
@@ -630,6 +648,7 @@ __device__ __forceinline__ bool frontend_region_fast(const Geo& g, const FrameIn
     const char* lut = reinterpret_cast<const char*>(g.eotf_lut);
     const uint32_t lut_b = (uint32_t)g.lut_n * (uint32_t)g.lut_n * 4u;   // byte offset of the B table
     uint32_t bad = 0;
+    uint32_t tiny = 0xffffffffu;   // sRGB f32: smallest (bits - 1) seen, i.e. the smallest NON-ZERO sample
     float s1[2][3];
     float s2[3] = {0.f, 0.f, 0.f};
     Rgb l2b = Rgb{0.f, 0.f, 0.f};
@@ -720,6 +739,25 @@ __device__ __forceinline__ bool frontend_region_fast(const Geo& g, const FrameIn
                     lg[i] = __uint_as_float(ww[3 * i + 1] & 0x7fffffffu);
                     lb[i] = __uint_as_float(ww[3 * i + 2] & 0x7fffffffu);
                 }
+            } else if constexpr (FMT == kSRGBF32) {
+                // non-linear f32 samples: the checked transfer function of the general path handles anything; here a sample must
+                // be 0 or in [1e-30, 1e6] (normal operands and quotients for the hand-rolled divisions, a normal positive
+                // argument for the unchecked powf) -- otherwise the region is redone by the general path
+                const uint32_t ww[12] = {wy.w0, wy.w1, wy.w2, wy.w3, wy.w4, wy.w5, wy.w6, wy.w7, wy.w8, wy.w9, wy.w10, wy.w11};
+#pragma unroll
+                for (int i = 0; i < 12; i++) {
+                    bad = max(bad, ww[i]);
+                    tiny = min(tiny, ww[i] - 1u);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    lr[i] = __uint_as_float(ww[3 * i] & 0x7fffffffu);
+                    lg[i] = __uint_as_float(ww[3 * i + 1] & 0x7fffffffu);
+                    lb[i] = __uint_as_float(ww[3 * i + 2] & 0x7fffffffu);
+                }
+                srgb_inverse_oetf_n<4>(lr, tb.T);
+                srgb_inverse_oetf_n<4>(lg, tb.T);
+                srgb_inverse_oetf_n<4>(lb, tb.T);
             } else {
                 // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
                 auto tab = [&](uint32_t w, int k) { return lds_f32(s_luma + (k == 0 ? (w << 2) & 0x3FCu : (w >> (8 * k - 2)) & 0x3FCu)); };
@@ -829,6 +867,8 @@ __device__ __forceinline__ bool frontend_region_fast(const Geo& g, const FrameIn
     }
     if constexpr (FMT == kP016) return !__any_sync(0xffffffffu, (bad & 0x003F003Fu) != 0);
     if constexpr (FMT == kLINEARF32) return !__any_sync(0xffffffffu, bad > 0x7149f2cau);   // bits of 1e30f; negatives and nan are larger
+    if constexpr (FMT == kSRGBF32)   // above 1e6f (0x49742400), or non-zero below 1e-30f (0x0da24260)
+        return !__any_sync(0xffffffffu, bad > 0x49742400u || tiny < 0x0da24260u - 1u);
     return true;
 }
 

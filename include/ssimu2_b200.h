@@ -100,6 +100,10 @@ typedef enum {
                                      by 0.0, ssimulacra2-cuda/src/lib.rs:586-603).  Scores are bit-identical to the full mode;    \
                                      ssimu2_get_norms returns SSIMU2_E_UNSUPPORTED. */
 #define SSIMU2_FLAG_NO_TIMING 2u  /* do not record the per-kernel timing events (ssimu2_b200_debug.h) */
+#define SSIMU2_FLAG_P016_DEEP 4u  /* SSIMU2_FMT_P016 only: the samples carry more than 10 significant bits (12-bit sources, e.g. HEVC \
+                                     Main12 through NVDEC).  Results never depend on this flag; it selects a front-end that      \
+                                     evaluates all three transfer functions instead of the exact 10-bit memo tables, which such  \
+                                     content cannot use (without the flag it is scored correctly, at a third of the speed). */
 
 typedef struct {
     uint32_t width, height;

@@ -30,7 +30,7 @@ def test_create_rejects_bad_configurations():
     assert lib.ssimu2_create(None, C.byref(_cfg(L))) == E_INVALID
     assert lib.ssimu2_create(C.byref(h), None) == E_INVALID
     for bad in (dict(width=4), dict(height=7), dict(width=40000), dict(format=6), dict(format=-1), dict(matrix=3), dict(pipeline=2),
-                dict(flags=0x80), dict(flags=1, pipeline=1)):
+                dict(flags=0x80), dict(flags=1, pipeline=1), dict(flags=4)):   # (flags=4: P016_DEEP on a non-P016 format)
         assert lib.ssimu2_create(C.byref(h), C.byref(_cfg(L, **bad))) == E_UNSUPPORTED, bad
         assert not h.value
     c = _cfg(L)

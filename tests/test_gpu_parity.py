@@ -191,6 +191,48 @@ def test_intermediate_planes_are_bit_identical_packed16_and_float(oracle, kind):
         _assert_norms(norms, no, score, so)
 
 
+@pytest.mark.parametrize("content", ["12bit", "random16", "10bit"])
+def test_p016_deep_flag_changes_the_speed_not_the_bits(oracle, content):
+    """SSIMU2_FLAG_P016_DEEP: a front-end for P016 samples with more than 10 significant bits (HEVC Main12 through NVDEC) that
+    evaluates the three transfer functions instead of the 10-bit memo tables.  With or without the flag, and whatever the
+    content, the planes must be the oracle's bits (the oracle applies biplanar.rs:7-70 to the full 16-bit samples)."""
+    tm = _tm()
+    w, h, pitch, ch = 256, 168, 512, 168
+    rng = np.random.default_rng(11)
+
+    def frame():
+        n = pitch // 2 * ch * 3 // 2
+        if content == "random16":
+            v = rng.integers(0, 65536, n, dtype=np.uint16)
+        else:
+            v = rng.integers(0, 1024, n, dtype=np.uint16) << 6
+            if content == "12bit":
+                v |= rng.integers(0, 4, n, dtype=np.uint16) << 4
+        return torch.from_numpy(v.view(np.uint8).copy())
+    r = frame()
+    d = r.clone()
+    d[::5] = frame()[::5]
+    a = oracle.linear_from_yuv420(r.numpy(), pitch, ch, w, h, 16)
+    b = oracle.linear_from_yuv420(d.numpy(), pitch, ch, w, h, 16)
+    F = lambda t: tm.DeviceFrame.yuv420(t, pitch, ch)
+    rg, dg = r.cuda(), d.cuda()
+    got = {}
+    for deep in (False, True):
+        with tm.Ssimulacra2(w, h, tm.PixelFormat.P016, batch=1, ring=1, pipeline="split", p016_deep=deep) as m:
+            t = m.compute(F(rg), F(dg))
+            got[deep] = (m.get_score(t), m.get_norms(t))
+            ns = m.info().nscales
+            xyb_o, _ = _oracle_stages(oracle, a, b, ns)
+            for s in range(ns):
+                assert np.array_equal(_bits(m.debug_read(t, 0, s)), _bits(xyb_o[s])), f"deep={deep}: XYB planes differ at scale {s}"
+    assert got[False][0] == got[True][0] and np.array_equal(got[False][1], got[True][1])
+    so, no, _ = oracle.ssimu2_linear_planar(a, b)
+    _assert_norms(got[True][1], no, got[True][0], so)
+    with pytest.raises(tm.Ssimu2Error) as e:     # the flag belongs to P016
+        tm.Ssimulacra2(w, h, tm.PixelFormat.NV12, p016_deep=True)
+    assert e.value.status == -2
+
+
 @pytest.mark.parametrize("bits", [8, 16])
 def test_intermediate_planes_are_bit_identical_yuv(oracle, bits):
     tm = _tm()

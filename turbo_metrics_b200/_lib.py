@@ -27,7 +27,7 @@ class Config(C.Structure):
 
 
 PIPELINE_DEFAULT, PIPELINE_SPLIT = 0, 1
-FLAG_SCORE_ONLY, FLAG_NO_TIMING = 1, 2
+FLAG_SCORE_ONLY, FLAG_NO_TIMING, FLAG_P016_DEEP = 1, 2, 4
 
 
 class Info(C.Structure):

@@ -288,7 +288,10 @@ static int launch_frontend(ssimu2_handle* h, Slot& sl, uint32_t upto, bool time_
     if (time_it) cudaEventRecord(sl.ev_k[0], sl.stream);
     switch (h->cfg.format) {
     case kNV12: launch_frontend_kernel<kNV12>(h, sl, f0, n); break;
-    case kP016: launch_frontend_kernel<kP016>(h, sl, f0, n); break;
+    case kP016:
+        if (h->cfg.flags & SSIMU2_FLAG_P016_DEEP) launch_frontend_kernel<kP016A>(h, sl, f0, n);
+        else launch_frontend_kernel<kP016>(h, sl, f0, n);
+        break;
     case kSRGB8: launch_frontend_kernel<kSRGB8>(h, sl, f0, n); break;
     case kSRGB16: launch_frontend_kernel<kSRGB16>(h, sl, f0, n); break;
     case kSRGBF32: launch_frontend_kernel<kSRGBF32>(h, sl, f0, n); break;
@@ -501,7 +504,8 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
     if (cfg->format < 0 || cfg->format > kLINEARF32) return SSIMU2_E_UNSUPPORTED;
     if (cfg->matrix < 0 || cfg->matrix > 2) return SSIMU2_E_UNSUPPORTED;
     if (cfg->pipeline > SSIMU2_PIPELINE_SPLIT) return SSIMU2_E_UNSUPPORTED;
-    if (cfg->flags & ~(SSIMU2_FLAG_SCORE_ONLY | SSIMU2_FLAG_NO_TIMING)) return SSIMU2_E_UNSUPPORTED;
+    if (cfg->flags & ~(SSIMU2_FLAG_SCORE_ONLY | SSIMU2_FLAG_NO_TIMING | SSIMU2_FLAG_P016_DEEP)) return SSIMU2_E_UNSUPPORTED;
+    if ((cfg->flags & SSIMU2_FLAG_P016_DEEP) && cfg->format != kP016) return SSIMU2_E_UNSUPPORTED;
     if ((cfg->flags & SSIMU2_FLAG_SCORE_ONLY) && cfg->pipeline != SSIMU2_PIPELINE_DEFAULT) return SSIMU2_E_UNSUPPORTED;
     for (int i = 0; i < 5; i++)
         if (cfg->reserved[i]) return SSIMU2_E_INVALID;
@@ -579,7 +583,7 @@ int ssimu2_create(ssimu2_t** out, const ssimu2_config* cfg)
         for (int i = 0; i < 256; i++) cs.tab[i] = exact_math::cbrt_scale_entry(i);
         CR(cudaMemcpyToSymbol(kCbrtC, &cs, sizeof(cs)));
     }
-    if (cfg->format == kNV12 || cfg->format == kP016) {
+    if ((cfg->format == kNV12 || cfg->format == kP016) && !(cfg->flags & SSIMU2_FLAG_P016_DEEP)) {
         const int n = cfg->format == kNV12 ? 256 : 1024, shift = cfg->format == kNV12 ? 0 : 6;
         const size_t bytes = (size_t)2 * n * n * sizeof(float);
         CR(cudaMalloc(&h->eotf_lut, bytes));

@@ -28,7 +28,15 @@ namespace ssimu2 {
 constexpr int kMaxScales = 6;
 constexpr int kMaxBatch = 1024;   // frame pairs per launch group (the frame table lives in device memory)
 
-enum Fmt : int { kNV12 = 0, kP016 = 1, kSRGB8 = 2, kSRGB16 = 3, kSRGBF32 = 4, kLINEARF32 = 5 };
+enum Fmt : int { kNV12 = 0, kP016 = 1, kSRGB8 = 2, kSRGB16 = 3, kSRGBF32 = 4, kLINEARF32 = 5,
+                 // internal: P016 whose samples carry more than 10 significant bits (SSIMU2_FLAG_P016_DEEP: 12-bit sources).
+                 // Same layout and arithmetic as kP016; no 10-bit memo tables, all three transfer functions are evaluated
+                 kP016A = 6 };
+template <int FMT>
+struct FmtIs {
+    static constexpr bool p016 = FMT == kP016 || FMT == kP016A;
+    static constexpr bool yuv = p016 || FMT == kNV12;
+};
 
 struct ScaleDesc {
     int w, h, pitch;       // pitch in floats (multiple of 32)
@@ -222,7 +230,7 @@ template <int FMT>
 __device__ __forceinline__ void load_px(const FrameIn& f, int x, int y, const YuvCoef& k, const exact_math::PowfTables& T,
                                         const float* __restrict__ lut, int lut_n, int lut_shift, float& r, float& g, float& b)
 {
-    if constexpr (FMT == kNV12 || FMT == kP016) {
+    if constexpr (FmtIs<FMT>::yuv) {
         int Y, cbi, cri;
         if constexpr (FMT == kNV12) {
             Y = __ldg(f.p0 + (size_t)y * f.pitch + x);
@@ -558,11 +566,11 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
 template <int FMT>
 struct FastFmt {
     static constexpr bool ok = true;   // every format has the fast schedule (edge regions / odd alignments use the general path)
-    static constexpr bool yuv = (FMT == kNV12 || FMT == kP016);
+    static constexpr bool yuv = FmtIs<FMT>::yuv;
     // bytes per sample of plane 0 (YUV: luma sample; packed formats: pixel), alignment the row loads need (mask)
-    static constexpr int bpp = FMT == kP016 ? 2 : (FMT == kNV12 ? 1 : (FMT == kSRGB8 ? 3 : (FMT == kSRGB16 ? 6 : 12)));
-    static constexpr uint32_t align = FMT == kP016 || FMT == kSRGB16 ? 7u : (FMT == kLINEARF32 || FMT == kSRGBF32 ? 15u : 3u);
-    static constexpr bool needs_lut = yuv || FMT == kSRGB16;
+    static constexpr int bpp = FmtIs<FMT>::p016 ? 2 : (FMT == kNV12 ? 1 : (FMT == kSRGB8 ? 3 : (FMT == kSRGB16 ? 6 : 12)));
+    static constexpr uint32_t align = FmtIs<FMT>::p016 || FMT == kSRGB16 ? 7u : (FMT == kLINEARF32 || FMT == kSRGBF32 ? 15u : 3u);
+    static constexpr bool needs_lut = FMT == kNV12 || FMT == kP016 || FMT == kSRGB16;
 };
 
 // the raw words of one row of four pixels (P016: 2 words, NV12: 1, sRGB8: 3) / of the two chroma samples under them
@@ -584,7 +592,7 @@ __device__ __forceinline__ RowWords load_row_words(const uint8_t* p)
         asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.w0), "=r"(r.w1), "=r"(r.w2), "=r"(r.w3) : "l"(p));
         asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(r.w4), "=r"(r.w5), "=r"(r.w6), "=r"(r.w7) : "l"(p));
         asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4+32];" : "=r"(r.w8), "=r"(r.w9), "=r"(r.w10), "=r"(r.w11) : "l"(p));
-    } else if constexpr (FMT == kP016) {
+    } else if constexpr (FmtIs<FMT>::p016) {
         asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.w0), "=r"(r.w1) : "l"(p));
     } else if constexpr (FMT == kNV12) {
         asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r.w0) : "l"(p));
@@ -668,8 +676,18 @@ __device__ __forceinline__ bool frontend_region_fast(const Geo& g, const FrameIn
         oY += f.pitch;
         // ---- chroma of the row pair: two samples, each shared by a 2x2 block
         float g_[2] = {0.f, 0.f};
+        float r_[2] = {0.f, 0.f}, b_[2] = {0.f, 0.f};   // kP016A: the chroma terms of R' and B' (yuv_chroma)
         uint32_t roff[2] = {0, 0}, boff[2] = {0, 0};
-        if constexpr (FMT == kP016) {
+        if constexpr (FMT == kP016A) {
+            const uint32_t w[2] = {wc.w0, wc.w1};
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const float cb = (float)((int)(w[j] & 0xFFFFu) - g.coef.neutral), cr = (float)((int)(w[j] >> 16) - g.coef.neutral);
+                g_[j] = fmaf(g.coef.g1, cb, g.coef.g2 * cr);
+                r_[j] = g.coef.r * cr;
+                b_[j] = g.coef.b * cb;
+            }
+        } else if constexpr (FMT == kP016) {
             bad |= wc.w0 | wc.w1;
             const uint32_t w[2] = {wc.w0, wc.w1};
 #pragma unroll
@@ -710,7 +728,21 @@ __device__ __forceinline__ bool frontend_region_fast(const Geo& g, const FrameIn
             } else if constexpr (FMT == kNV12) {
                 yc[0] = (wy.w0 << 2) & 0x3FCu; yc[1] = (wy.w0 >> 6) & 0x3FCu; yc[2] = (wy.w0 >> 14) & 0x3FCu; yc[3] = (wy.w0 >> 22) & 0x3FCu;
             }
-            if constexpr (kYuv) {
+            if constexpr (FMT == kP016A) {
+                // the same expressions as yuv_px on the full 16-bit samples; three transfer functions per pixel, as three
+                // lock-step groups of four
+                const int Ys[4] = {(int)(wy.w0 & 0xFFFFu), (int)(wy.w0 >> 16), (int)(wy.w1 & 0xFFFFu), (int)(wy.w1 >> 16)};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float luma = (float)(max(Ys[i], g.coef.luma_min) - g.coef.luma_min) * g.coef.y;
+                    lr[i] = luma + r_[i >> 1];
+                    lg[i] = luma + g_[i >> 1];
+                    lb[i] = luma + b_[i >> 1];
+                }
+                bt709_eotf_clamped_n<4>(lr, tb.T);
+                bt709_eotf_clamped_n<4>(lg, tb.T);
+                bt709_eotf_clamped_n<4>(lb, tb.T);
+            } else if constexpr (kYuv) {
                 // the exact R / B memo: all eight gathers of the row are issued before the first transfer-function chain
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
@@ -766,7 +798,7 @@ __device__ __forceinline__ bool frontend_region_fast(const Geo& g, const FrameIn
                 lr[2] = tab(wy.w1, 2); lg[2] = tab(wy.w1, 3); lb[2] = tab(wy.w2, 0);
                 lr[3] = tab(wy.w2, 1); lg[3] = tab(wy.w2, 2); lb[3] = tab(wy.w2, 3);
             }
-            if constexpr (kYuv) {
+            if constexpr (kYuv && FMT != kP016A) {
 #pragma unroll
                 for (int i = 0; i < 4; i++) lg[i] = lds_f32(s_luma + yc[i]) + g_[i >> 1];
                 bt709_eotf_clamped_n<4>(lg, tb.T);
@@ -893,7 +925,7 @@ __device__ __forceinline__ void frontend_region(const Geo& g, const FrameIn& f, 
     const int W0 = g.sc[0].w, H0 = g.sc[0].h;
     auto plane_of = [&](int s) { return (size_t)g.sc[s].h * g.sc[s].pitch; };
     auto base_of = [&](int s) { return ximg + g.sc[s].xyb_off + (size_t)img * 3 * plane_of(s); };
-    const bool vec_ok = (FMT == kNV12 || FMT == kP016) &&
+    const bool vec_ok = FmtIs<FMT>::yuv &&
                         ((((uintptr_t)f.p0 | (uintptr_t)f.p1 | (uintptr_t)f.pitch) & 3u) == 0);
     Rgb l3b = Rgb{0.f, 0.f, 0.f}, l4b = l3b;   // level 3 / 4 pixels of pass 1 (pass 0's are parked in slots 3, 4)
     park(3, l3b);
@@ -912,11 +944,11 @@ __device__ __forceinline__ void frontend_region(const Geo& g, const FrameIn& f, 
             const int x = px0 + 2 * (blk & 1), y = py0 + (blk & 2);
             Rgb lin[2][2];
             bool done = false;
-            if constexpr (FMT == kNV12 || FMT == kP016) {
+            if constexpr (FmtIs<FMT>::yuv) {
                 if (vec_ok && x + 2 <= W0 && y + 2 <= H0) {
                     // interior block: two luma samples per row in one load, one chroma pair for all four pixels
                     int Y00, Y01, Y10, Y11, cbi, cri;
-                    if constexpr (FMT == kP016) {
+                    if constexpr (FmtIs<FMT>::p016) {
                         const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(f.p0 + (size_t)y * f.pitch + 2 * x));
                         const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(f.p0 + (size_t)(y + 1) * f.pitch + 2 * x));
                         const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(f.p1 + (size_t)(y >> 1) * f.pitch + 2 * x));
@@ -938,7 +970,7 @@ __device__ __forceinline__ void frontend_region(const Geo& g, const FrameIn& f, 
             if (!done) {
                 // generic path: per-pixel loads at clamped coordinates (edge blocks, packed RGB formats); rolled for the
                 // YUV formats, where it only serves the frame edges
-#pragma unroll(FMT == kNV12 || FMT == kP016 ? 1 : 4)
+#pragma unroll(FmtIs<FMT>::yuv ? 1 : 4)
                 for (int p = 0; p < 4; p++) {
                     Rgb o;
                     load_px<FMT>(f, min(x + (p & 1), W0 - 1), min(y + (p >> 1), H0 - 1), g.coef, T, g.eotf_lut, g.lut_n, g.lut_shift, o.r,

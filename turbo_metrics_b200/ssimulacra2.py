@@ -92,15 +92,18 @@ class Ssimulacra2:
     def __init__(self, width: int, height: int, fmt: PixelFormat = PixelFormat.LINEARF32,
                  matrix: ColorMatrix = ColorMatrix.BT709, full_range: bool = False, device: int = 0,
                  batch: int = 0, ring: int = 0, pipeline: Optional[str] = None, score_only: bool = False,
-                 input_group: int = 0, timing: bool = True):
+                 input_group: int = 0, timing: bool = True, p016_deep: bool = False):
         """pipeline: None / "hv" = the product pipeline (front-end, fused H+V kernel, finalize); "split" = development
         pipeline with the H-pass planes in HBM (debug_read(what=1)).
         score_only: SSIMU2_FLAG_SCORE_ONLY -- skip the work whose weights are zero (scores identical, no norms).
-        input_group: pairs per front-end launch (0 = whole batch): input frames are consumed sooner, see wait_input()."""
+        input_group: pairs per front-end launch (0 = whole batch): input frames are consumed sooner, see wait_input().
+        p016_deep: SSIMU2_FLAG_P016_DEEP -- P016 samples with more than 10 significant bits (12-bit sources): same results,
+        a front-end without the 10-bit memo tables."""
         self._h = C.c_void_p()
         if pipeline not in (None, "hv", "split"):
             raise ValueError(f"unknown pipeline {pipeline!r}")
-        flags = (_lib.FLAG_SCORE_ONLY if score_only else 0) | (0 if timing else _lib.FLAG_NO_TIMING)
+        flags = (_lib.FLAG_SCORE_ONLY if score_only else 0) | (0 if timing else _lib.FLAG_NO_TIMING) | \
+                (_lib.FLAG_P016_DEEP if p016_deep else 0)
         cfg = make_config(width, height, fmt, matrix, full_range, device, batch, ring,
                           _lib.PIPELINE_SPLIT if pipeline == "split" else _lib.PIPELINE_DEFAULT, flags, input_group)
         check(_lib.lib().ssimu2_create(C.byref(self._h), C.byref(cfg)), "ssimu2_create")

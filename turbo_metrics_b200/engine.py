@@ -101,8 +101,15 @@ class TurboMetrics:
     """`TurboMetrics::new(width, height, &Metrics)` (lib.rs:201-251) for metrics = {ssimulacra2}."""
 
     def __init__(self, width: int, height: int, fmt: PixelFormat, matrix: ColorMatrix = ColorMatrix.BT709,
-                 full_range: bool = False, device: int = 0, batch: int = 0, ring: int = 0):
-        self.ssimulacra2 = Ssimulacra2(width, height, fmt, matrix, full_range, device, batch, ring)
+                 full_range: bool = False, device: int = 0, batch: int = 0, ring: int = 0, score_only: bool = True,
+                 bit_depth: Optional[int] = None):
+        """score_only: the engine only ever hands out scores (`FrameScores`), so it asks the scorer for nothing else
+        (SSIMU2_FLAG_SCORE_ONLY: same score bits, ~8 % faster).  bit_depth: of the decoded stream (the reference reads it from the
+        stream's colour info, turbo-metrics/src/lib.rs:185-199); P016 frames of a stream deeper than 10 bits select the
+        front-end without the 10-bit memo tables (SSIMU2_FLAG_P016_DEEP)."""
+        deep = fmt == PixelFormat.P016 and bit_depth is not None and bit_depth > 10
+        self.ssimulacra2 = Ssimulacra2(width, height, fmt, matrix, full_range, device, batch, ring, score_only=score_only,
+                                       p016_deep=deep)
         info = self.ssimulacra2.info()
         self.window = info.batch * info.ring
 
@@ -154,7 +161,7 @@ class ShardedTurboMetrics:
     HOST frames (decoded / loaded on the CPU: turbo-metrics/src/input_image.rs:206-228 copies each frame itself)."""
 
     def __init__(self, width: int, height: int, fmt: PixelFormat, devices: Sequence[int], matrix: ColorMatrix = ColorMatrix.BT709,
-                 full_range: bool = False, batch: int = 0, ring: int = 0, score_only: bool = False):
+                 full_range: bool = False, batch: int = 0, ring: int = 0, score_only: bool = True):
         self.sharded = ShardedSsimulacra2(width, height, fmt, devices, matrix, full_range, batch, ring, score_only)
         self.chunk = max(1, (batch or 8) * len(devices))
         self.window = self.chunk * max(2, ring or 3)

@@ -752,6 +752,37 @@ def test_score_only_strip_handoff_under_load():
         assert s[i] == full[i % nd], (i, s[i], full[i % nd])
 
 
+def test_geometry_sweep_against_the_oracle(oracle):
+    """Frame sizes on and around every tiling boundary of the pipeline (32-pixel front-end regions, 64-column strips, 12-row
+    bands, the 8x8 stop of the pyramid, odd sizes at every scale), sRGB8 and NV12, default pipeline, against the oracle."""
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    ws = [8, 9, 31, 32, 33, 63, 64, 65, 96, 127, 128, 129, 191, 193, 257]
+    hs = [8, 9, 11, 12, 13, 20, 23, 24, 25, 31, 33, 36, 47, 49, 64, 71, 73]
+    rng = np.random.default_rng(2)
+    combos = [(int(rng.choice(ws)), int(rng.choice(hs))) for _ in range(40)] + [(64, 12), (65, 13), (63, 11), (128, 24), (129, 25),
+                                                                                  (32, 32), (33, 33), (257, 73), (8, 8), (9, 9)]
+    worst = 0.0
+    for i, (w, h) in enumerate(combos):
+        if i % 3 == 2 and w >= 16 and h >= 16:
+            w2, h2 = w & ~1, h & ~1                      # 4:2:0 frames have even sizes
+            rb, db, pitch, ch = synth.make_pair_yuv420(w2, h2, 8, frame=i, seed=21)
+            so, no, nso = oracle.ssimu2_yuv420(rb.numpy(), db.numpy(), pitch, ch, w2, h2, 8)
+            fmt, mk, r, d, ww, hh = tm.PixelFormat.NV12, (lambda t, p=pitch, c=ch: tm.DeviceFrame.yuv420(t, p, c)), rb, db, w2, h2
+        else:
+            r, d = synth.make_pair_srgb8(w, h, frame=i, seed=21)
+            so, no, nso = oracle.ssimu2_srgb8(r.numpy(), d.numpy())
+            fmt, mk, ww, hh = tm.PixelFormat.SRGB8, tm.DeviceFrame.packed, w, h
+        with tm.Ssimulacra2(ww, hh, fmt, batch=2, ring=1) as m:
+            rg, dg = r.cuda(), d.cuda()
+            ts = m.compute_batch([mk(rg)] * 3, [mk(dg)] * 3)
+            sc = m.get_scores(ts)
+            assert m.info().nscales == nso, (ww, hh)
+            assert sc[0] == sc[1] == sc[2], (ww, hh)
+            worst = max(worst, _assert_norms(m.get_norms(ts[0]), no, sc[0], so))
+    assert worst <= NORM_RTOL
+
+
 def test_small_frames_follow_the_cpu_reference_scale_rule(oracle):
     """with min(width, height) < 113 the pyramid stops early (cpu.rs:359 tests the size BEFORE each downscale) and the
     108 weights are consumed densely over the scales that exist (cpu.rs:842-854).  The reference's GPU op always runs six

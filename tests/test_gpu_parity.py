@@ -783,6 +783,35 @@ def test_geometry_sweep_against_the_oracle(oracle):
     assert worst <= NORM_RTOL
 
 
+def test_fast_lite_strips_with_many_waves_do_not_deadlock():
+    """Regression (found by tools/soak.py).  An H warp of k_hv only OBSERVES the XYB tile barrier of the bands of the other
+    parity; it did not take part in handing the tile slot back, so in a fast strip (score-only mode, small frames, several
+    waves of work items) the tile of band j + 3 could land while it was still suspended in its wait for band j: its parity
+    wait then never completed and the strip chain ran into the watchdog trap (about one launch in a few hundred).  Every H
+    warp now arrives on the slot's free barrier.  256x254 NV12, batch 64, random batch fills and interleaved fetches."""
+    import random
+    tm = _tm()
+    from turbo_metrics_b200 import synth
+    w, h = 256, 254
+    fr = [synth.make_pair_yuv420(w, h, 8, frame=i, seed=4493, device="cuda") for i in range(3)]
+    pitch, ch = fr[0][2], fr[0][3]
+    F = lambda t: tm.DeviceFrame.yuv420(t, pitch, ch)
+    with tm.Ssimulacra2(w, h, tm.PixelFormat.NV12, batch=1, ring=1) as m:
+        want = [m.compute_sync(F(a), F(b)) for a, b, _, _ in fr]
+    for rep in range(250):
+        rnd = random.Random(rep)
+        n = rnd.randint(64, 12 * 64)
+        with tm.Ssimulacra2(w, h, tm.PixelFormat.NV12, batch=64, ring=1 + rep % 3, score_only=True, input_group=(0, 3)[rep & 1]) as m:
+            ts, got = [], {}
+            for i in range(n):
+                ts.append(m.compute(F(fr[i % 3][0]), F(fr[i % 3][1])))
+                if rnd.random() < 0.1:
+                    j = rnd.randrange(len(ts))
+                    got[j] = m.get_score(ts[j])
+            sc = m.get_scores(range(ts[0], ts[-1] + 1))
+        assert all(sc[j] == want[j % 3] for j in range(n)) and all(v == want[j % 3] for j, v in got.items()), rep
+
+
 def test_small_frames_follow_the_cpu_reference_scale_rule(oracle):
     """with min(width, height) < 113 the pyramid stops early (cpu.rs:359 tests the size BEFORE each downscale) and the
     108 weights are consumed densely over the scales that exist (cpu.rs:842-854).  The reference's GPU op always runs six

@@ -1872,7 +1872,7 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
     const uint32_t sbase = smem_u32(xs);
     uint64_t* bars = reinterpret_cast<uint64_t*>(xs + kXOffBars);
     uint64_t* in_full = bars;        // [3] TMA
-    uint64_t* in_free = bars + 3;    // [3] 3 Vb warps
+    uint64_t* in_free = bars + 3;    // [3] 3 Vb warps + every H warp (6, lite strips 4)
     uint64_t* hb_full = bars + 6;    // [3] 3 H warps
     uint64_t* hb_free = bars + 9;    // [3] 3 Va + 3 Vb warps
     uint64_t* hs_ready = bars + 12;  // [2] P_state: the left strip has published the state record of band j (slot j & 1)
@@ -1892,7 +1892,10 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
         // arrivals per phase: the H warps that write a tile (one per channel / per set), the V warps that read it
         for (int i = 0; i < 3; i++) {
             mbar_init(&in_full[i], 1);
-            mbar_init(&in_free[i], 3);
+            // a tile slot is handed back by the three Vb warps AND by every H warp that waits on in_full: a parity wait is only
+            // sound if no waiter can fall a whole ring cycle behind, and an H warp is a mere observer of the bands of the other
+            // parity (see the H loop) -- without its arrival here the tile of band j + 3 could land before it has seen band j
+            mbar_init(&in_free[i], lt ? 3 + 4 : 3 + 6);
             mbar_init(&hb_full[i], lt ? 2 : 3);
             mbar_init(&hb_free[i], lt ? 4 : 6);
         }
@@ -2030,6 +2033,11 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
                 }
             }
             if (!mine) {
+                // observed, not consumed: hand the slot back at once (found by tools/soak.py: in a fast lite strip the tile of
+                // band j + 3 could land while this warp was still suspended in the wait for band j; its parity wait then saw
+                // "not complete" for ever and the strip chain dead-locked)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&in_free[sin]);
                 if (j >= 2) mbar_wait_wd(&hb_free[si], (uint32_t)(((j - 2) / 3) & 1));
                 continue;
             }
@@ -2092,6 +2100,7 @@ __global__ void __maxnreg__(kXMaxNReg) k_hv(const __grid_constant__ Geo g, const
             __syncwarp();
             KX_TR(3);
             if (lane == 0) {
+                mbar_arrive(&in_free[sin]);    // this warp's last read of the XYB tile was in the scan
                 mbar_arrive(&hb_full[si]);
                 if (!last_strip) {
                     // progress words of the publisher: one per channel; HB stands for X and B

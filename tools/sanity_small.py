@@ -24,7 +24,6 @@ for (w, h, kind) in [(203, 131, "srgb8"), (320, 180, "nv12"), (130, 70, "p016"),
             r[3, 5, 1] = -1.0   # one region through the fall-back
     else:
         bits = 8 if kind == "nv12" else 16
-        kind_deep = deep
         r, d, pitch, ch = synth.make_pair_yuv420(w, h, bits, frame=1, seed=3)
         mk = lambda t: tm.DeviceFrame.yuv420(t, pitch, ch)
         fmt = tm.PixelFormat.NV12 if bits == 8 else tm.PixelFormat.P016

@@ -11,6 +11,8 @@ T = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 rnd = random.Random(7)
 P = tm.PixelFormat
 sizes = [(3840, 2160), (1920, 1080), (1280, 720), (512, 512), (640, 360), (257, 255), (2560, 1440), (720, 480)]
+if os.environ.get("SOAK_BIG"):      # only the large geometries (many strips x many bands per chain)
+    sizes = [(3840, 2160), (1920, 1080), (2560, 1440)]
 t0 = time.time(); runs = 0; pairs = 0
 while time.time() - t0 < T:
     w, h = rnd.choice(sizes)

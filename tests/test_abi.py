@@ -105,3 +105,17 @@ def test_plain_c_client_links_and_fails_loudly_without_a_gpu(tmp_path):
     z.write_bytes(bytes(64 * 64 * 3))
     r = subprocess.run([exe, "64", "64", str(z), str(z)], capture_output=True, text=True)
     assert r.returncode == 1 and "no usable CUDA device" in r.stderr and r.stdout == ""
+
+
+def test_flag_and_status_constants_match_the_header():
+    """The Python loader's constants are the header's (a binding written from include/ssimu2_b200.h must agree with ours)."""
+    import re
+    from turbo_metrics_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "ssimu2_b200.h")).read()
+    flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+SSIMU2_FLAG_(\w+)\s+(\d+)u", hdr)}
+    assert flags == {"SCORE_ONLY": _lib.FLAG_SCORE_ONLY, "NO_TIMING": _lib.FLAG_NO_TIMING, "P016_DEEP": _lib.FLAG_P016_DEEP}
+    status = {m.group(1): int(m.group(2)) for m in re.finditer(r"SSIMU2_E_(\w+)\s*=\s*(-\d+)", hdr)}
+    assert status == {"INVALID": -1, "UNSUPPORTED": -2, "NOMEM": -3, "NODEVICE": -4, "TICKET": -5, "INTERNAL": -6}
+    fmts = {m.group(1): int(m.group(2)) for m in re.finditer(r"SSIMU2_FMT_(\w+)\s*=\s*(\d+)", hdr)}
+    from turbo_metrics_b200 import PixelFormat
+    assert fmts == {f.name: int(f.value) for f in PixelFormat}
